@@ -1,0 +1,175 @@
+/*
+ * mrc_b200.h -- C ABI of libmrc_b200.so: the B200 (sm_100a) implementation of the
+ * parametric negative-cycle hot path of DiogoRibeiro7/min_ratio_cycle.
+ *
+ * The reference has no FFI: its "plugin boundary" for this path is the set of private
+ * methods that MinRatioCycleSolver.solve() calls (min_ratio_cycle/solver.py).  Every entry
+ * point below names the reference method it replaces (file:line).  The reference-side
+ * binding a maintainer would add is a ctypes stub; see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status
+ * (MRC_OK == 0), never throws; mrc_last_error() gives the message for the calling thread.
+ * Host pointers unless a name starts with d_.  Edge arrays handed to mrc_graph_create are
+ * ALREADY destination-sorted in the reference's stable order (solver.py:476-478), so an
+ * edge index here is the reference's index into _U/_V/_C/_T.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * MRC_ERR_NO_DEVICE.
+ */
+#ifndef MRC_B200_H
+#define MRC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRC_ABI_VERSION 1
+#define MRC_KMAX 8 /* candidate lambdas evaluated by one relaxation launch */
+
+/* status codes */
+#define MRC_OK 0
+#define MRC_ERR_CUDA 1
+#define MRC_ERR_ARG 2
+#define MRC_ERR_NO_DEVICE 3
+#define MRC_ERR_OVERFLOW 4     /* int64 q*cost - p*time (or its n-fold sum) would wrap; reference wraps silently (solver.py:799-809) */
+#define MRC_ERR_NO_CYCLE 5     /* NumericalInstabilityError("No negative cycle found"), solver.py:1087-1090 */
+#define MRC_ERR_CONVERGENCE 6  /* ConvergenceError, solver.py:1102-1109 */
+#define MRC_ERR_LOWER_NEG 7    /* RuntimeError("Lower bound has negative cycle"), solver.py:759-760 */
+#define MRC_ERR_UPPER_NONNEG 8 /* RuntimeError("Upper bound has no negative cycle"), solver.py:761-762 */
+#define MRC_ERR_SB_STEPS 9     /* RuntimeError("Stern-Brocot search did not converge"), solver.py:797 */
+#define MRC_ERR_NOT_INTEGER 10 /* "Exact mode requires integer weights", solver.py:689-697 */
+#define MRC_ERR_TIMEOUT 11     /* TimeoutError, solver.py:1032-1041 */
+#define MRC_ERR_EDGE_MISSING 12
+
+/* per-candidate verdicts of a probe */
+#define MRC_V_NONNEG 0         /* relaxation reached a fixed point: no negative cycle at this lambda */
+#define MRC_V_NEG 1            /* a cycle of the predecessor graph was extracted and verified negative */
+#define MRC_V_NEG_NOCYCLE 2    /* still relaxing after n passes (reference: has_neg=True, cycle_data=None) */
+#define MRC_V_TIE 3            /* extracted cycle has ratio >= lambda within rounding: lambda ~ ratio of that cycle */
+#define MRC_V_SKIPPED_NEG 4    /* not evaluated to the end: a smaller lambda of the batch was already negative */
+#define MRC_V_SKIPPED_NONNEG 5 /* not evaluated to the end: a larger lambda of the batch already had no negative cycle */
+
+/* probe flags */
+#define MRC_F_MONOTONE_PRUNE 1u /* stop candidates whose verdict is implied by monotonicity in lambda */
+
+typedef struct mrc_graph mrc_graph;
+
+typedef struct mrc_stats {
+    int64_t relax_launches;       /* relaxation kernel launches */
+    int64_t relax_edge_visits;    /* sum over launches of m * (active candidates) = edge relaxations */
+    int64_t check_launches;       /* predecessor-graph cycle checks */
+    int64_t probes;               /* candidate lambdas evaluated */
+    int64_t rounds;               /* outer search rounds */
+    int64_t other_launches;       /* init / tight-mask / gather / bounds kernels */
+    double relax_ms;              /* CUDA-event time spent in relaxation launches */
+    double check_ms;              /* CUDA-event time spent in cycle checks */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} mrc_stats;
+
+int mrc_abi_version(void);
+const char *mrc_last_error(void);
+int mrc_device_count(int *count);
+
+/* ---- device-resident graph -------------------------------------------------------------
+ * Replaces the array build + implicit "upload" of _build_arrays_if_needed (solver.py:450-511).
+ * src/dst: int32[m], dst non-decreasing.  cost/time: f64[m].  icost/itime: int64[m] or both NULL
+ * (graph not all-integer, solver.py:491-498).  The library copies everything to `device`.
+ */
+int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const int32_t *dst, const double *cost,
+                     const double *time, const int64_t *icost, const int64_t *itime, int device,
+                     mrc_graph **out);
+int mrc_graph_destroy(mrc_graph *g);
+int mrc_graph_info(const mrc_graph *g, int64_t *n, int64_t *m, int *device, int *has_int);
+/* min/max of cost/time over edges -/+ 1.0: the default bracket of _solve_numeric (solver.py:1019-1023) */
+int mrc_numeric_bounds(mrc_graph *g, double *lo, double *hi);
+int mrc_get_stats(const mrc_graph *g, mrc_stats *out);
+int mrc_reset_stats(mrc_graph *g);
+
+/* Perturb edges in place on the device: replaces the per-scenario Edge replacement + array rebuild of
+ * sensitivity_analysis (solver.py:1716-1722).  idx are dst-sorted edge indices; deltas are added to the
+ * f64 weights.  mrc_graph_restore undoes all outstanding patches (solver.py:1726-1727). */
+int mrc_graph_patch_edges(mrc_graph *g, int64_t k, const int64_t *idx, const double *dcost, const double *dtime);
+int mrc_graph_restore(mrc_graph *g);
+
+/* ---- numeric probes -----------------------------------------------------------------------
+ * K candidate lambdas in ONE batched Bellman-Ford (1 <= K <= MRC_KMAX).  K = 1 is the GPU analogue
+ * of _detect_negative_cycle_numeric(lam, slack) (solver.py:1124-1294): same arithmetic per edge
+ * (w = cost - lam*time rounded twice, cand = dist[src] + w, strict < with absolute slack), but
+ * asynchronous relaxation and early exit as soon as a verified negative cycle closes in the
+ * predecessor graph, instead of n passes.
+ * Outputs (arrays of K): verdict; cyc_len (0 if none); cycles as CLOSED vertex lists, candidate k at
+ * cyc_buf[k*cyc_cap .. ), starting at the smallest vertex of the cycle, truncated to cyc_cap entries;
+ * sum_cost/sum_time accumulated in that forward order over the edges Bellman-Ford actually used;
+ * passes run for that candidate.  Any output pointer may be NULL.
+ */
+int mrc_probe_numeric(mrc_graph *g, const double *lam, int K, double slack, uint32_t flags, int32_t *verdict,
+                      int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap, double *sum_cost, double *sum_time,
+                      int64_t *passes);
+
+/* ---- numeric lambda search -----------------------------------------------------------------
+ * Replaces the bisection of _solve_numeric (solver.py:1017-1117) by K-way multisection: every round
+ * evaluates K lambdas of the bracket in one batched probe; a verified negative cycle tightens the upper
+ * end to that cycle's own ratio, the largest lambda without negative cycle becomes the lower end; stops
+ * when hi - lo <= tol (same absolute test as solver.py:1075).  K = 1 degenerates to bisection with the
+ * same midpoints as the reference until the first cycle is found.
+ * Returns MRC_ERR_NO_CYCLE / MRC_ERR_CONVERGENCE / MRC_ERR_TIMEOUT like the reference raises.
+ * cycle: CLOSED vertex list (cap entries), max_seconds <= 0 = no limit (solver.py:1032-1041).
+ */
+int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int max_iter, double tol, double slack, int K,
+                      double max_seconds, double *ratio, double *sum_cost, double *sum_time, int32_t *cycle,
+                      int64_t cycle_cap, int64_t *cycle_len, int32_t *iterations, double *final_lo,
+                      double *final_hi);
+
+/* Pure host helpers shared by mrc_solve_numeric and the multi-GPU driver (one process per GPU, the
+ * candidates of a round split across ranks, verdicts all-gathered): no device work.
+ * plan: writes K_total candidates in increasing order for the bracket [lo, hi]; have_cycle says whether
+ *       hi is the ratio of a known cycle (then the last candidate is the certifier hi - min(tol/2, gap/(2K))).
+ * reduce: folds K_total (lambda, verdict, ratio-of-extracted-cycle) records into the new bracket; returns
+ *       in *best_idx the record whose cycle is the new best (or -1). */
+int mrc_plan_candidates(double lo, double hi, int have_cycle, double tol, int K_total, double *lam_out);
+int mrc_reduce_round(int K_total, const double *lam, const int32_t *verdict, const double *cyc_ratio, double *lo,
+                     double *hi, int *have_cycle, int *best_idx);
+
+/* ---- exact (int64) probes ---------------------------------------------------------------------
+ * lambda_k = a[k]/b[k], b > 0; weights w = b*icost - a*itime in int64 (solver.py:799-809), guarded
+ * against overflow (MRC_ERR_OVERFLOW) where the reference would wrap.  Verdicts as above (no TIE:
+ * integer arithmetic is exact).  K = 1 replaces _has_negative_cycle_exact (solver.py:811-856).
+ * sum_cost/sum_time: exact int64 sums over the extracted negative cycle.
+ */
+int mrc_probe_exact(mrc_graph *g, const int64_t *a, const int64_t *b, int K, uint32_t flags, int32_t *verdict,
+                    int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap, int64_t *sum_cost, int64_t *sum_time,
+                    int64_t *passes);
+
+/* _compute_potentials_exact (solver.py:922-969): ok = 1 and dist[n] = fixed point of the relaxation from
+ * dist == 0 when there is no negative cycle at a/b; ok = 0 otherwise (dist undefined). */
+int mrc_potentials_exact(mrc_graph *g, int64_t a, int64_t b, uint8_t *ok, int64_t *dist);
+
+/* (dist[U] + W) == dist[V] of _find_zero_cycle_exact (solver.py:878-879), one byte per edge */
+int mrc_tight_mask_exact(mrc_graph *g, int64_t a, int64_t b, uint8_t *ok, uint8_t *mask);
+
+/* _find_zero_cycle_exact (solver.py:858-920) incl. _compute_cycle_weights_exact (:971-995):
+ * found = 0 -> None.  cycle is the OPEN list the reference's DFS returns (same order). */
+int mrc_zero_cycle_exact(mrc_graph *g, int64_t a, int64_t b, uint8_t *found, int32_t *cycle, int64_t cycle_cap,
+                         int64_t *cycle_len, int64_t *sum_cost, int64_t *sum_time);
+
+/* _stern_brocot_search (solver.py:734-797).  max_den / max_steps < 0 = None (defaults :746-751).
+ * strategy 0: every Stern-Brocot step probes the GPU (same (a,b) sequence as the reference).
+ * strategy 1: lambda* is first found by exact Newton steps on cycle ratios (int64 probes), then the
+ *             reference's Stern-Brocot trajectory is replayed on the host with verdicts decided by exact
+ *             comparison with lambda*; identical outputs, far fewer probes.
+ * a_out/b_out: reduced fraction; iterations: Stern-Brocot steps as the reference counts them (-1 on the
+ * path where the reference does not record them, :772-776); probes_ab (2*probes_cap int64, may be NULL)
+ * receives the (a,b) sequence the reference would hand to _has_negative_cycle_exact.
+ */
+int mrc_solve_exact(mrc_graph *g, int64_t max_den, int64_t max_steps, int strategy, int32_t *cycle,
+                    int64_t cycle_cap, int64_t *cycle_len, int64_t *sum_cost, int64_t *sum_time, int64_t *a_out,
+                    int64_t *b_out, int64_t *iterations, int64_t *probes_ab, int64_t probes_cap,
+                    int64_t *nprobes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRC_B200_H */

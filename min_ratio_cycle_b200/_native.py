@@ -1,0 +1,289 @@
+"""
+ctypes binding of libmrc_b200.so (C ABI: include/mrc_b200.h).
+
+There is NO fallback: if the shared library is missing or no CUDA device is present the calls raise
+`NativeError` -- the product never routes through a CPU implementation.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmrc_b200.so")
+
+KMAX = 8
+
+OK, ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_OVERFLOW, ERR_NO_CYCLE, ERR_CONVERGENCE = range(7)
+ERR_LOWER_NEG, ERR_UPPER_NONNEG, ERR_SB_STEPS, ERR_NOT_INTEGER, ERR_TIMEOUT, ERR_EDGE_MISSING = range(7, 13)
+
+V_NONNEG, V_NEG, V_NEG_NOCYCLE, V_TIE, V_SKIPPED_NEG, V_SKIPPED_NONNEG = range(6)
+F_MONOTONE_PRUNE = 1
+
+EXPORTS = [
+    "mrc_abi_version", "mrc_last_error", "mrc_device_count", "mrc_graph_create", "mrc_graph_destroy",
+    "mrc_graph_info", "mrc_numeric_bounds", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
+    "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
+    "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
+]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libmrc_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("relax_launches", C.c_int64), ("relax_edge_visits", C.c_int64), ("check_launches", C.c_int64),
+        ("probes", C.c_int64), ("rounds", C.c_int64), ("other_launches", C.c_int64),
+        ("relax_ms", C.c_double), ("check_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (building it is `python -m min_ratio_cycle_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(-1, f"{LIB_PATH} is missing: build it with `python -m min_ratio_cycle_b200.build` "
+                              "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    p32, p64, pd = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    pu8, pi = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    vp = C.c_void_p
+    L.mrc_abi_version.restype = C.c_int
+    L.mrc_last_error.restype = C.c_char_p
+    L.mrc_device_count.argtypes = [pi]
+    L.mrc_graph_create.argtypes = [C.c_int64, C.c_int64, p32, p32, pd, pd, p64, p64, C.c_int, C.POINTER(vp)]
+    L.mrc_graph_destroy.argtypes = [vp]
+    L.mrc_graph_info.argtypes = [vp, p64, p64, pi, pi]
+    L.mrc_numeric_bounds.argtypes = [vp, pd, pd]
+    L.mrc_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.mrc_reset_stats.argtypes = [vp]
+    L.mrc_graph_patch_edges.argtypes = [vp, C.c_int64, p64, pd, pd]
+    L.mrc_graph_restore.argtypes = [vp]
+    L.mrc_probe_numeric.argtypes = [vp, pd, C.c_int, C.c_double, C.c_uint32, p32, p32, p32, C.c_int64, pd, pd, p64]
+    L.mrc_solve_numeric.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
+                                    C.c_double, pd, pd, pd, p32, C.c_int64, p64, p32, pd, pd]
+    L.mrc_plan_candidates.argtypes = [C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, pd]
+    L.mrc_reduce_round.argtypes = [C.c_int, pd, p32, pd, pd, pd, pi, pi]
+    L.mrc_probe_exact.argtypes = [vp, p64, p64, C.c_int, C.c_uint32, p32, p32, p32, C.c_int64, p64, p64, p64]
+    L.mrc_potentials_exact.argtypes = [vp, C.c_int64, C.c_int64, pu8, p64]
+    L.mrc_tight_mask_exact.argtypes = [vp, C.c_int64, C.c_int64, pu8, pu8]
+    L.mrc_zero_cycle_exact.argtypes = [vp, C.c_int64, C.c_int64, pu8, p32, C.c_int64, p64, p64, p64]
+    L.mrc_solve_exact.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, p32, C.c_int64, p64, p64, p64, p64, p64, p64,
+                                  p64, C.c_int64, p64]
+    for name in EXPORTS:
+        if name not in ("mrc_last_error",):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != OK:
+        raise NativeError(rc, lib().mrc_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    c = C.c_int(0)
+    rc = lib().mrc_device_count(C.byref(c))
+    return c.value if rc == OK else 0
+
+
+def _ptr(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+class DeviceGraph:
+    """
+    Device-resident destination-sorted edge arrays (mrc_graph).  Inputs are the reference's
+    `_U, _V, _C, _T[, _Ci, _Ti]` (solver.py:488-498) in any integer/float dtype; they are narrowed to
+    int32/f64/int64 here.
+    """
+
+    def __init__(self, n, U, V, Cw, Tw, Ci=None, Ti=None, device: int = 0):
+        L = lib()
+        self._h = None
+        self.n = int(n)
+        self.m = int(len(U))
+        src = np.ascontiguousarray(U, dtype=np.int32)
+        dst = np.ascontiguousarray(V, dtype=np.int32)
+        cost = np.ascontiguousarray(Cw, dtype=np.float64)
+        time = np.ascontiguousarray(Tw, dtype=np.float64)
+        ic = None if Ci is None else np.ascontiguousarray(Ci, dtype=np.int64)
+        it = None if Ti is None else np.ascontiguousarray(Ti, dtype=np.int64)
+        h = C.c_void_p()
+        check(L.mrc_graph_create(self.n, self.m, _ptr(src, C.c_int32), _ptr(dst, C.c_int32), _ptr(cost, C.c_double),
+                                 _ptr(time, C.c_double), _ptr(ic, C.c_int64), _ptr(it, C.c_int64), int(device),
+                                 C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.has_int = ic is not None
+
+    def close(self):
+        if self._h is not None:
+            lib().mrc_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- bookkeeping ----------------------------------------------------
+    def stats(self) -> dict:
+        s = Stats()
+        check(lib().mrc_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        check(lib().mrc_reset_stats(self._h))
+
+    def bounds(self):
+        lo, hi = C.c_double(), C.c_double()
+        check(lib().mrc_numeric_bounds(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def patch_edges(self, idx, dcost, dtime):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        dc = np.ascontiguousarray(dcost, dtype=np.float64)
+        dt = np.ascontiguousarray(dtime, dtype=np.float64)
+        check(lib().mrc_graph_patch_edges(self._h, len(idx), _ptr(idx, C.c_int64), _ptr(dc, C.c_double),
+                                          _ptr(dt, C.c_double)))
+
+    def restore(self):
+        check(lib().mrc_graph_restore(self._h))
+
+    # -- probes -----------------------------------------------------------
+    def probe_numeric(self, lams, slack: float = 1e-15, flags: int = 0, cyc_cap: int | None = None):
+        """K-batched analogue of _detect_negative_cycle_numeric.  Returns a list of dicts."""
+        lam = np.ascontiguousarray(lams, dtype=np.float64)
+        K = len(lam)
+        cap = int(cyc_cap if cyc_cap is not None else self.n + 1)
+        vd = np.zeros(K, np.int32); cl = np.zeros(K, np.int32); buf = np.zeros(K * cap, np.int32)
+        sc = np.zeros(K); st = np.zeros(K); ps = np.zeros(K, np.int64)
+        check(lib().mrc_probe_numeric(self._h, _ptr(lam, C.c_double), K, float(slack), int(flags), _ptr(vd, C.c_int32),
+                                      _ptr(cl, C.c_int32), _ptr(buf, C.c_int32), cap, _ptr(sc, C.c_double),
+                                      _ptr(st, C.c_double), _ptr(ps, C.c_int64)))
+        out = []
+        for k in range(K):
+            cyc = buf[k * cap: k * cap + min(cl[k], cap)].tolist() if cl[k] else None
+            out.append(dict(lam=float(lam[k]), verdict=int(vd[k]), cycle=cyc, cycle_len=int(cl[k]),
+                            sum_cost=float(sc[k]), sum_time=float(st[k]), passes=int(ps[k])))
+        return out
+
+    def probe_exact(self, a, b, flags: int = 0, cyc_cap: int | None = None):
+        a = np.ascontiguousarray(a, dtype=np.int64); b = np.ascontiguousarray(b, dtype=np.int64)
+        K = len(a)
+        cap = int(cyc_cap if cyc_cap is not None else self.n + 1)
+        vd = np.zeros(K, np.int32); cl = np.zeros(K, np.int32); buf = np.zeros(K * cap, np.int32)
+        sc = np.zeros(K, np.int64); st = np.zeros(K, np.int64); ps = np.zeros(K, np.int64)
+        check(lib().mrc_probe_exact(self._h, _ptr(a, C.c_int64), _ptr(b, C.c_int64), K, int(flags), _ptr(vd, C.c_int32),
+                                    _ptr(cl, C.c_int32), _ptr(buf, C.c_int32), cap, _ptr(sc, C.c_int64),
+                                    _ptr(st, C.c_int64), _ptr(ps, C.c_int64)))
+        out = []
+        for k in range(K):
+            cyc = buf[k * cap: k * cap + min(cl[k], cap)].tolist() if cl[k] else None
+            out.append(dict(a=int(a[k]), b=int(b[k]), verdict=int(vd[k]), cycle=cyc, cycle_len=int(cl[k]),
+                            sum_cost=int(sc[k]), sum_time=int(st[k]), passes=int(ps[k])))
+        return out
+
+    # -- searches -----------------------------------------------------------
+    def solve_numeric(self, lo: float, hi: float, max_iter: int = 60, tol: float = 1e-12, slack: float = 1e-15,
+                      K: int = 4, max_seconds: float = 0.0):
+        """Returns dict(rc, cycle(closed), sum_cost, sum_time, ratio, iterations, lo, hi); rc may be
+        ERR_CONVERGENCE with a valid best cycle, ERR_NO_CYCLE / ERR_TIMEOUT without one."""
+        cap = self.n + 1
+        buf = np.zeros(cap, np.int32)
+        ratio, sc, st, flo, fhi = (C.c_double() for _ in range(5))
+        cl = C.c_int64(); it = C.c_int32()
+        rc = lib().mrc_solve_numeric(self._h, float(lo), float(hi), int(max_iter), float(tol), float(slack), int(K),
+                                     float(max_seconds or 0.0), C.byref(ratio), C.byref(sc), C.byref(st),
+                                     _ptr(buf, C.c_int32), cap, C.byref(cl), C.byref(it), C.byref(flo), C.byref(fhi))
+        if rc not in (OK, ERR_CONVERGENCE, ERR_NO_CYCLE, ERR_TIMEOUT):
+            check(rc)
+        have = rc in (OK, ERR_CONVERGENCE)
+        return dict(rc=rc, message=lib().mrc_last_error().decode() if rc else "",
+                    cycle=buf[: cl.value].tolist() if have else [], sum_cost=sc.value, sum_time=st.value,
+                    ratio=ratio.value, iterations=it.value, lo=flo.value, hi=fhi.value)
+
+    def potentials_exact(self, a: int, b: int):
+        ok = C.c_uint8()
+        dist = np.zeros(self.n, np.int64)
+        check(lib().mrc_potentials_exact(self._h, int(a), int(b), C.byref(ok), _ptr(dist, C.c_int64)))
+        return bool(ok.value), dist
+
+    def tight_mask_exact(self, a: int, b: int):
+        ok = C.c_uint8()
+        mask = np.zeros(self.m, np.uint8)
+        check(lib().mrc_tight_mask_exact(self._h, int(a), int(b), C.byref(ok), _ptr(mask, C.c_uint8)))
+        return bool(ok.value), mask
+
+    def zero_cycle_exact(self, a: int, b: int):
+        found = C.c_uint8()
+        cap = self.n + 1
+        buf = np.zeros(cap, np.int32)
+        cl, sc, st = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().mrc_zero_cycle_exact(self._h, int(a), int(b), C.byref(found), _ptr(buf, C.c_int32), cap,
+                                         C.byref(cl), C.byref(sc), C.byref(st)))
+        if not found.value:
+            return None
+        return buf[: cl.value].tolist(), sc.value, st.value
+
+    def solve_exact(self, max_den=None, max_steps=None, strategy: int = 1, probes_cap: int = 4096):
+        """_stern_brocot_search analogue.  Returns dict(rc, cycle(open), sum_cost, sum_time, a, b, iterations, probes)."""
+        cap = self.n + 1
+        buf = np.zeros(cap, np.int32)
+        pr = np.zeros(2 * probes_cap, np.int64)
+        cl, sc, st, a, b, it, npb = (C.c_int64() for _ in range(7))
+        rc = lib().mrc_solve_exact(self._h, -1 if max_den is None else int(max_den),
+                                   -1 if max_steps is None else int(max_steps), int(strategy), _ptr(buf, C.c_int32),
+                                   cap, C.byref(cl), C.byref(sc), C.byref(st), C.byref(a), C.byref(b), C.byref(it),
+                                   _ptr(pr, C.c_int64), probes_cap, C.byref(npb))
+        if rc not in (OK, ERR_LOWER_NEG, ERR_UPPER_NONNEG, ERR_SB_STEPS, ERR_OVERFLOW, ERR_EDGE_MISSING,
+                      ERR_CONVERGENCE):
+            check(rc)
+        k = min(npb.value, probes_cap)
+        return dict(rc=rc, message=lib().mrc_last_error().decode() if rc else "",
+                    cycle=buf[: cl.value].tolist() if rc == OK else [], sum_cost=sc.value, sum_time=st.value,
+                    a=a.value, b=b.value, iterations=it.value,
+                    probes=[(int(pr[2 * i]), int(pr[2 * i + 1])) for i in range(k)])
+
+
+def plan_candidates(lo: float, hi: float, have_cycle: bool, tol: float, K_total: int) -> np.ndarray:
+    out = np.zeros(K_total)
+    check(lib().mrc_plan_candidates(float(lo), float(hi), int(bool(have_cycle)), float(tol), int(K_total),
+                                    _ptr(out, C.c_double)))
+    return out
+
+
+def reduce_round(lam, verdict, cyc_ratio, lo: float, hi: float, have_cycle: bool):
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    vd = np.ascontiguousarray(verdict, dtype=np.int32)
+    cr = np.ascontiguousarray(cyc_ratio, dtype=np.float64)
+    clo, chi = C.c_double(lo), C.c_double(hi)
+    hc, best = C.c_int(int(bool(have_cycle))), C.c_int(-1)
+    check(lib().mrc_reduce_round(len(lam), _ptr(lam, C.c_double), _ptr(vd, C.c_int32), _ptr(cr, C.c_double),
+                                 C.byref(clo), C.byref(chi), C.byref(hc), C.byref(best)))
+    return clo.value, chi.value, bool(hc.value), best.value

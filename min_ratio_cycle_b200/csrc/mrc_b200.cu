@@ -1,0 +1,905 @@
+// mrc_b200.cu -- host side of libmrc_b200.so: device-resident graph, batched probes with early
+// negative-cycle detection, the numeric multisection driver and the exact (int64) Stern-Brocot driver.
+// C ABI declared in include/mrc_b200.h; each entry point cites the reference method it replaces.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "mrc_kernels.cuh"
+
+typedef __int128 i128;
+
+static thread_local std::string g_err;
+static int set_err(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e_ = (x);                                                                           \
+        if (e_ != cudaSuccess)                                                                          \
+            return set_err(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? MRC_ERR_NO_DEVICE \
+                                                                                        : MRC_ERR_CUDA, \
+                           "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+    } while (0)
+#define MRC_TRY(x)            \
+    do {                      \
+        int rc_ = (x);        \
+        if (rc_) return rc_;  \
+    } while (0)
+
+struct PatchRec {
+    ll k;
+    ll *d_idx;
+    double *d_oldc, *d_oldt;
+};
+
+struct mrc_graph {
+    int device = 0, sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ll n = 0, m = 0;
+    int *d_src = nullptr, *d_dst = nullptr;
+    double *d_cost = nullptr, *d_time = nullptr;
+    ll *d_icost = nullptr, *d_itime = nullptr;
+    // workspace
+    void *d_dist = nullptr;      // [n][KT] f64 or i64
+    int *d_pred = nullptr;       // [n][KT]
+    int *d_jump = nullptr;       // [n][KT]
+    int *d_cyc_edges = nullptr;  // [KMAX][cap]
+    ll cyc_cap = 0;
+    DevStatus *d_status = nullptr, *h_status = nullptr;
+    int *d_g_src = nullptr; double *d_g_c = nullptr, *d_g_t = nullptr; ll *d_g_ic = nullptr, *d_g_it = nullptr;
+    uint8_t *d_mask = nullptr;
+    ull *d_keys = nullptr;
+    // host mirrors needed by the exact path (tight-subgraph DFS and first-(u,v)-edge lookup)
+    std::vector<int> h_src, h_dst;
+    std::vector<ll> h_icost, h_itime, h_starts;
+    ll max_abs_ic = 0, max_abs_it = 0, max_it = 1;
+    double min_ratio_i = 0, max_ratio_i = 0;
+    bool has_int = false;
+    // dist cache: the last exact K=1 probe that converged left potentials in d_dist
+    bool pot_valid = false; ll pot_a = 0, pot_b = 0;
+    std::vector<PatchRec> patches;
+    int relax_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int check_blocks[4] = {0, 0, 0, 0};
+    int burst_init = 2, burst_max = MRC_MAX_BURST;
+    bool alternate = true;
+    mrc_stats stats;
+};
+
+struct ProbeOut {
+    int verdict = -1;
+    int len = 0;
+    int minv = -1;
+    double sumc = 0, sumt = 0;   // predecessor-walk order (device)
+    ll isumc = 0, isumt = 0;
+    ll passes = 0;
+};
+
+extern "C" int mrc_abi_version(void) { return MRC_ABI_VERSION; }
+extern "C" const char *mrc_last_error(void) { return g_err.c_str(); }
+extern "C" int mrc_device_count(int *count) {
+    if (!count) return set_err(MRC_ERR_ARG, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return set_err(MRC_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
+    *count = c;
+    return c > 0 ? MRC_OK : set_err(MRC_ERR_NO_DEVICE, "no CUDA device");
+}
+
+static int kt_of(int K) { return K <= 1 ? 1 : K <= 2 ? 2 : K <= 4 ? 4 : 8; }
+static int kt_index(int KT) { return KT == 1 ? 0 : KT == 2 ? 1 : KT == 4 ? 2 : 3; }
+
+template <int K, bool EXACT> static const void *relax_fn() { return (const void *)relax_kernel<K, EXACT>; }
+static const void *relax_fn_of(int KT, bool exact) {
+    switch (KT) {
+        case 1: return exact ? relax_fn<1, true>() : relax_fn<1, false>();
+        case 2: return exact ? relax_fn<2, true>() : relax_fn<2, false>();
+        case 4: return exact ? relax_fn<4, true>() : relax_fn<4, false>();
+        default: return exact ? relax_fn<8, true>() : relax_fn<8, false>();
+    }
+}
+static const void *check_fn_of(int KT) {
+    switch (KT) {
+        case 1: return (const void *)cycle_check_kernel<1>;
+        case 2: return (const void *)cycle_check_kernel<2>;
+        case 4: return (const void *)cycle_check_kernel<4>;
+        default: return (const void *)cycle_check_kernel<8>;
+    }
+}
+
+extern "C" int mrc_graph_destroy(mrc_graph *g) {
+    if (!g) return MRC_OK;
+    cudaSetDevice(g->device);
+    for (auto &p : g->patches) { cudaFree(p.d_idx); cudaFree(p.d_oldc); cudaFree(p.d_oldt); }
+    cudaFree(g->d_src); cudaFree(g->d_dst); cudaFree(g->d_cost); cudaFree(g->d_time);
+    cudaFree(g->d_icost); cudaFree(g->d_itime); cudaFree(g->d_dist); cudaFree(g->d_pred); cudaFree(g->d_jump);
+    cudaFree(g->d_cyc_edges); cudaFree(g->d_status); cudaFree(g->d_g_src); cudaFree(g->d_g_c); cudaFree(g->d_g_t);
+    cudaFree(g->d_g_ic); cudaFree(g->d_g_it); cudaFree(g->d_mask); cudaFree(g->d_keys);
+    if (g->h_status) cudaFreeHost(g->h_status);
+    for (auto &e : g->ev) if (e) cudaEventDestroy(e);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+    return MRC_OK;
+}
+
+extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const int32_t *dst, const double *cost,
+                                const double *time, const int64_t *icost, const int64_t *itime, int device,
+                                mrc_graph **out) {
+    if (!out) return set_err(MRC_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n <= 0 || m <= 0) return set_err(MRC_ERR_ARG, "n and m must be positive (n=%lld m=%lld)", (ll)n, (ll)m);
+    if (n > 0x7ffffff0ll || m > 0x7ffffff0ll) return set_err(MRC_ERR_ARG, "n, m must fit int32");
+    if (!src || !dst || !cost || !time) return set_err(MRC_ERR_ARG, "edge arrays are NULL");
+    if ((icost == nullptr) != (itime == nullptr)) return set_err(MRC_ERR_ARG, "icost/itime must both be set or both NULL");
+    int ndev = 0;
+    MRC_TRY(mrc_device_count(&ndev));
+    if (device < 0 || device >= ndev) return set_err(MRC_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    for (ll e = 0; e < m; e++) {
+        if ((unsigned)src[e] >= (unsigned)n || (unsigned)dst[e] >= (unsigned)n)
+            return set_err(MRC_ERR_ARG, "edge %lld has an endpoint outside [0,n)", e);
+        if (e && dst[e] < dst[e - 1]) return set_err(MRC_ERR_ARG, "edges are not destination-sorted at %lld", e);
+        if (!(time[e] > 0)) return set_err(MRC_ERR_ARG, "edge %lld: time must be strictly positive", e);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    mrc_graph *g = new mrc_graph();
+    memset(&g->stats, 0, sizeof g->stats);
+    g->device = device; g->n = n; g->m = m;
+    int rc = [&]() -> int {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        g->sms = prop.multiProcessorCount;
+        CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+        for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
+        const size_t m4 = ((size_t)m + 3) & ~(size_t)3;   // vector loads never read past the allocation
+        CUDA_TRY(cudaMalloc(&g->d_src, m4 * 4)); CUDA_TRY(cudaMalloc(&g->d_dst, m4 * 4));
+        CUDA_TRY(cudaMalloc(&g->d_cost, m4 * 8)); CUDA_TRY(cudaMalloc(&g->d_time, m4 * 8));
+        CUDA_TRY(cudaMemcpyAsync(g->d_src, src, (size_t)m * 4, cudaMemcpyHostToDevice, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(g->d_dst, dst, (size_t)m * 4, cudaMemcpyHostToDevice, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(g->d_cost, cost, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(g->d_time, time, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
+        g->stats.h2d_bytes += (int64_t)m * 24;
+        if (icost) {
+            g->has_int = true;
+            CUDA_TRY(cudaMalloc(&g->d_icost, m4 * 8)); CUDA_TRY(cudaMalloc(&g->d_itime, m4 * 8));
+            CUDA_TRY(cudaMemcpyAsync(g->d_icost, icost, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
+            CUDA_TRY(cudaMemcpyAsync(g->d_itime, itime, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
+            g->stats.h2d_bytes += (int64_t)m * 16;
+            CUDA_TRY(cudaMalloc(&g->d_mask, (size_t)m));
+            g->h_src.assign(src, src + m); g->h_dst.assign(dst, dst + m);
+            g->h_icost.assign(icost, icost + m); g->h_itime.assign(itime, itime + m);
+            g->h_starts.assign((size_t)n + 1, 0);
+            for (ll e = 0; e < m; e++) g->h_starts[dst[e] + 1]++;
+            for (ll v = 0; v < n; v++) g->h_starts[v + 1] += g->h_starts[v];
+            double mn = INFINITY, mx = -INFINITY;
+            for (ll e = 0; e < m; e++) {
+                if (itime[e] <= 0) return set_err(MRC_ERR_ARG, "edge %lld: integer time must be positive", e);
+                g->max_abs_ic = std::max<ll>(g->max_abs_ic, icost[e] < 0 ? -icost[e] : icost[e]);
+                g->max_abs_it = std::max<ll>(g->max_abs_it, itime[e]);
+                const double r = (double)icost[e] / (double)itime[e];   // solver.py:754
+                mn = std::min(mn, r); mx = std::max(mx, r);
+            }
+            g->max_it = g->max_abs_it;
+            g->min_ratio_i = mn; g->max_ratio_i = mx;
+        }
+        CUDA_TRY(cudaMalloc(&g->d_dist, (size_t)n * MRC_KMAX * 8));
+        CUDA_TRY(cudaMalloc(&g->d_pred, (size_t)n * MRC_KMAX * 4));
+        CUDA_TRY(cudaMalloc(&g->d_jump, (size_t)n * MRC_KMAX * 4));
+        g->cyc_cap = n;
+        CUDA_TRY(cudaMalloc(&g->d_cyc_edges, (size_t)g->cyc_cap * MRC_KMAX * 4));
+        CUDA_TRY(cudaMalloc(&g->d_status, sizeof(DevStatus)));
+        CUDA_TRY(cudaMemsetAsync(g->d_status, 0, sizeof(DevStatus), g->stream));
+        CUDA_TRY(cudaMallocHost(&g->h_status, sizeof(DevStatus)));
+        CUDA_TRY(cudaMalloc(&g->d_keys, 16));
+        // launch geometry: persistent grids sized to whole waves of the 148 SMs
+        for (int KT : {1, 2, 4, 8})
+            for (int ex = 0; ex < 2; ex++) {
+                int occ = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, relax_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
+                if (occ < 1) return set_err(MRC_ERR_CUDA, "relax kernel K=%d does not fit on an SM", KT);
+                ll need = ((m >> 2) + MRC_RELAX_THREADS - 1) / MRC_RELAX_THREADS;
+                need = std::max<ll>(need, 1);
+                g->relax_blocks[kt_index(KT)][ex] = (int)std::min<ll>(need, (ll)occ * g->sms);
+            }
+        for (int KT : {1, 2, 4, 8}) {
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_fn_of(KT), 256, 0));
+            if (occ < 1) return set_err(MRC_ERR_CUDA, "check kernel K=%d does not fit on an SM", KT);
+            ll need = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
+            g->check_blocks[kt_index(KT)] = (int)std::min<ll>(need, (ll)occ * g->sms);
+        }
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        return MRC_OK;
+    }();
+    if (rc) { mrc_graph_destroy(g); return rc; }
+    *out = g;
+    return MRC_OK;
+}
+
+extern "C" int mrc_graph_info(const mrc_graph *g, int64_t *n, int64_t *m, int *device, int *has_int) {
+    if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
+    if (n) *n = g->n;
+    if (m) *m = g->m;
+    if (device) *device = g->device;
+    if (has_int) *has_int = g->has_int;
+    return MRC_OK;
+}
+extern "C" int mrc_get_stats(const mrc_graph *g, mrc_stats *out) {
+    if (!g || !out) return set_err(MRC_ERR_ARG, "NULL argument");
+    *out = g->stats;
+    return MRC_OK;
+}
+extern "C" int mrc_reset_stats(mrc_graph *g) {
+    if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
+    memset(&g->stats, 0, sizeof g->stats);
+    return MRC_OK;
+}
+
+static double key_to_f64(ull k) {
+    ull b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+extern "C" int mrc_numeric_bounds(mrc_graph *g, double *lo, double *hi) {
+    if (!g || !lo || !hi) return set_err(MRC_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    ull init[2] = {~0ull, 0ull}, keys[2];
+    CUDA_TRY(cudaMemcpyAsync(g->d_keys, init, 16, cudaMemcpyHostToDevice, g->stream));
+    int blocks = (int)std::min<ll>((g->m + 255) / 256, (ll)g->sms * 8);
+    ratio_bounds_kernel<<<blocks, 256, 0, g->stream>>>(g->d_cost, g->d_time, g->m, g->d_keys, g->d_keys + 1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(keys, g->d_keys, 16, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    g->stats.other_launches++;
+    *lo = key_to_f64(keys[0]) - 1.0;   // solver.py:1022-1023
+    *hi = key_to_f64(keys[1]) + 1.0;
+    return MRC_OK;
+}
+
+extern "C" int mrc_graph_patch_edges(mrc_graph *g, int64_t k, const int64_t *idx, const double *dcost,
+                                     const double *dtime) {
+    if (!g || k < 0 || (k && (!idx || !dcost || !dtime))) return set_err(MRC_ERR_ARG, "bad patch arguments");
+    if (k == 0) return MRC_OK;
+    for (ll i = 0; i < k; i++)
+        if (idx[i] < 0 || idx[i] >= g->m) return set_err(MRC_ERR_ARG, "edge index out of range");
+    CUDA_TRY(cudaSetDevice(g->device));
+    PatchRec p;
+    p.k = k;
+    double *d_dc, *d_dt;
+    CUDA_TRY(cudaMalloc(&p.d_idx, (size_t)k * 8)); CUDA_TRY(cudaMalloc(&p.d_oldc, (size_t)k * 8));
+    CUDA_TRY(cudaMalloc(&p.d_oldt, (size_t)k * 8));
+    CUDA_TRY(cudaMalloc(&d_dc, (size_t)k * 8)); CUDA_TRY(cudaMalloc(&d_dt, (size_t)k * 8));
+    CUDA_TRY(cudaMemcpyAsync(p.d_idx, idx, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_dc, dcost, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_dt, dtime, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
+    patch_edges_kernel<<<(int)((k + 127) / 128), 128, 0, g->stream>>>(g->d_cost, g->d_time, p.d_idx, d_dc, d_dt, k,
+                                                                      p.d_oldc, p.d_oldt);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    cudaFree(d_dc); cudaFree(d_dt);
+    g->patches.push_back(p);
+    g->pot_valid = false;
+    g->stats.other_launches++;
+    g->stats.h2d_bytes += k * 24;
+    return MRC_OK;
+}
+extern "C" int mrc_graph_restore(mrc_graph *g) {
+    if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
+    CUDA_TRY(cudaSetDevice(g->device));
+    while (!g->patches.empty()) {
+        PatchRec p = g->patches.back();
+        g->patches.pop_back();
+        unpatch_edges_kernel<<<(int)((p.k + 127) / 128), 128, 0, g->stream>>>(g->d_cost, g->d_time, p.d_idx, p.k,
+                                                                              p.d_oldc, p.d_oldt);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        cudaFree(p.d_idx); cudaFree(p.d_oldc); cudaFree(p.d_oldt);
+        g->stats.other_launches++;
+    }
+    return MRC_OK;
+}
+
+// ------------------------------------------------------------------------------------------- probe engine
+static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra) {
+    const int blocks = g->relax_blocks[kt_index(KT)][exact ? 1 : 0];
+    void *args[] = {(void *)&ra};
+    CUDA_TRY(cudaLaunchKernel(relax_fn_of(KT, exact), dim3(blocks), dim3(MRC_RELAX_THREADS), args, 0, g->stream));
+    return MRC_OK;
+}
+static int launch_check(mrc_graph *g, int KT, const CheckArgs &ca) {
+    const int blocks = g->check_blocks[kt_index(KT)];
+    void *args[] = {(void *)&ca};
+    CUDA_TRY(cudaLaunchCooperativeKernel(check_fn_of(KT), dim3(blocks), dim3(256), args, 0, g->stream));
+    return MRC_OK;
+}
+
+/*
+ * Batched Bellman-Ford for K candidates.  Numeric: lam[k]; exact: a[k]/b[k].
+ * Per burst: <= burst relaxation launches back to back, then ONE cooperative cycle check, then one
+ * small D2H of the status block.  A candidate is decided when
+ *   - some pass of the burst changed nothing for it            -> NONNEG (true fixed point)
+ *   - the predecessor graph holds a cycle that verifies negative-> NEG
+ *   - (numeric) the cycle's ratio is >= lambda but within rounding of it -> TIE
+ *   - n passes done and still relaxing (reference rule :1252-1257)       -> NEG_NOCYCLE
+ */
+static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
+                     unsigned flags, ProbeOut *res) {
+    if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
+    if (K < 1 || K > MRC_KMAX) return set_err(MRC_ERR_ARG, "K must be in [1,%d]", MRC_KMAX);
+    if (exact && !g->has_int) return set_err(MRC_ERR_NOT_INTEGER, "Exact mode requires integer weights");
+    if (exact && !g->patches.empty()) return set_err(MRC_ERR_ARG, "exact probes on a patched graph are not supported");
+    CUDA_TRY(cudaSetDevice(g->device));
+    const int KT = kt_of(K);
+    const ll n = g->n, m = g->m;
+    g->pot_valid = false;
+    if (exact) {
+        for (int k = 0; k < K; k++) {
+            if (b[k] <= 0) return set_err(MRC_ERR_ARG, "denominator must be positive");
+            const i128 wmax = (i128)b[k] * g->max_abs_ic + (i128)(a[k] < 0 ? -(i128)a[k] : (i128)a[k]) * g->max_abs_it;
+            if (wmax * (i128)(n + 1) >= ((i128)1 << 62))
+                return set_err(MRC_ERR_OVERFLOW, "int64 overflow: |b*cost - a*time| * n exceeds 2^62 for a=%lld b=%lld", a[k], b[k]);
+        }
+    }
+    RelaxArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.src = g->d_src; ra.dst = g->d_dst; ra.cost = g->d_cost; ra.time = g->d_time;
+    ra.icost = g->d_icost; ra.itime = g->d_itime; ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = m;
+    ra.slack = slack;
+    for (int k = 0; k < K; k++) {
+        if (exact) { ra.a[k] = a[k]; ra.b[k] = b[k]; } else ra.lam[k] = lam[k];
+        res[k] = ProbeOut();
+    }
+    CheckArgs ca;
+    memset(&ca, 0, sizeof ca);
+    ca.src = g->d_src; ca.cost = g->d_cost; ca.time = g->d_time; ca.icost = g->d_icost; ca.itime = g->d_itime;
+    ca.pred = g->d_pred; ca.jump = g->d_jump; ca.cyc_edges = g->d_cyc_edges; ca.st = g->d_status;
+    ca.n = n; ca.cap = g->cyc_cap; ca.exact = exact;
+    { int r = 1; while (((ll)1 << r) < n + 1) r++; ca.rounds = std::min(r + 1, MRC_MAX_ROUNDS); }
+
+    CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)n * KT * 8, g->stream));      // dist = 0 (:1148 / :829)
+    CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)n * KT * 4, g->stream));   // pred = -1 (:1154)
+    unsigned active = (1u << K) - 1u;
+    const ll max_passes = n;   // n-1 passes + the detection pass
+    ll passes = 0;
+    int burst = g->burst_init;
+    g->stats.probes += K;
+    while (active) {
+        const int nb = (int)std::min<ll>(burst, max_passes - passes);
+        if (nb <= 0) {
+            for (int k = 0; k < K; k++)
+                if ((active >> k) & 1u) { res[k].verdict = MRC_V_NEG_NOCYCLE; res[k].passes = passes; }
+            break;
+        }
+        CUDA_TRY(cudaMemsetAsync(g->d_status->changed, 0, sizeof(unsigned) * MRC_MAX_BURST, g->stream));
+        CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
+        ra.active = active;
+        for (int i = 0; i < nb; i++) {
+            ra.changed = &g->d_status->changed[i];
+            ra.reverse = g->alternate ? (int)((passes + i) & 1) : 0;
+            MRC_TRY(launch_relax(g, KT, exact, ra));
+        }
+        CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
+        ca.active = active;
+        MRC_TRY(launch_check(g, KT, ca));
+        CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
+        CUDA_TRY(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->stats.relax_ms += ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
+        passes += nb;
+        g->stats.relax_launches += nb;
+        g->stats.relax_edge_visits += (int64_t)nb * m * __builtin_popcount(active);
+        g->stats.check_launches++;
+        g->stats.d2h_bytes += sizeof(DevStatus);
+        const DevStatus &hs = *g->h_status;
+        for (int k = 0; k < K; k++) {
+            if (!((active >> k) & 1u)) continue;
+            bool conv = false;
+            for (int i = 0; i < nb; i++) conv |= !((hs.changed[i] >> k) & 1u);
+            ProbeOut &o = res[k];
+            if (conv) { o.verdict = MRC_V_NONNEG; }
+            else if (((hs.cyc_mask >> k) & 1u) && hs.out[k].found) {
+                const CycleOut &c = hs.out[k];
+                if (exact) {
+                    if ((i128)b[k] * c.isumc - (i128)a[k] * c.isumt < 0) o.verdict = MRC_V_NEG;
+                } else if (c.sumt > 0) {
+                    const double r = c.sumc / c.sumt;
+                    if (r < lam[k]) o.verdict = MRC_V_NEG;
+                    else if (r - lam[k] <= 1e-12 * std::max(1.0, std::fabs(lam[k]))) o.verdict = MRC_V_TIE;
+                }
+                if (o.verdict >= 0) {
+                    o.len = c.len; o.minv = c.minv; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
+                }
+            }
+            if (o.verdict >= 0) { o.passes = passes; active &= ~(1u << k); }
+        }
+        if (flags & MRC_F_MONOTONE_PRUNE) {
+            // verdicts are monotone in lambda: NEG at x implies NEG above x, NONNEG at x implies NONNEG below x
+            for (int k = 0; k < K; k++) {
+                if (res[k].verdict != MRC_V_NEG && res[k].verdict != MRC_V_NONNEG) continue;
+                for (int j = 0; j < K; j++) {
+                    if (!((active >> j) & 1u)) continue;
+                    bool above = exact ? ((i128)a[j] * b[k] > (i128)a[k] * b[j]) : (lam[j] > lam[k]);
+                    bool below = exact ? ((i128)a[j] * b[k] < (i128)a[k] * b[j]) : (lam[j] < lam[k]);
+                    if (res[k].verdict == MRC_V_NEG && above) { res[j].verdict = MRC_V_SKIPPED_NEG; res[j].passes = passes; active &= ~(1u << j); }
+                    if (res[k].verdict == MRC_V_NONNEG && below) { res[j].verdict = MRC_V_SKIPPED_NONNEG; res[j].passes = passes; active &= ~(1u << j); }
+                }
+            }
+        }
+        burst = std::min(burst * 2, g->burst_max);
+    }
+    if (exact && K == 1 && res[0].verdict == MRC_V_NONNEG) { g->pot_valid = true; g->pot_a = a[0]; g->pot_b = b[0]; }
+    return MRC_OK;
+}
+
+/*
+ * Bring the cycle of candidate k to the host: CLOSED vertex list in forward order starting at the
+ * smallest vertex, and cost/time sums accumulated in that order over the edges Bellman-Ford used.
+ */
+static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::vector<int> &verts, double *sc,
+                       double *st, ll *isc, ll *ist) {
+    const ll L = o.len;
+    verts.clear();
+    if (L <= 0) return MRC_OK;
+    if (L > g->cyc_cap) return set_err(MRC_ERR_ARG, "cycle longer than buffer");
+    if (!g->d_g_src) {
+        CUDA_TRY(cudaMalloc(&g->d_g_src, (size_t)g->cyc_cap * 4));
+        CUDA_TRY(cudaMalloc(&g->d_g_c, (size_t)g->cyc_cap * 8)); CUDA_TRY(cudaMalloc(&g->d_g_t, (size_t)g->cyc_cap * 8));
+        CUDA_TRY(cudaMalloc(&g->d_g_ic, (size_t)g->cyc_cap * 8)); CUDA_TRY(cudaMalloc(&g->d_g_it, (size_t)g->cyc_cap * 8));
+    }
+    const int blocks = (int)std::min<ll>((L + 127) / 128, 1024);
+    gather_cycle_kernel<<<blocks, 128, 0, g->stream>>>(g->d_cyc_edges + (ll)k * g->cyc_cap, L, g->d_src, g->d_cost,
+                                                       g->d_time, g->d_icost, g->d_itime, exact, g->d_g_src, g->d_g_c,
+                                                       g->d_g_t, g->d_g_ic, g->d_g_it);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<int> hsrc((size_t)L);
+    std::vector<double> hc, ht;
+    std::vector<ll> hic, hit;
+    CUDA_TRY(cudaMemcpyAsync(hsrc.data(), g->d_g_src, (size_t)L * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (exact) {
+        hic.resize(L); hit.resize(L);
+        CUDA_TRY(cudaMemcpyAsync(hic.data(), g->d_g_ic, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(hit.data(), g->d_g_it, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
+    } else {
+        hc.resize(L); ht.resize(L);
+        CUDA_TRY(cudaMemcpyAsync(hc.data(), g->d_g_c, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(ht.data(), g->d_g_t, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    g->stats.other_launches++;
+    g->stats.d2h_bytes += L * 20;
+    // backward walk e_0..e_{L-1} from minv; forward cycle uses e_{L-1}, ..., e_0
+    verts.reserve((size_t)L + 1);
+    verts.push_back(o.minv);
+    for (ll j = L - 2; j >= 0; j--) verts.push_back(hsrc[j]);
+    verts.push_back(o.minv);
+    if (exact) {
+        ll c = 0, t = 0;
+        for (ll j = L - 1; j >= 0; j--) { c += hic[j]; t += hit[j]; }
+        if (isc) *isc = c;
+        if (ist) *ist = t;
+    } else {
+        double c = 0.0, t = 0.0;
+        for (ll j = L - 1; j >= 0; j--) { c += hc[j]; t += ht[j]; }
+        if (sc) *sc = c;
+        if (st) *st = t;
+    }
+    return MRC_OK;
+}
+
+template <typename S>
+static int probe_common(mrc_graph *g, bool exact, const double *lam, const ll *a, const ll *b, int K, double slack,
+                        uint32_t flags, int32_t *verdict, int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap,
+                        S *sum_cost, S *sum_time, int64_t *passes) {
+    ProbeOut res[MRC_KMAX];
+    MRC_TRY(run_probe(g, exact, K, lam, a, b, slack, flags, res));
+    std::vector<int> verts;
+    for (int k = 0; k < K; k++) {
+        if (verdict) verdict[k] = res[k].verdict;
+        if (passes) passes[k] = res[k].passes;
+        if (cyc_len) cyc_len[k] = 0;
+        if (sum_cost) sum_cost[k] = 0;
+        if (sum_time) sum_time[k] = 0;
+        if (res[k].verdict == MRC_V_NEG || res[k].verdict == MRC_V_TIE) {
+            double sc = 0, st = 0; ll isc = 0, ist = 0;
+            MRC_TRY(fetch_cycle(g, exact, k, res[k], verts, &sc, &st, &isc, &ist));
+            if (cyc_len) cyc_len[k] = (int32_t)verts.size();
+            if (cyc_buf && cyc_cap > 0)
+                for (size_t i = 0; i < verts.size() && (int64_t)i < cyc_cap; i++) cyc_buf[(size_t)k * cyc_cap + i] = verts[i];
+            if (sum_cost) sum_cost[k] = exact ? (S)isc : (S)sc;
+            if (sum_time) sum_time[k] = exact ? (S)ist : (S)st;
+        }
+    }
+    return MRC_OK;
+}
+
+extern "C" int mrc_probe_numeric(mrc_graph *g, const double *lam, int K, double slack, uint32_t flags,
+                                 int32_t *verdict, int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap,
+                                 double *sum_cost, double *sum_time, int64_t *passes) {
+    if (!lam) return set_err(MRC_ERR_ARG, "lam is NULL");
+    return probe_common<double>(g, false, lam, nullptr, nullptr, K, slack, flags, verdict, cyc_len, cyc_buf, cyc_cap,
+                                sum_cost, sum_time, passes);
+}
+extern "C" int mrc_probe_exact(mrc_graph *g, const int64_t *a, const int64_t *b, int K, uint32_t flags,
+                               int32_t *verdict, int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap,
+                               int64_t *sum_cost, int64_t *sum_time, int64_t *passes) {
+    if (!a || !b) return set_err(MRC_ERR_ARG, "a/b is NULL");
+    return probe_common<int64_t>(g, true, nullptr, (const ll *)a, (const ll *)b, K, 0.0, flags, verdict, cyc_len,
+                                 cyc_buf, cyc_cap, sum_cost, sum_time, passes);
+}
+
+// ------------------------------------------------------------------------------- numeric lambda search
+extern "C" int mrc_plan_candidates(double lo, double hi, int have_cycle, double tol, int K_total, double *lam_out) {
+    if (!lam_out || K_total < 1) return set_err(MRC_ERR_ARG, "bad plan arguments");
+    const double gap = hi - lo;
+    const int K = K_total;
+    if (!have_cycle) {
+        if (K == 1) { lam_out[0] = (lo + hi) / 2.0; return MRC_OK; }   // the reference's midpoint, solver.py:1053
+        for (int j = 1; j <= K; j++) lam_out[j - 1] = lo + gap * ((double)j / (double)(K + 1));
+        return MRC_OK;
+    }
+    // hi is the ratio of a known cycle: K-1 interior points + the certifier just below hi.  If the
+    // certifier has no negative cycle, the known cycle is optimal to within tol and the search ends.
+    const double cert = hi - std::min(tol * 0.5, gap / (2.0 * K));
+    if (K == 1) { lam_out[0] = cert; return MRC_OK; }
+    for (int j = 1; j < K; j++) lam_out[j - 1] = lo + gap * ((double)j / (double)K);
+    lam_out[K - 1] = cert;
+    if (K >= 2 && lam_out[K - 2] >= cert) lam_out[K - 2] = lo + (cert - lo) * 0.5;
+    return MRC_OK;
+}
+
+extern "C" int mrc_reduce_round(int K_total, const double *lam, const int32_t *verdict, const double *cyc_ratio,
+                                double *lo, double *hi, int *have_cycle, int *best_idx) {
+    if (!lam || !verdict || !cyc_ratio || !lo || !hi || !have_cycle || !best_idx)
+        return set_err(MRC_ERR_ARG, "NULL argument");
+    double nlo = *lo, nhi = *hi;
+    int best = -1, hc = *have_cycle;
+    double best_ratio = hc ? *hi : INFINITY;
+    for (int k = 0; k < K_total; k++) {
+        switch (verdict[k]) {
+            case MRC_V_NEG:
+            case MRC_V_TIE:
+                if (cyc_ratio[k] < best_ratio) { best_ratio = cyc_ratio[k]; best = k; }
+                if (verdict[k] == MRC_V_TIE) nlo = std::max(nlo, lam[k]);
+                break;
+            case MRC_V_NEG_NOCYCLE:   // reference: hi = mid without a cycle (solver.py:1057-1060)
+                if (lam[k] < nhi) { nhi = lam[k]; }
+                break;
+            case MRC_V_NONNEG:
+                nlo = std::max(nlo, lam[k]);
+                break;
+            default: break;
+        }
+    }
+    if (best >= 0 && best_ratio <= nhi) { nhi = best_ratio; hc = 1; }
+    else if (nhi < *hi) hc = 0;   // upper end moved without a cycle to show for it
+    if (nlo > nhi) nlo = nhi;     // rounding noise near lambda*
+    *lo = nlo; *hi = nhi; *have_cycle = hc; *best_idx = best;
+    return MRC_OK;
+}
+
+extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int max_iter, double tol, double slack, int K,
+                                 double max_seconds, double *ratio, double *sum_cost, double *sum_time,
+                                 int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len, int32_t *iterations,
+                                 double *final_lo, double *final_hi) {
+    if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
+    if (K < 1 || K > MRC_KMAX) return set_err(MRC_ERR_ARG, "K must be in [1,%d]", MRC_KMAX);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<int> best_cycle, verts;
+    double best_sc = 0, best_st = 0;
+    bool have_best = false;
+    int have_cycle = 0, iters = 0, it = -1;
+    double lam[MRC_KMAX], cr[MRC_KMAX];
+    int32_t vd[MRC_KMAX];
+    ProbeOut res[MRC_KMAX];
+    for (int i = 0; i < max_iter; i++) {
+        it = i;
+        if (max_seconds > 0) {   // solver.py:1032-1041
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (el > max_seconds) return set_err(MRC_ERR_TIMEOUT, "Numeric solve exceeded time limit");
+        }
+        iters++;
+        g->stats.rounds++;
+        MRC_TRY(mrc_plan_candidates(lo, hi, have_cycle, tol, K, lam));
+        MRC_TRY(run_probe(g, false, K, lam, nullptr, nullptr, slack, MRC_F_MONOTONE_PRUNE, res));
+        for (int k = 0; k < K; k++) {
+            vd[k] = res[k].verdict;
+            cr[k] = (vd[k] == MRC_V_NEG || vd[k] == MRC_V_TIE) ? res[k].sumc / res[k].sumt : NAN;
+        }
+        int best = -1;
+        MRC_TRY(mrc_reduce_round(K, lam, vd, cr, &lo, &hi, &have_cycle, &best));
+        if (best >= 0) {
+            MRC_TRY(fetch_cycle(g, false, best, res[best], verts, &best_sc, &best_st, nullptr, nullptr));
+            best_cycle = verts;
+            have_best = true;
+        }
+        if (hi - lo <= tol) break;   // solver.py:1075-1076
+    }
+    if (!have_best) {   // solver.py:1079-1085: one more try at the upper bound
+        MRC_TRY(run_probe(g, false, 1, &hi, nullptr, nullptr, slack, 0, res));
+        if (res[0].verdict == MRC_V_NEG) {
+            MRC_TRY(fetch_cycle(g, false, 0, res[0], verts, &best_sc, &best_st, nullptr, nullptr));
+            best_cycle = verts;
+            have_best = true;
+        }
+    }
+    if (iterations) *iterations = iters;
+    if (final_lo) *final_lo = lo;
+    if (final_hi) *final_hi = hi;
+    if (!have_best) return set_err(MRC_ERR_NO_CYCLE, "No negative cycle found");   // solver.py:1087-1090
+    if (cycle_len) *cycle_len = (int64_t)best_cycle.size();
+    if (cycle)
+        for (size_t i = 0; i < best_cycle.size() && (int64_t)i < cycle_cap; i++) cycle[i] = best_cycle[i];
+    if (sum_cost) *sum_cost = best_sc;
+    if (sum_time) *sum_time = best_st;
+    if (ratio) *ratio = best_sc / best_st;   // solver.py:1293
+    if (max_iter > 0 && it == max_iter - 1 && hi - lo > tol)   // solver.py:1102-1109
+        return set_err(MRC_ERR_CONVERGENCE, "Numeric solver failed to converge");
+    return MRC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ exact mode
+static int ensure_potentials(mrc_graph *g, ll a, ll b, bool *ok) {
+    if (g->pot_valid && g->pot_a == a && g->pot_b == b) { *ok = true; return MRC_OK; }
+    ProbeOut r;
+    MRC_TRY(run_probe(g, true, 1, nullptr, &a, &b, 0.0, 0, &r));
+    *ok = (r.verdict == MRC_V_NONNEG);
+    return MRC_OK;
+}
+
+extern "C" int mrc_potentials_exact(mrc_graph *g, int64_t a, int64_t b, uint8_t *ok, int64_t *dist) {
+    if (!g || !ok) return set_err(MRC_ERR_ARG, "NULL argument");
+    bool good = false;
+    MRC_TRY(ensure_potentials(g, a, b, &good));
+    *ok = good;
+    if (good && dist) {
+        CUDA_TRY(cudaMemcpyAsync(dist, g->d_dist, (size_t)g->n * 8, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        g->stats.d2h_bytes += g->n * 8;
+    }
+    return MRC_OK;
+}
+
+static int tight_mask_device(mrc_graph *g, ll a, ll b, bool *ok) {
+    MRC_TRY(ensure_potentials(g, a, b, ok));
+    if (!*ok) return MRC_OK;
+    const int blocks = (int)std::min<ll>((g->m + 255) / 256, (ll)g->sms * 8);
+    tight_mask_kernel<<<blocks, 256, 0, g->stream>>>(g->d_src, g->d_dst, g->d_icost, g->d_itime, (const ll *)g->d_dist,
+                                                     a, b, g->m, g->d_mask);
+    CUDA_TRY(cudaGetLastError());
+    g->stats.other_launches++;
+    return MRC_OK;
+}
+
+extern "C" int mrc_tight_mask_exact(mrc_graph *g, int64_t a, int64_t b, uint8_t *ok, uint8_t *mask) {
+    if (!g || !ok || !mask) return set_err(MRC_ERR_ARG, "NULL argument");
+    bool good = false;
+    MRC_TRY(tight_mask_device(g, a, b, &good));
+    *ok = good;
+    if (good) {
+        CUDA_TRY(cudaMemcpyAsync(mask, g->d_mask, (size_t)g->m, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        g->stats.d2h_bytes += g->m;
+    }
+    return MRC_OK;
+}
+
+/*
+ * Host part of _find_zero_cycle_exact (solver.py:884-920): the reference's recursive three-colour DFS
+ * over the tight subgraph, replayed with an explicit stack.  Adjacency of u lists tight edges in
+ * ascending dst-sorted edge index (:886-888); roots 0..n-1 in order (:914); the first GRAY neighbour
+ * closes the cycle, reported as [child-of-v, ..., u, v] (:903-910).
+ */
+static bool zero_cycle_dfs(const mrc_graph *g, const std::vector<uint8_t> &mask, std::vector<int> &cyc) {
+    const ll n = g->n, m = g->m;
+    std::vector<ll> adj_start((size_t)n + 1, 0);
+    ll tight = 0;
+    for (ll e = 0; e < m; e++) if (mask[e]) { adj_start[g->h_src[e] + 1]++; tight++; }
+    if (!tight) return false;   // :881-882
+    for (ll v = 0; v < n; v++) adj_start[v + 1] += adj_start[v];
+    std::vector<int> adj((size_t)tight);
+    std::vector<ll> cursor(adj_start.begin(), adj_start.end() - 1);
+    for (ll e = 0; e < m; e++) if (mask[e]) adj[cursor[g->h_src[e]]++] = g->h_dst[e];
+    std::copy(adj_start.begin(), adj_start.end() - 1, cursor.begin());
+    std::vector<int8_t> color((size_t)n, 0);
+    std::vector<int> parent((size_t)n, -1), stack;
+    stack.reserve(1024);
+    for (ll s = 0; s < n; s++) {
+        if (color[s]) continue;
+        stack.clear();
+        stack.push_back((int)s); color[s] = 1;
+        while (!stack.empty()) {
+            const int u = stack.back();
+            if (cursor[u] < adj_start[u + 1]) {
+                const int v = adj[cursor[u]++];
+                if (color[v] == 0) { parent[v] = u; color[v] = 1; stack.push_back(v); }
+                else if (color[v] == 1) {
+                    cyc.clear();
+                    cyc.push_back(v);
+                    for (int x = u; x != v && x != -1; x = parent[x]) cyc.push_back(x);
+                    std::reverse(cyc.begin(), cyc.end());
+                    return true;
+                }
+            } else { color[u] = 2; stack.pop_back(); }
+        }
+    }
+    return false;
+}
+
+// _compute_cycle_weights_exact (solver.py:971-995): first inserted (u,v) edge == first hit in v's segment
+static int cycle_weights_exact(const mrc_graph *g, const std::vector<int> &cyc, ll *sc, ll *st) {
+    ll c = 0, t = 0;
+    const size_t L = cyc.size();
+    for (size_t i = 0; i < L; i++) {
+        const int u = cyc[i], v = cyc[(i + 1) % L];
+        ll k = g->h_starts[v];
+        const ll e = g->h_starts[v + 1];
+        for (; k < e; k++) if (g->h_src[k] == u) break;
+        if (k == e) return set_err(MRC_ERR_EDGE_MISSING, "Edge %d -> %d not found in cycle extraction", u, v);
+        c += g->h_icost[k]; t += g->h_itime[k];
+    }
+    *sc = c; *st = t;
+    return MRC_OK;
+}
+
+static int zero_cycle(mrc_graph *g, ll a, ll b, bool *found, std::vector<int> &cyc, ll *sc, ll *st) {
+    *found = false;
+    bool ok = false;
+    MRC_TRY(tight_mask_device(g, a, b, &ok));
+    if (!ok) return MRC_OK;   // :866-867
+    std::vector<uint8_t> mask((size_t)g->m);
+    CUDA_TRY(cudaMemcpyAsync(mask.data(), g->d_mask, (size_t)g->m, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    g->stats.d2h_bytes += g->m;
+    if (!zero_cycle_dfs(g, mask, cyc)) return MRC_OK;
+    MRC_TRY(cycle_weights_exact(g, cyc, sc, st));
+    *found = true;
+    return MRC_OK;
+}
+
+extern "C" int mrc_zero_cycle_exact(mrc_graph *g, int64_t a, int64_t b, uint8_t *found, int32_t *cycle,
+                                    int64_t cycle_cap, int64_t *cycle_len, int64_t *sum_cost, int64_t *sum_time) {
+    if (!g || !found) return set_err(MRC_ERR_ARG, "NULL argument");
+    if (!g->has_int) return set_err(MRC_ERR_NOT_INTEGER, "Exact mode requires integer weights");
+    std::vector<int> cyc;
+    bool f = false;
+    ll sc = 0, st = 0;
+    MRC_TRY(zero_cycle(g, a, b, &f, cyc, &sc, &st));
+    *found = f;
+    if (cycle_len) *cycle_len = f ? (int64_t)cyc.size() : 0;
+    if (f && cycle) for (size_t i = 0; i < cyc.size() && (int64_t)i < cycle_cap; i++) cycle[i] = cyc[i];
+    if (sum_cost) *sum_cost = sc;
+    if (sum_time) *sum_time = st;
+    return MRC_OK;
+}
+
+static ll gcd_ll(ll a, ll b) {
+    if (a < 0) a = -a;
+    if (b < 0) b = -b;
+    while (b) { ll t = a % b; a = b; b = t; }
+    return a;
+}
+static ll floordiv_ll(ll a, ll b) {
+    ll q = a / b, r = a % b;
+    return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+
+/*
+ * _stern_brocot_search (solver.py:734-797).  `neg(a,b)` answers _has_negative_cycle_exact and `zero(a,b)`
+ * answers _find_zero_cycle_exact's "is not None"; strategy 0 backs them with GPU probes, strategy 1 with
+ * exact comparisons against the lambda* found by Newton steps.
+ */
+extern "C" int mrc_solve_exact(mrc_graph *g, int64_t max_den, int64_t max_steps, int strategy, int32_t *cycle,
+                               int64_t cycle_cap, int64_t *cycle_len, int64_t *sum_cost, int64_t *sum_time,
+                               int64_t *a_out, int64_t *b_out, int64_t *iterations, int64_t *probes_ab,
+                               int64_t probes_cap, int64_t *nprobes) {
+    if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
+    if (!g->has_int) return set_err(MRC_ERR_NOT_INTEGER, "Exact mode requires integer weights");
+    if (max_den < 0) max_den = g->n * std::max<ll>(1, g->max_it);   // :746-748
+    if (max_steps < 0) max_steps = 2 * max_den + 10;                 // :750-751
+    ll aL = (ll)std::floor(g->min_ratio_i) - 1, bL = 1;              // :754-756
+    ll aR = (ll)std::ceil(g->max_ratio_i) + 1, bR = 1;
+    ll np = 0;
+    if (nprobes) *nprobes = 0;
+
+    // lambda* = ps/qs, known in advance only with strategy 1
+    ll ps = 0, qs = 1;
+    if (strategy == 1) {
+        ProbeOut r;
+        MRC_TRY(run_probe(g, true, 1, nullptr, &aL, &bL, 0.0, 0, &r));
+        if (r.verdict != MRC_V_NONNEG) {
+            if (probes_ab && probes_cap > 0) { probes_ab[0] = aL; probes_ab[1] = bL; }
+            if (nprobes) *nprobes = 1;
+            return set_err(MRC_ERR_LOWER_NEG, "Lower bound has negative cycle");
+        }
+        ll a = aR, b = bR;
+        bool first = true;
+        for (;;) {
+            g->stats.rounds++;
+            MRC_TRY(run_probe(g, true, 1, nullptr, &a, &b, 0.0, 0, &r));
+            if (r.verdict == MRC_V_NONNEG) {
+                if (first) {
+                    if (probes_ab && probes_cap > 1) { probes_ab[0] = aL; probes_ab[1] = bL; probes_ab[2] = aR; probes_ab[3] = bR; }
+                    if (nprobes) *nprobes = 2;
+                    return set_err(MRC_ERR_UPPER_NONNEG, "Upper bound has no negative cycle");
+                }
+                ps = a; qs = b;
+                break;
+            }
+            first = false;
+            if (r.verdict != MRC_V_NEG) return set_err(MRC_ERR_CONVERGENCE, "exact probe hit the pass limit without a cycle");
+            const ll gg = gcd_ll(r.isumc, r.isumt);
+            a = r.isumc / gg; b = r.isumt / gg;   // Newton step: lambda <- ratio of the extracted cycle
+        }
+    }
+    auto record = [&](ll a, ll b) {
+        if (probes_ab && np < probes_cap) { probes_ab[2 * np] = a; probes_ab[2 * np + 1] = b; }
+        np++;
+        if (nprobes) *nprobes = np;
+    };
+    auto neg = [&](ll a, ll b, bool *out) -> int {
+        record(a, b);
+        if (strategy == 1) { *out = (i128)a * qs > (i128)ps * b; return MRC_OK; }
+        ProbeOut r;
+        MRC_TRY(run_probe(g, true, 1, nullptr, &a, &b, 0.0, 0, &r));
+        *out = (r.verdict == MRC_V_NEG || r.verdict == MRC_V_NEG_NOCYCLE);
+        return MRC_OK;
+    };
+    std::vector<int> cyc;
+    ll sc = 0, st = 0;
+    auto zero = [&](ll a, ll b, bool *found) -> int {
+        if (strategy == 1 && (i128)a * qs != (i128)ps * b) { *found = false; return MRC_OK; }
+        if (strategy == 1) { a = ps; b = qs; }   // same tight subgraph at any positive scale of (a,b)
+        return zero_cycle(g, a, b, found, cyc, &sc, &st);
+    };
+    auto finish = [&](ll a, ll b, ll iters) -> int {
+        const ll gg = gcd_ll(a, b);
+        if (a_out) *a_out = floordiv_ll(a, gg);
+        if (b_out) *b_out = floordiv_ll(b, gg);
+        if (iterations) *iterations = iters;
+        if (cycle_len) *cycle_len = (int64_t)cyc.size();
+        if (cycle) for (size_t i = 0; i < cyc.size() && (int64_t)i < cycle_cap; i++) cycle[i] = cyc[i];
+        if (sum_cost) *sum_cost = sc;
+        if (sum_time) *sum_time = st;
+        return MRC_OK;
+    };
+    bool hn = false, found = false;
+    MRC_TRY(neg(aL, bL, &hn));
+    if (hn) return set_err(MRC_ERR_LOWER_NEG, "Lower bound has negative cycle");          // :759-760
+    MRC_TRY(neg(aR, bR, &hn));
+    if (!hn) return set_err(MRC_ERR_UPPER_NONNEG, "Upper bound has no negative cycle");   // :761-762
+    ll iters = 0;
+    for (ll step = 0; step < max_steps; step++) {   // :766
+        iters++;
+        if (strategy == 0) g->stats.rounds++;
+        ll aM = aL + aR, bM = bL + bR;              // :768
+        if (bM > max_den) {                         // :770-780
+            MRC_TRY(zero(aL, bL, &found));
+            if (found) return finish(aL, bL, -1);
+            ll k = std::max<ll>(1, floordiv_ll(max_den - bL, bR));
+            if ((i128)k * (aR < 0 ? -(i128)aR : (i128)aR) > ((i128)1 << 62) || (i128)k * bR > ((i128)1 << 62))
+                return set_err(MRC_ERR_OVERFLOW, "Stern-Brocot jump leaves int64");
+            aM = aL + k * aR; bM = bL + k * bR;
+        }
+        MRC_TRY(neg(aM, bM, &hn));                  // :782
+        if (hn) { aR = aM; bR = bM; continue; }     // :783-784
+        MRC_TRY(zero(aM, bM, &found));              // :787
+        if (found) return finish(aM, bM, iters);    // :788-793
+        aL = aM; bL = bM;                           // :795
+    }
+    return set_err(MRC_ERR_SB_STEPS, "Stern-Brocot search did not converge");   // :797
+}

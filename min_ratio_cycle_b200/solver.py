@@ -1,0 +1,691 @@
+"""
+Host-side mirror of the reference's solver interface (min_ratio_cycle/solver.py) with the parametric
+negative-cycle hot path running on a B200 through libmrc_b200.so (include/mrc_b200.h).
+
+What is kept identical to the reference (so this class is a drop-in for that path):
+  * types and defaults: SolverMode/LogLevel/SolverConfig/Edge/SolverMetrics/SolverResult (:46-172)
+  * MinRatioCycleSolver(n_vertices, config) with add_edge/add_edges/remove_edge/clear_edges (:193-333),
+    solve(mode, target_ratio, **kwargs) incl. its recovery ladder and error types (:581-679),
+    _solve_exact / _stern_brocot_search return conventions (:685-797), sensitivity_analysis (:1699-1729)
+  * private names other code reads: n, config, _edges, _all_int, _arrays_built, _U/_V/_C/_T/_Ci/_Ti
+    (destination-sorted, stable), _starts/_counts, _last_result, _build_numpy_arrays_once
+What replaces reference code: every `_detect_negative_cycle_numeric`, `_has_negative_cycle_exact`,
+`_compute_potentials_exact`, tight-mask and lambda-search call goes to the GPU library.  There is no
+CPU fallback: without the library or a CUDA device these methods raise.
+
+Additive (not in the reference): SolverConfig.gpu_* fields, add_edges_arrays() bulk ingestion,
+solve_exact_fraction().
+"""
+
+from __future__ import annotations
+
+import logging
+import math
+import time as _time
+from dataclasses import dataclass, field
+from enum import Enum
+from fractions import Fraction
+from typing import Any
+
+import numpy as np
+
+from . import _native as N
+from .exceptions import ConvergenceError, NumericalInstabilityError, ResourceExhaustionError, TimeoutError
+
+__version__ = "0.1.0"
+
+
+class SolverMode(Enum):
+    AUTO = "auto"
+    EXACT = "exact"
+    NUMERIC = "numeric"
+    APPROXIMATE = "approximate"
+
+
+class LogLevel(Enum):
+    NONE = 0
+    ERROR = 1
+    WARN = 2
+    INFO = 3
+    DEBUG = 4
+
+
+@dataclass
+class SolverConfig:
+    # reference fields and defaults (solver.py:69-100)
+    numeric_max_iter: int = 60
+    numeric_tolerance: float = 1e-12
+    numeric_cycle_slack: float = 1e-15
+    exact_max_denominator: int | None = None
+    exact_max_steps: int | None = None
+    sparse_threshold: float = 0.1
+    enable_preprocessing: bool = True
+    enable_early_termination: bool = True
+    validate_cycles: bool = True
+    repair_cycles: bool = True
+    log_level: LogLevel = LogLevel.INFO
+    collect_metrics: bool = True
+    use_kahan_summation: bool = True   # accepted for compatibility; the device update has no Kahan term
+    max_solve_time: float | None = None
+    max_memory_mb: int | None = None
+    # additive GPU knobs
+    gpu_device: int = 0
+    gpu_candidates: int = 4            # lambdas evaluated per relaxation launch (1..8)
+    gpu_exact_strategy: int = 1        # 0: every Stern-Brocot step probes the GPU; 1: Newton + replay
+    honor_mode: bool = False           # True: solve(mode="exact") really runs _solve_exact (reference ignores mode)
+
+
+@dataclass(frozen=True)
+class Edge:
+    u: int
+    v: int
+    cost: float | int | Fraction
+    time: float | int | Fraction
+
+    def __post_init__(self):
+        if not isinstance(self.u, int) or not isinstance(self.v, int):
+            raise ValueError("Vertex indices must be integers")
+        if self.u < 0 or self.v < 0:
+            raise ValueError("Vertex indices must be non-negative")
+        if self.time <= 0:
+            raise ValueError("Edge transit time must be strictly positive")
+
+
+@dataclass
+class SolverMetrics:
+    solve_time: float = 0.0
+    iterations: int = 0
+    mode_used: str = ""
+    preprocessing_time: float = 0.0
+    graph_properties: dict[str, Any] = field(default_factory=dict)
+    memory_peak: int | None = None
+
+
+@dataclass
+class SolverResult:
+    cycle: list[int]
+    sum_cost: float | Fraction
+    sum_time: float | Fraction
+    ratio: float | Fraction
+    success: bool = True
+    error_message: str = ""
+    metrics: SolverMetrics | None = None
+    config_used: SolverConfig | None = None
+
+    def __iter__(self):
+        return iter((self.cycle, self.sum_cost, self.sum_time, self.ratio))
+
+
+def _is_integral(x) -> bool:
+    """`_all_int` rule of the reference (solver.py:289-298): int, Fraction, or an integral float."""
+    return isinstance(x, (int, Fraction)) or (isinstance(x, float) and x.is_integer())
+
+
+class MinRatioCycleSolver:
+    """Minimum cost-to-time ratio cycle; lambda search and Bellman-Ford run on the GPU."""
+
+    def __init__(self, n_vertices: int, config: SolverConfig | None = None):
+        if not isinstance(n_vertices, int) or n_vertices <= 0:
+            raise ValueError("n_vertices must be a positive integer")
+        self.n = n_vertices
+        self.config = config or SolverConfig()
+        self._edges: list[Edge] = []
+        self._bulk: list[tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = []
+        self._setup_logging()
+        self._arrays_built = False
+        self._U = self._V = self._C = self._T = self._Ci = self._Ti = None
+        self._starts = self._counts = self._order = None
+        self._all_int = True
+        self._is_sparse = False
+        self._last_result: SolverResult | None = None
+        self._metrics = SolverMetrics() if self.config.collect_metrics else None
+        self._dev: N.DeviceGraph | None = None
+        self._last_exact: dict | None = None
+        self.logger.info("Initialized solver with %d vertices", n_vertices)
+
+    # ------------------------------------------------------------------ plumbing
+    def _setup_logging(self) -> None:
+        self.logger = logging.getLogger(f"{__name__}.{id(self)}")
+        level = {LogLevel.NONE: logging.CRITICAL + 1, LogLevel.ERROR: logging.ERROR, LogLevel.WARN: logging.WARNING,
+                 LogLevel.INFO: logging.INFO, LogLevel.DEBUG: logging.DEBUG}[self.config.log_level]
+        self.logger.setLevel(level)
+        if not self.logger.handlers and self.config.log_level != LogLevel.NONE:
+            h = logging.StreamHandler()
+            h.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s"))
+            self.logger.addHandler(h)
+
+    def _build_numpy_arrays_once(self) -> None:
+        self._build_arrays_if_needed()
+
+    def _invalidate(self) -> None:
+        self._arrays_built = False
+
+    def _num_edges(self) -> int:
+        return len(self._edges) + sum(len(b[0]) for b in self._bulk)
+
+    def __del__(self):
+        try:
+            if self._dev is not None:
+                self._dev.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ edge management (:267-333)
+    def add_edge(self, u: int, v: int, cost, time) -> None:
+        if not (0 <= u < self.n and 0 <= v < self.n):
+            raise ValueError("u and v must be valid vertex indices")
+        edge = Edge(u, v, cost, time)
+        if self._all_int and not (_is_integral(cost) and _is_integral(time)):
+            self._all_int = False
+        self._edges.append(edge)
+        self._invalidate()
+
+    def add_edges(self, edges) -> None:
+        for u, v, cost, time in edges:
+            self.add_edge(u, v, cost, time)
+
+    def add_edges_arrays(self, U, V, cost, time) -> None:
+        """
+        Bulk ingestion (additive; the reference only has the per-edge Python path, :267-310, which costs
+        minutes and GBs of Edge objects at 10^7 edges).  Edges added here come after all add_edge() edges
+        in insertion order.  Weights count as integers when every value is integral.
+        """
+        U = np.ascontiguousarray(U, dtype=np.int64)
+        V = np.ascontiguousarray(V, dtype=np.int64)
+        Cw = np.ascontiguousarray(cost, dtype=np.float64)
+        Tw = np.ascontiguousarray(time, dtype=np.float64)
+        if not (len(U) == len(V) == len(Cw) == len(Tw)):
+            raise ValueError("edge arrays must have equal length")
+        if len(U) == 0:
+            return
+        if U.min() < 0 or V.min() < 0 or U.max() >= self.n or V.max() >= self.n:
+            raise ValueError("u and v must be valid vertex indices")
+        if not np.all(Tw > 0):
+            raise ValueError("Edge transit time must be strictly positive")
+        if self._all_int and not (np.all(Cw == np.trunc(Cw)) and np.all(Tw == np.trunc(Tw))):
+            self._all_int = False
+        self._bulk.append((U, V, Cw, Tw))
+        self._invalidate()
+
+    def remove_edge(self, u: int, v: int) -> bool:
+        for i, e in enumerate(self._edges):
+            if e.u == u and e.v == v:
+                del self._edges[i]
+                self._invalidate()
+                return True
+        return False
+
+    def clear_edges(self) -> None:
+        self._edges.clear()
+        self._bulk.clear()
+        self._invalidate()
+
+    # ------------------------------------------------------------------ graph analysis (:339-444)
+    def get_graph_properties(self) -> dict[str, Any]:
+        if self._num_edges() == 0:
+            return {"error": "No edges in graph"}
+        self._build_arrays_if_needed()
+        n, m = self.n, len(self._U)
+        indeg = np.bincount(self._V, minlength=n)
+        outdeg = np.bincount(self._U, minlength=n)
+        density = m / (n * n)
+        return {
+            "vertices": n, "edges": m, "density": density, "is_sparse": density < self.config.sparse_threshold,
+            "connectivity": {
+                "isolated_vertices": int(np.sum((indeg == 0) & (outdeg == 0))),
+                "source_vertices": int(np.sum((indeg == 0) & (outdeg > 0))),
+                "sink_vertices": int(np.sum((indeg > 0) & (outdeg == 0))),
+                "avg_in_degree": float(indeg.mean()), "avg_out_degree": float(outdeg.mean()),
+                "max_in_degree": int(indeg.max()), "max_out_degree": int(outdeg.max()),
+            },
+            "weights": {
+                "all_integer": self._all_int,
+                "cost_range": (float(self._C.min()), float(self._C.max())),
+                "time_range": (float(self._T.min()), float(self._T.max())),
+                "cost_mean": float(self._C.mean()), "time_mean": float(self._T.mean()),
+                "cost_std": float(self._C.std()), "time_std": float(self._T.std()),
+            },
+        }
+
+    def detect_issues(self) -> list[dict[str, str]]:
+        props = self.get_graph_properties()
+        if "error" in props:
+            return [{"level": "ERROR", "message": props["error"]}]
+        issues = []
+        iso = props["connectivity"]["isolated_vertices"]
+        if iso > 0:
+            issues.append({"level": "WARNING", "message": f"{iso} isolated vertices (no cycles possible through them)"})
+        if props["density"] < 0.01:
+            issues.append({"level": "INFO", "message": f"Very sparse graph (density: {props['density']:.4f})"})
+        w = props["weights"]
+        if w["cost_range"][1] - w["cost_range"][0] > 1e10:
+            issues.append({"level": "WARNING", "message": "Very large cost range may cause numerical issues"})
+        if w["time_range"][0] > 0 and w["time_range"][1] / w["time_range"][0] > 1e6:
+            issues.append({"level": "WARNING", "message": "Very large time ratio may cause numerical issues"})
+        return issues
+
+    # ------------------------------------------------------------------ arrays + preprocessing (:450-575)
+    def _insertion_arrays(self):
+        m1 = len(self._edges)
+        U = np.fromiter((e.u for e in self._edges), dtype=np.int64, count=m1)
+        V = np.fromiter((e.v for e in self._edges), dtype=np.int64, count=m1)
+        Cw = np.fromiter((float(e.cost) for e in self._edges), dtype=np.float64, count=m1)
+        Tw = np.fromiter((float(e.time) for e in self._edges), dtype=np.float64, count=m1)
+        if self._bulk:
+            U = np.concatenate([U] + [b[0] for b in self._bulk])
+            V = np.concatenate([V] + [b[1] for b in self._bulk])
+            Cw = np.concatenate([Cw] + [b[2] for b in self._bulk])
+            Tw = np.concatenate([Tw] + [b[3] for b in self._bulk])
+        return U, V, Cw, Tw
+
+    def _build_arrays_if_needed(self) -> None:
+        """Destination-sorted COO + CSR-by-destination, then upload (replaces :450-511)."""
+        if self._arrays_built:
+            return
+        t0 = _time.time()
+        if self._num_edges() == 0:
+            self.logger.warning("No edges to build arrays from")
+            return
+        U, V, Cw, Tw = self._insertion_arrays()
+        order = np.argsort(V, kind="stable")
+        self._U, self._V, self._C, self._T = U[order], V[order], Cw[order], Tw[order]
+        self._order = order
+        self._counts = np.bincount(self._V, minlength=self.n)
+        self._starts = np.zeros(self.n, dtype=np.int64)
+        if self.n > 1:
+            np.cumsum(self._counts[:-1], out=self._starts[1:])
+        if self._all_int:
+            self._Ci = np.trunc(self._C).astype(np.int64)   # int(edge.cost), :493-498
+            self._Ti = np.trunc(self._T).astype(np.int64)
+        else:
+            self._Ci = self._Ti = None
+        self._is_sparse = len(U) / (self.n * self.n) < self.config.sparse_threshold
+        if self._dev is not None:
+            self._dev.close()
+        self._dev = N.DeviceGraph(self.n, self._U, self._V, self._C, self._T, self._Ci, self._Ti,
+                                  device=self.config.gpu_device)
+        self._arrays_built = True
+        if self._metrics:
+            self._metrics.preprocessing_time = _time.time() - t0
+
+    def _device(self) -> N.DeviceGraph:
+        self._build_arrays_if_needed()
+        if self._dev is None:
+            raise RuntimeError("Edge arrays must be initialized before solving")
+        return self._dev
+
+    def _preprocess_graph(self) -> None:
+        if not self.config.enable_preprocessing:
+            return
+        before = self._num_edges()
+        self._remove_dominated_edges()
+        if self._num_edges() != before:
+            self.logger.info("Preprocessing removed %d dominated edges", before - self._num_edges())
+            self._invalidate()
+
+    def _remove_dominated_edges(self) -> None:
+        """
+        Drop an edge when another edge with the same (u,v) has cost <= and time <= with one strict
+        (:531-575).  Vectorised: only (u,v) groups with more than one member are examined.
+        """
+        m = self._num_edges()
+        if m < 2:
+            return
+        U, V, Cw, Tw = self._insertion_arrays()
+        key = U * self.n + V
+        order = np.argsort(key, kind="stable")
+        ks = key[order]
+        dup = np.zeros(m, dtype=bool)
+        same = ks[1:] == ks[:-1]
+        dup[1:] |= same
+        dup[:-1] |= same
+        if not dup.any():
+            return
+        drop = np.zeros(m, dtype=bool)
+        idx = order[dup]
+        kd = ks[dup]
+        bounds = np.flatnonzero(np.concatenate([[True], kd[1:] != kd[:-1], [True]]))
+        for s, e in zip(bounds[:-1], bounds[1:]):
+            grp = idx[s:e]
+            c, t = Cw[grp], Tw[grp]
+            le = (c[:, None] <= c[None, :]) & (t[:, None] <= t[None, :])
+            lt = (c[:, None] < c[None, :]) | (t[:, None] < t[None, :])
+            drop[grp[(le & lt).any(axis=0)]] = True
+        if not drop.any():
+            return
+        m1 = len(self._edges)
+        self._edges = [e for i, e in enumerate(self._edges) if not drop[i]]
+        off = m1
+        kept = []
+        for b in self._bulk:
+            k = ~drop[off: off + len(b[0])]
+            off += len(b[0])
+            if k.any():
+                kept.append(tuple(a[k] for a in b))
+        self._bulk = kept
+
+    # ------------------------------------------------------------------ solve (:581-679)
+    def solve(self, mode: SolverMode | str = SolverMode.AUTO, target_ratio: float | None = None, **kwargs) -> SolverResult:
+        if isinstance(mode, str):
+            mode = SolverMode(mode)
+        t_start = _time.time()
+        if self.config.max_memory_mb is not None:
+            import psutil
+            mem = psutil.Process().memory_info().rss / (1024 * 1024)
+            if mem > self.config.max_memory_mb:
+                raise ResourceExhaustionError("Memory limit exceeded before solve", resource="memory",
+                                              limit=self.config.max_memory_mb, usage=mem,
+                                              suggested_fix="increase max_memory_mb")
+        self._preprocess_graph()
+        self._build_arrays_if_needed()
+        if self._num_edges() == 0:
+            raise ValueError("Graph has no edges")
+        run_exact = self.config.honor_mode and (mode == SolverMode.EXACT or (mode == SolverMode.AUTO and self._all_int))
+        actual = SolverMode.EXACT if run_exact else SolverMode.NUMERIC   # the reference always runs numeric (:622-623)
+        self.logger.info("Starting solve in %s mode", actual.value)
+        if run_exact:
+            result = self._solve_exact(**kwargs)
+        else:
+            try:
+                result = self._solve_numeric(target_ratio=target_ratio, **kwargs)
+            except (NumericalInstabilityError, ConvergenceError) as exc:
+                self.logger.warning("Numeric solve failed: %s", exc)
+                if self._all_int:
+                    result = self._solve_exact(**kwargs)          # :630-632
+                else:
+                    old = self.config.numeric_tolerance           # :634-638
+                    self.config.numeric_tolerance *= 10
+                    try:
+                        result = self._solve_numeric(target_ratio=target_ratio, **kwargs)
+                    finally:
+                        self.config.numeric_tolerance = old
+                if not result.success:
+                    raise NumericalInstabilityError("Solver failed in all recovery attempts", component="solve",
+                                                    suggested_fix="check input weights",
+                                                    recovery_hint="try exact mode or scale weights") from exc
+        if self.config.validate_cycles and result.success:
+            result = self._validate_result(result)
+        if self._metrics:
+            self._metrics.solve_time = _time.time() - t_start
+            self._metrics.mode_used = actual.value
+            self._metrics.graph_properties = self.get_graph_properties()
+            result.metrics = self._metrics
+        result.config_used = self.config
+        self._last_result = result
+        if not result.success:
+            self.logger.error("Solve failed: %s", result.error_message)
+            raise RuntimeError(result.error_message)
+        return result
+
+    # ------------------------------------------------------------------ exact mode (:685-995)
+    def _solve_exact(self, **kwargs) -> SolverResult:
+        fail = dict(cycle=[], sum_cost=0, sum_time=0, ratio=float("inf"), success=False)
+        if not self._all_int:
+            return SolverResult(error_message="Exact mode requires integer weights", **fail)
+        if self._Ci is None or self._Ti is None:
+            raise RuntimeError("Integer weight arrays (_Ci, _Ti) must be initialized before solving")
+        max_den = kwargs.get("max_denominator", self.config.exact_max_denominator)
+        max_steps = kwargs.get("max_steps", self.config.exact_max_steps)
+        try:
+            cycle, sum_c, sum_t, _ab, _r = self._stern_brocot_search(max_den, max_steps)
+            if cycle and (len(cycle) == 1 or cycle[0] != cycle[-1]):
+                cycle.append(cycle[0])
+            return SolverResult(cycle=cycle, sum_cost=float(sum_c), sum_time=float(sum_t),
+                                ratio=float(sum_c) / float(sum_t), success=True)
+        except Exception as exc:  # the reference swallows everything here (:724-732)
+            return SolverResult(error_message=f"Exact solver failed: {exc}", **fail)
+
+    def solve_exact_fraction(self, **kwargs):
+        """Additive: (closed cycle, Fraction(sum_cost, sum_time)) from the exact path, or raises RuntimeError."""
+        self._preprocess_graph()
+        self._build_arrays_if_needed()
+        r = self._solve_exact(**kwargs)
+        if not r.success:
+            raise RuntimeError(r.error_message)
+        return r.cycle, Fraction(int(r.sum_cost), int(r.sum_time))
+
+    def _stern_brocot_search(self, max_den, max_steps):
+        dev = self._device()
+        out = dev.solve_exact(max_den, max_steps, strategy=self.config.gpu_exact_strategy)
+        self._last_exact = out
+        if out["rc"] != N.OK:
+            raise RuntimeError(out["message"])
+        if self._metrics and out["iterations"] >= 0:
+            self._metrics.iterations = int(out["iterations"])
+        sc, st = int(out["sum_cost"]), int(out["sum_time"])
+        return list(out["cycle"]), sc, st, (int(out["a"]), int(out["b"])), sc / st
+
+    def _has_negative_cycle_exact(self, a: int, b: int) -> bool:
+        r = self._device().probe_exact([a], [b])[0]
+        return r["verdict"] in (N.V_NEG, N.V_NEG_NOCYCLE)
+
+    def _compute_potentials_exact(self, a: int, b: int):
+        return self._device().potentials_exact(a, b)
+
+    def _find_zero_cycle_exact(self, a: int, b: int):
+        z = self._device().zero_cycle_exact(a, b)
+        return None if z is None else (list(z[0]), int(z[1]), int(z[2]))
+
+    def _compute_cycle_weights_exact(self, cycle):
+        """Per hop the first-inserted (u,v) edge (:971-995); lookup through the CSR instead of a scan of _edges."""
+        self._build_arrays_if_needed()
+        sc = st = 0
+        L = len(cycle)
+        for i in range(L):
+            u, v = cycle[i], cycle[(i + 1) % L]
+            s = int(self._starts[v])
+            hit = np.flatnonzero(self._U[s: s + int(self._counts[v])] == u)
+            if hit.size == 0:
+                raise RuntimeError(f"Edge {u} -> {v} not found in cycle extraction")
+            sc += int(self._Ci[s + hit[0]])
+            st += int(self._Ti[s + hit[0]])
+        return cycle, sc, st
+
+    # ------------------------------------------------------------------ numeric mode (:1001-1337)
+    def _solve_numeric(self, target_ratio: float | None = None, **kwargs) -> SolverResult:
+        lambda_lo, lambda_hi = kwargs.get("lambda_lo"), kwargs.get("lambda_hi")
+        max_iter = kwargs.get("max_iter", self.config.numeric_max_iter)
+        tol = kwargs.get("tolerance", self.config.numeric_tolerance)
+        slack = kwargs.get("cycle_slack", self.config.numeric_cycle_slack)
+        try:
+            dev = self._device()
+            if lambda_lo is None or lambda_hi is None:
+                lo, hi = dev.bounds()                      # min/max of C/T -/+ 1 (:1019-1023)
+                lambda_lo = lambda_lo or lo                # sic (:1024-1025)
+                lambda_hi = lambda_hi or hi
+            if self.config.max_memory_mb is not None:
+                import psutil
+                mem = psutil.Process().memory_info().rss / (1024 * 1024)
+                if mem > self.config.max_memory_mb:
+                    raise ResourceExhaustionError("Numeric solve exceeded memory limit", resource="memory",
+                                                  limit=self.config.max_memory_mb, usage=mem)
+            t0 = _time.time()
+            limit = self.config.max_solve_time
+            out = dev.solve_numeric(lambda_lo, lambda_hi, max_iter, tol, slack, K=self.config.gpu_candidates,
+                                    max_seconds=-1.0 if limit is None else max(float(limit), 1e-300))
+            if out["rc"] == N.ERR_TIMEOUT:
+                raise TimeoutError("Numeric solve exceeded time limit", time_elapsed=_time.time() - t0,
+                                   time_limit=limit, operation="numeric_solve")
+            if out["rc"] == N.ERR_NO_CYCLE:
+                raise NumericalInstabilityError("No negative cycle found", component="numeric_solve")
+            cycle = [int(x) for x in out["cycle"]]
+            sum_cost, sum_time = self._compute_cycle_weights_float(cycle[:-1])   # reference hop rule (:1289)
+            if self._metrics:
+                self._metrics.iterations = int(out["iterations"])
+            if out["rc"] == N.ERR_CONVERGENCE:
+                raise ConvergenceError("Numeric solver failed to converge", algorithm_name="Lawler",
+                                       max_iterations=max_iter, tolerance=tol, final_error=out["hi"] - out["lo"])
+            return SolverResult(cycle=cycle, sum_cost=sum_cost, sum_time=sum_time, ratio=sum_cost / sum_time,
+                                success=True)
+        except Exception as exc:   # every failure surfaces as NumericalInstabilityError (:1119-1122)
+            raise NumericalInstabilityError("Numeric solver failed", component="numeric_solve") from exc
+
+    def _detect_negative_cycle_numeric(self, lam: float, slack: float = 0.0):
+        """(has_neg, (open cycle, sum_cost, sum_time, ratio) | None) like :1124-1294, via one GPU probe."""
+        r = self._device().probe_numeric([lam], slack)[0]
+        if r["verdict"] in (N.V_NONNEG, N.V_TIE):
+            return False, None
+        if r["verdict"] == N.V_NEG_NOCYCLE or not r["cycle"]:
+            return True, None
+        cycle = [int(x) for x in r["cycle"][:-1]]
+        sc, st = self._compute_cycle_weights_float(cycle)
+        if st <= 0:
+            return True, None
+        return True, (cycle, sc, st, sc / st)
+
+    def _compute_cycle_weights_float(self, cycle):
+        """
+        Per hop, among parallel (u,v) edges the first with minimal cost/time (:1309-1313), summed in cycle
+        order from 0.0.  Uses the current CSR arrays (the reference's dict is built once and goes stale,
+        SURVEY 0.8 -- deliberately not reproduced).
+        """
+        self._build_arrays_if_needed()
+        sc = st = 0.0
+        L = len(cycle)
+        for i in range(L):
+            u, v = cycle[i], cycle[(i + 1) % L]
+            s = int(self._starts[v])
+            hit = np.flatnonzero(self._U[s: s + int(self._counts[v])] == u)
+            if hit.size == 0:
+                raise RuntimeError(f"Edge {u} -> {v} not found in cycle")
+            if hit.size > 1:
+                k = s + hit[int(np.argmin(self._C[s + hit] / self._T[s + hit]))]
+            else:
+                k = s + hit[0]
+            sc += float(self._C[k])
+            st += float(self._T[k])
+        return sc, st
+
+    # ------------------------------------------------------------------ validation (:1495-1582)
+    def _verify_cycle_exists(self, cycle):
+        issues = []
+        for u, v in zip(cycle[:-1], cycle[1:]):
+            s = int(self._starts[v])
+            if not np.any(self._U[s: s + int(self._counts[v])] == u):
+                issues.append(f"Missing edge {u} -> {v}")
+        return not issues, issues
+
+    def _validate_result(self, result: SolverResult) -> SolverResult:
+        if not result.success or not result.cycle:
+            return result
+        try:
+            if len(result.cycle) < 3 and not self.config.repair_cycles:
+                result.success, result.error_message = False, "Cycle too short"
+                return result
+            ok, issues = self._verify_cycle_exists(result.cycle)
+            if not ok:
+                result.success = False
+                result.error_message = (f"Could not repair cycle: {', '.join(issues)}" if self.config.repair_cycles
+                                        else f"Invalid cycle: {', '.join(issues)}")
+                return result
+            c, t = self._compute_cycle_weights_float(result.cycle[:-1])
+            tol = 1e-10 if isinstance(result.ratio, (int, Fraction)) else 1e-6
+            if (abs(c - float(result.sum_cost)) > tol or abs(t - float(result.sum_time)) > tol
+                    or abs(c / t - float(result.ratio)) > tol):
+                if not self.config.repair_cycles:
+                    result.success, result.error_message = False, "Weight validation failed"
+                    return result
+                result.sum_cost, result.sum_time, result.ratio = c, t, c / t
+            return result
+        except Exception as exc:
+            result.success, result.error_message = False, f"Validation failed: {exc}"
+            return result
+
+    # ------------------------------------------------------------------ analytics (:1699-1759)
+    def sensitivity_analysis(self, edge_perturbations: list[dict[int, tuple[float, float]]]) -> list[SolverResult]:
+        """
+        One re-solve per scenario {edge index: (delta_cost, delta_time)} (:1699-1729).  Edge indices are
+        insertion-order indices into the (preprocessed) edge list, as in the reference.  The perturbation is
+        applied to the device-resident arrays (mrc_graph_patch_edges) instead of rebuilding Edge objects and
+        arrays per scenario; reported sums use the perturbed weights.
+        """
+        results: list[SolverResult] = []
+        self._preprocess_graph()
+        self._build_arrays_if_needed()
+        m = self._num_edges()
+        inv = np.empty(m, dtype=np.int64)
+        inv[self._order] = np.arange(m)
+        for scenario in edge_perturbations:
+            for idx in scenario:
+                if idx < 0 or idx >= m:
+                    raise IndexError("edge index out of range")
+            pos = inv[np.fromiter(scenario.keys(), dtype=np.int64, count=len(scenario))]
+            dc = np.array([float(d[0]) for d in scenario.values()], dtype=np.float64)
+            dt = np.array([float(d[1]) for d in scenario.values()], dtype=np.float64)
+            if np.any(self._T[pos] + dt <= 0):
+                raise ValueError("Edge transit time must be strictly positive")
+            saved = (self._C[pos].copy(), self._T[pos].copy(), self._all_int)
+            self._dev.patch_edges(pos, dc, dt)
+            self._C[pos] += dc
+            self._T[pos] += dt
+            try:
+                res = self._solve_numeric()
+                if self.config.validate_cycles:
+                    res = self._validate_result(res)
+                res.config_used = self.config
+                if self._metrics:
+                    res.metrics = SolverMetrics(iterations=self._metrics.iterations, mode_used="numeric")
+                results.append(res)
+            finally:
+                self._dev.restore()
+                self._C[pos], self._T[pos] = saved[0], saved[1]
+        return results
+
+    def stability_region(self, epsilon: float = 0.01) -> dict[int, bool]:
+        base = self._last_result if self._last_result is not None else self.solve()
+        self._build_arrays_if_needed()
+        m = self._num_edges()
+        U, V, Cw, Tw = self._insertion_arrays()
+        out: dict[int, bool] = {}
+        for idx in range(m):
+            res = self.sensitivity_analysis([{idx: (float(Cw[idx]) * epsilon, float(Tw[idx]) * epsilon)}])
+            out[idx] = res[0].cycle == base.cycle
+        return out
+
+    # ------------------------------------------------------------------ misc (:1631-1693, :1814-1933)
+    def get_debug_info(self) -> str:
+        lines = ["Min Ratio Cycle Solver - Debug Info", "=" * 50, f"Vertices: {self.n}",
+                 f"Edges: {self._num_edges()}", f"Integer weights: {self._all_int}"]
+        props = self.get_graph_properties()
+        if "error" not in props:
+            lines.append(f"Density: {props['density']:.4f}")
+            lines.append(f"Is sparse: {props['is_sparse']}")
+        for issue in self.detect_issues():
+            lines.append(f"  [{issue['level']}] {issue['message']}")
+        if self._last_result is not None and self._last_result.success:
+            lines.append(f"  Ratio: {self._last_result.ratio}")
+            lines.append(f"  Cycle length: {len(self._last_result.cycle) - 1}")
+        return "\n".join(lines)
+
+    def health_check(self) -> dict[str, Any]:
+        checks = []
+        ndev = N.device_count()
+        checks.append({"name": "cuda_device", "status": "PASS" if ndev > 0 else "FAIL",
+                       "details": f"{ndev} CUDA device(s)", "recommendation": None if ndev else "needs a B200"})
+        if self._num_edges() == 0:
+            checks.append({"name": "graph_state", "status": "WARN", "details": "No edges in graph",
+                           "recommendation": "Add edges before solving"})
+        else:
+            warn = sum(1 for i in self.detect_issues() if i["level"] == "WARNING")
+            checks.append({"name": "graph_state", "status": "WARN" if warn else "PASS",
+                           "details": f"{warn} warnings found" if warn else "Graph structure looks good",
+                           "recommendation": "Review warnings" if warn else None})
+        n_pass = sum(c["status"] == "PASS" for c in checks)
+        n_warn = sum(c["status"] == "WARN" for c in checks)
+        n_fail = sum(c["status"] == "FAIL" for c in checks)
+        return {"timestamp": _time.time(), "checks": checks,
+                "summary": {"total": len(checks), "passed": n_pass, "warnings": n_warn, "failures": n_fail,
+                            "overall_status": "FAIL" if n_fail else ("WARN" if n_warn else "PASS")}}
+
+    def __repr__(self) -> str:
+        return f"MinRatioCycleSolver(n_vertices={self.n}, n_edges={self._num_edges()}, integer_mode={self._all_int})"
+
+
+def solve_min_ratio_cycle(edges, n_vertices: int | None = None, mode: SolverMode | str = SolverMode.AUTO,
+                          config: SolverConfig | None = None) -> SolverResult:
+    """Convenience wrapper (:1941-1969)."""
+    if n_vertices is None:
+        n_vertices = max((max(u, v) for u, v, _, _ in edges), default=0) + 1
+    solver = MinRatioCycleSolver(n_vertices, config)
+    solver.add_edges(edges)
+    return solver.solve(mode=mode)

@@ -46,6 +46,7 @@ typedef struct {
     int64_t *starts, *counts;/* CSR by destination, solver.py:481-485 */
     int64_t *order;          /* sorted position -> insertion index */
     int nthreads;
+    int ref_quirks;          /* 1 = reproduce reference defects that change verdicts (default); 0 = textbook Jacobi */
 } orc_graph;
 
 int orc_max_threads(void) {
@@ -113,7 +114,7 @@ orc_graph *orc_graph_build(int64_t n, int64_t m, const int64_t *u, const int64_t
     orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
     if (!g) return NULL;
     size_t mm = (size_t)(m > 0 ? m : 1), nn = (size_t)(n > 0 ? n : 1);
-    g->n = n; g->m = m; g->nthreads = 1;
+    g->n = n; g->m = m; g->nthreads = 1; g->ref_quirks = 1;
     g->U = (int64_t *)malloc(8 * mm); g->V = (int64_t *)malloc(8 * mm);
     g->C = (double *)malloc(8 * mm); g->T = (double *)malloc(8 * mm);
     g->order = (int64_t *)malloc(8 * mm);
@@ -137,6 +138,8 @@ orc_graph *orc_graph_build(int64_t n, int64_t m, const int64_t *u, const int64_t
 }
 
 void orc_graph_set_threads(orc_graph *g, int nthreads) { g->nthreads = nthreads > 0 ? nthreads : 1; }
+/* quirks off = the certifying checker of SURVEY 7 step 2(b): same arithmetic, defects removed */
+void orc_graph_set_quirks(orc_graph *g, int on) { g->ref_quirks = on ? 1 : 0; }
 int64_t orc_graph_m(const orc_graph *g) { return g->m; }
 void orc_graph_arrays(const orc_graph *g, int64_t *U, int64_t *V, double *C, double *T, int64_t *starts,
                       int64_t *counts, int64_t *order) {
@@ -205,7 +208,7 @@ static int orc_relax_numeric(const orc_graph *g, const double *W, double slack, 
         /* Reference quirk (:1179-1183): base[1:] = cs[starts[1:] - 1] wraps to cs[-1] for every v
          * with starts[v] == 0, so when vertex 0 has no in-edge the FIRST non-empty segment never
          * gets a first_mask hit and that vertex is never updated. */
-        if (s == 0 && v > 0) bi = -1;
+        if (g->ref_quirks && s == 0 && v > 0) bi = -1;
         best[v] = b; bidx[v] = bi;
         if (bi >= 0) any = 1;
     }
@@ -411,7 +414,7 @@ static int orc_relax_exact(const orc_graph *g, const int64_t *W, int64_t *dist, 
         if (imp) any = 1;
     }
     if (!any) return 0;                                                /* :834-835 */
-    if (g->counts[n - 1] == 0) return -1;                              /* reduceat IndexError, :839 */
+    if (g->ref_quirks && g->counts[n - 1] == 0) return -1;             /* reduceat IndexError, :839 */
     for (int64_t v = 0; v < n; v++) if (best[v] != INT64_MAX) dist[v] = best[v];   /* :847-848 */
     return 1;
 }
