@@ -1,0 +1,313 @@
+"""
+bench.py -- headline benchmark of the parametric negative-cycle hot path (BASELINE.json).
+
+Workload (configs[2], the one the metric is quoted on): random simple digraph n=1,000,000 m=10,000,000,
+cost ~ U(-10,10), time ~ U(0.1,5), seed 0 (SURVEY.md 8d "C3"); numeric multisection solve, lambda
+candidates sharded over the GPUs (K_local per GPU per round).
+
+A "step" = one full solve() of that graph: every relaxation pass, cycle check and lambda round until
+hi - lo <= 1e-12.  metric = edge relaxations per second (one relaxation = evaluate
+cand = dist[src] + cost - lambda*time and min-update dist[dst] for ONE lambda), whole job over all GPUs.
+  value : edge arrays already resident in HBM when the timed region starts
+  e2e   : same metric through the C-ABI with HOST buffers: mrc_graph_create (H2D of the edge arrays from
+          pinned memory) + solve + result D2H + destroy inside the timed region, every step
+  roofline : relaxation kernel, algorithmic bytes = 24 B/edge/pass (+16*n*K only if 8*n*K > L2) over its
+             CUDA-event time measured inside the timed steps, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : oracle port (bug-compatible Jacobi pass of the reference) on the host cores, bounded sample
+
+--impl reference times the reference's CPU algorithm (oracle port, all host threads) on the same graph.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_VERT, N_EDGE, SEED = 1_000_000, 10_000_000, 0
+METRIC = "edge relaxations/s, numeric lambda-search solve(), random digraph n=1M m=10M"
+UNIT = "G edge-relax/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def make_workload(n=N_VERT, m=N_EDGE, seed=SEED):
+    from min_ratio_cycle_b200 import synthetic
+    n, U, V, C, T = synthetic.random_float(n, m, seed=seed)
+    order = np.argsort(V, kind="stable")          # reference layout, solver.py:476-478
+    return n, U[order], V[order], C[order], T[order]
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_baseline_sample(n, U, V, C, T, lam, passes, threads):
+    """Oracle port: `passes` Jacobi passes of the reference's relax_once_kahan on the host."""
+    from oracle import oracle
+    o = oracle.Oracle(n, U, V, C, T, all_int=False, preprocess=False, threads=threads)
+    o.time_passes_numeric(lam, 1)                  # touch memory
+    t0 = time.perf_counter()
+    done = o.time_passes_numeric(lam, passes)
+    dt = time.perf_counter() - t0
+    return done * len(U) / dt / 1e9, done, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU algorithm (oracle port) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    threads = oracle.lib().orc_max_threads()
+    n, U, V, C, T = make_workload()
+    o = oracle.Oracle(n, U, V, C, T, all_int=False, preprocess=False, threads=threads)
+    lo, hi = o.bounds()
+    lam = (lo + hi) / 2.0
+    P = 8
+    for _ in range(max(args.warmup, 1)):
+        o.time_passes_numeric(lam, 1)
+    times, relax = [], 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        done = o.time_passes_numeric(lam, P)
+        times.append(time.perf_counter() - t0)
+        relax += done * len(U)
+    total = sum(times)
+    val = relax / total / 1e9
+    sample = f"{P} Jacobi passes (relax_once_kahan restated in C, OpenMP over destinations) at lambda=(lo+hi)/2 per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 random digraph n=1M m=10M f64, numeric", "n": n, "m": len(U), "seed": SEED},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--klocal", type=int, default=4, help="lambda candidates per GPU per round")
+    ap.add_argument("--n", type=int, default=N_VERT)
+    ap.add_argument("--m", type=int, default=N_EDGE)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    from min_ratio_cycle_b200 import _native as N
+    from min_ratio_cycle_b200 import sharded
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, U, V, C, T = make_workload(args.n, args.m)
+    m = len(U)
+    # pinned host copies for the e2e leg
+    pin = [torch.from_numpy(a).pin_memory() for a in (U.astype(np.int32), V.astype(np.int32), C, T)]
+    pU, pV, pC, pT = [p.numpy() for p in pin]
+    g = N.DeviceGraph(n, pU, pV, pC, pT, device=local_rank)
+    lo0, hi0 = g.bounds()
+    K = args.klocal
+    tol, slack, max_iter = 1e-12, 1e-15, 60
+
+    def probe(lams, slack_, flags):
+        return g.probe_numeric(lams, slack_, flags)
+
+    def one_solve(graph):
+        if world == 1:
+            return graph.solve_numeric(lo0, hi0, max_iter, tol, slack, K=K)
+        r = sharded.solve_numeric_sharded(lambda l, s, f: graph.probe_numeric(l, s, f), lo0, hi0, max_iter, tol,
+                                          slack, K_local=K)
+        return dict(rc=r.rc, ratio=r.ratio, cycle=r.cycle, iterations=r.iterations)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg
+    for _ in range(args.warmup):
+        out = one_solve(g)
+    barrier()
+    g.reset_stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = one_solve(g)
+    torch.cuda.synchronize()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    st = g.stats()
+    loc = torch.tensor([dev_s, wall, float(st["relax_edge_visits"]), float(st["relax_launches"]), st["relax_ms"],
+                        float(st["relax_launches"] + st["check_launches"] + st["other_launches"]),
+                        st["check_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        allv = [torch.zeros_like(loc) for _ in range(world)]
+        dist.all_gather(allv, loc)
+        allv = torch.stack(allv).cpu().numpy()
+    else:
+        allv = loc.cpu().numpy()[None, :]
+    t_max = float(allv[:, 0].max())
+    relax_total = float(allv[:, 2].sum())
+    value = relax_total / t_max / 1e9
+    launches = int(allv[:, 5].sum())
+
+    # ---------------- e2e leg: host buffers through the C ABI, every step
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = m * 24
+    barrier()
+    e2e_relax = 0.0
+    for i in range(1 + e2e_steps):
+        if i == 1:
+            barrier()
+            t0 = time.perf_counter()
+        g2 = N.DeviceGraph(n, pU, pV, pC, pT, device=local_rank)
+        o2 = one_solve(g2)
+        if i >= 1:
+            e2e_relax += g2.stats()["relax_edge_visits"]
+        d2h = g2.stats()["d2h_bytes"]
+        g2.close()
+    torch.cuda.synchronize()
+    e2e_t = time.perf_counter() - t0
+    loc = torch.tensor([e2e_t, e2e_relax], dtype=torch.float64, device="cuda")
+    if world > 1:
+        allv2 = [torch.zeros_like(loc) for _ in range(world)]
+        dist.all_gather(allv2, loc)
+        allv2 = torch.stack(allv2).cpu().numpy()
+    else:
+        allv2 = loc.cpu().numpy()[None, :]
+    e2e_val = float(allv2[:, 1].sum()) / float(allv2[:, 0].max()) / 1e9
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        relax_launches = float(allv[0, 3])
+        relax_ms = float(allv[0, 4])
+        bytes_per_launch = 24.0 * m + (16.0 * n * K if 8.0 * n * K > L2_BYTES else 0.0)
+        achieved = bytes_per_launch * relax_launches / (relax_ms * 1e-3) / 1e9 if relax_ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "relax_traffic.json")) as fh:
+                traffic = json.load(fh).get(f"K{K}")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 random digraph n=1M m=10M f64, numeric multisection", "n": n, "m": m,
+                       "seed": SEED, "lambda_candidates_per_gpu": K, "tolerance": tol,
+                       "l2": "edge arrays 240 MB > 126 MB L2, streamed every pass (no flush needed)",
+                       "parallelism": f"lambda-candidate sharding x{world}"},
+            "solve_ms": 1e3 * t_max / args.steps, "ratio": out["ratio"], "rounds": out["iterations"],
+            "cycle_len": len(out["cycle"]) - 1, "wall_ms_per_step": 1e3 * wall / args.steps,
+            "relax_passes_per_step": relax_launches / args.steps,
+            "relax_us_per_pass": 1e3 * relax_ms / max(relax_launches, 1),
+            "relax_share_of_step": relax_ms * 1e-3 / float(allv[0, 0]),
+            "check_share_of_step": float(allv[0, 6]) * 1e-3 / float(allv[0, 0]),
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * float(allv2[:, 0].max()) / e2e_steps, "steps": e2e_steps,
+                    "path": "mrc_graph_create(pinned host arrays) + mrc_solve_numeric + mrc_graph_destroy"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_kind": peak_kind, "kernel": f"relax_kernel<K={K if K in (1,2,4,8) else 8},f64>",
+                         "bytes_per_launch": bytes_per_launch, "frac_of_8TBs_nominal": achieved / 8000.0},
+        }
+        if not args.no_cpu_baseline:
+            lam = (lo0 + hi0) / 2.0
+            v1, d1, t1 = cpu_baseline_sample(n, U, V, C, T, lam, 6, 1)
+            line["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{d1} Jacobi passes (reference relax_once_kahan restated in C) at "
+                                              f"lambda=(lo+hi)/2 on the same graph, {t1:.1f}s"}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

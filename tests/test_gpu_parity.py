@@ -97,7 +97,7 @@ def test_kat_errors(mrc):
         s.add_edge(0, 1, 1.0, 0.0)
     with pytest.raises(ValueError):
         s.add_edge(0, 7, 1.0, 1.0)
-    s2 = facade(mrc, 3, KAT["triangle"]["edges"], max_solve_time=0.0)
+    s2 = facade(mrc, 3, KAT["float_triangle"]["edges"], max_solve_time=0.0)   # non-integer: no exact fallback
     with pytest.raises(NumericalInstabilityError) as ei:
         s2.solve()
     assert type(ei.value.__cause__).__name__ == "TimeoutError"

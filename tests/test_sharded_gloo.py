@@ -1,0 +1,105 @@
+"""
+World-size-2 test of the multi-GPU lambda-sharding driver on CPU with the gloo backend.
+The collective logic (candidate split, all-gather of verdicts, bracket folding, cycle broadcast) is the
+product code in min_ratio_cycle_b200/sharded.py; the probe is injected and answered by the CPU oracle
+(test infrastructure), because there is no GPU here.
+"""
+
+from __future__ import annotations
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_probe_factory(o, N):
+    def probe(lams, slack, flags):
+        out = []
+        for lam in lams:
+            r = o.detect_negative_cycle_numeric(float(lam), slack, True)
+            if r.has_neg and r.cycle is not None:
+                cyc = list(r.cycle)
+                k = cyc.index(min(cyc))
+                cyc = cyc[k:] + cyc[:k]
+                sc, st = o.cycle_weights_float(cyc)
+                out.append(dict(lam=float(lam), verdict=N.V_NEG, cycle=cyc + [cyc[0]], sum_cost=sc, sum_time=st, passes=0))
+            elif r.has_neg:
+                out.append(dict(lam=float(lam), verdict=N.V_NEG_NOCYCLE, cycle=None, sum_cost=0.0, sum_time=0.0, passes=0))
+            else:
+                out.append(dict(lam=float(lam), verdict=N.V_NONNEG, cycle=None, sum_cost=0.0, sum_time=0.0, passes=0))
+        return out
+    return probe
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from min_ratio_cycle_b200 import _native as N
+        from min_ratio_cycle_b200 import sharded, synthetic
+        from oracle import oracle
+        res = {}
+        for seed in (1, 2):
+            n, U, V, C, T = synthetic.ring_plus_random(40, 120, seed=seed)
+            o = oracle.Oracle(n, U, V, C, T, all_int=False)
+            o.set_quirks(False)
+            lo, hi = o.bounds()
+            r = sharded.solve_numeric_sharded(_oracle_probe_factory(o, N), lo, hi, K_local=3)
+            ok, why = o.certify(r.cycle, r.ratio)
+            res[seed] = (r.rc, r.cycle, r.ratio, r.iterations, r.lo, r.hi, ok, why)
+        # acyclic graph: every rank must agree on NO_CYCLE
+        U = np.array([0, 1, 2]); V = np.array([1, 2, 3])
+        o = oracle.Oracle(4, U, V, np.array([1.5, -2.0, 0.5]), np.array([1.0, 1.0, 2.0]), all_int=False)
+        o.set_quirks(False)
+        lo, hi = o.bounds()
+        r = sharded.solve_numeric_sharded(_oracle_probe_factory(o, N), lo, hi, K_local=2)
+        res["acyclic"] = r.rc
+        res["units"] = list(sharded.shard_units(11, rank, world))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_lambda_sharding_world2():
+    from min_ratio_cycle_b200 import build
+    build.build()
+    from oracle import oracle
+    oracle.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from min_ratio_cycle_b200 import _native as N
+    for seed in (1, 2):
+        a, b = got[0][seed], got[1][seed]
+        assert a == b, "ranks disagree"
+        rc, cycle, ratio, iters, lo, hi, ok, why = a
+        assert rc == N.OK and ok, why
+        assert hi - lo <= 1e-12 and cycle[0] == cycle[-1]
+        assert iters <= 12
+    assert got[0]["acyclic"] == got[1]["acyclic"] == N.ERR_NO_CYCLE
+    assert got[0]["units"] + got[1]["units"] == list(range(11))
