@@ -67,6 +67,7 @@ typedef struct mrc_stats {
     double check_ms;              /* CUDA-event time spent in cycle checks */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
+    int64_t false_cycles_cut;     /* predecessor-graph cycles that did not verify negative and were cut */
 } mrc_stats;
 
 int mrc_abi_version(void);
@@ -126,7 +127,7 @@ int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int max_iter, double t
 /* Pure host helpers shared by mrc_solve_numeric and the multi-GPU driver (one process per GPU, the
  * candidates of a round split across ranks, verdicts all-gathered): no device work.
  * plan: writes K_total candidates in increasing order for the bracket [lo, hi]; have_cycle says whether
- *       hi is the ratio of a known cycle (then the last candidate is the certifier hi - min(tol/2, gap/(2K))).
+ *       hi is the ratio of a known cycle (then the last candidate is the certifier hi - min(0.75*tol, gap/(2K))).
  * reduce: folds K_total (lambda, verdict, ratio-of-extracted-cycle) records into the new bracket; returns
  *       in *best_idx the record whose cycle is the new best (or -1). */
 int mrc_plan_candidates(double lo, double hi, int have_cycle, double tol, int K_total, double *lam_out);

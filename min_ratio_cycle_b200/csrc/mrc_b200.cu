@@ -209,8 +209,8 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
                 int occ = 0;
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, relax_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
                 if (occ < 1) return set_err(MRC_ERR_CUDA, "relax kernel K=%d does not fit on an SM", KT);
-                ll need = ((m >> 2) + MRC_RELAX_THREADS - 1) / MRC_RELAX_THREADS;
-                need = std::max<ll>(need, 1);
+                const ll chunks = (m + 32 * MRC_ROWS - 1) / (32 * MRC_ROWS);   // one chunk per warp step
+                ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
                 g->relax_blocks[kt_index(KT)][ex] = (int)std::min<ll>(need, (ll)occ * g->sms);
             }
         for (int KT : {1, 2, 4, 8}) {
@@ -332,7 +332,7 @@ static int launch_check(mrc_graph *g, int KT, const CheckArgs &ca) {
  * small D2H of the status block.  A candidate is decided when
  *   - some pass of the burst changed nothing for it            -> NONNEG (true fixed point)
  *   - the predecessor graph holds a cycle that verifies negative-> NEG
- *   - (numeric) the cycle's ratio is >= lambda but within rounding of it -> TIE
+ *   - (numeric) the cycle's ratio is >= lambda but within the rounding noise of the walk -> TIE
  *   - n passes done and still relaxing (reference rule :1252-1257)       -> NEG_NOCYCLE
  */
 static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
@@ -358,14 +358,14 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     ra.src = g->d_src; ra.dst = g->d_dst; ra.cost = g->d_cost; ra.time = g->d_time;
     ra.icost = g->d_icost; ra.itime = g->d_itime; ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = m;
     ra.slack = slack;
-    for (int k = 0; k < K; k++) {
-        if (exact) { ra.a[k] = a[k]; ra.b[k] = b[k]; } else ra.lam[k] = lam[k];
-        res[k] = ProbeOut();
-    }
     CheckArgs ca;
     memset(&ca, 0, sizeof ca);
+    for (int k = 0; k < K; k++) {
+        if (exact) { ra.a[k] = ca.a[k] = a[k]; ra.b[k] = ca.b[k] = b[k]; } else ra.lam[k] = ca.lam[k] = lam[k];
+        res[k] = ProbeOut();
+    }
     ca.src = g->d_src; ca.cost = g->d_cost; ca.time = g->d_time; ca.icost = g->d_icost; ca.itime = g->d_itime;
-    ca.pred = g->d_pred; ca.jump = g->d_jump; ca.cyc_edges = g->d_cyc_edges; ca.st = g->d_status;
+    ca.pred = g->d_pred; ca.dist = g->d_dist; ca.jump = g->d_jump; ca.cyc_edges = g->d_cyc_edges; ca.st = g->d_status;
     ca.n = n; ca.cap = g->cyc_cap; ca.exact = exact;
     { int r = 1; while (((ll)1 << r) < n + 1) r++; ca.rounds = std::min(r + 1, MRC_MAX_ROUNDS); }
 
@@ -404,6 +404,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         g->stats.relax_launches += nb;
         g->stats.relax_edge_visits += (int64_t)nb * m * __builtin_popcount(active);
         g->stats.check_launches++;
+        g->stats.false_cycles_cut += g->h_status->cuts;
         g->stats.d2h_bytes += sizeof(DevStatus);
         const DevStatus &hs = *g->h_status;
         for (int k = 0; k < K; k++) {
@@ -413,17 +414,11 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
             ProbeOut &o = res[k];
             if (conv) { o.verdict = MRC_V_NONNEG; }
             else if (((hs.cyc_mask >> k) & 1u) && hs.out[k].found) {
+                // the check kernel extracted a cycle and tested it against lambda on the device:
+                // found == 1 verified negative, 2 rounding tie; cycles that are neither were cut there
                 const CycleOut &c = hs.out[k];
-                if (exact) {
-                    if ((i128)b[k] * c.isumc - (i128)a[k] * c.isumt < 0) o.verdict = MRC_V_NEG;
-                } else if (c.sumt > 0) {
-                    const double r = c.sumc / c.sumt;
-                    if (r < lam[k]) o.verdict = MRC_V_NEG;
-                    else if (r - lam[k] <= 1e-12 * std::max(1.0, std::fabs(lam[k]))) o.verdict = MRC_V_TIE;
-                }
-                if (o.verdict >= 0) {
-                    o.len = c.len; o.minv = c.minv; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
-                }
+                o.verdict = (c.found == 1) ? MRC_V_NEG : MRC_V_TIE;
+                o.len = c.len; o.minv = c.minv; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
             }
             if (o.verdict >= 0) { o.passes = passes; active &= ~(1u << k); }
         }
@@ -554,7 +549,7 @@ extern "C" int mrc_plan_candidates(double lo, double hi, int have_cycle, double 
     }
     // hi is the ratio of a known cycle: K-1 interior points + the certifier just below hi.  If the
     // certifier has no negative cycle, the known cycle is optimal to within tol and the search ends.
-    const double cert = hi - std::min(tol * 0.5, gap / (2.0 * K));
+    const double cert = hi - std::min(tol * 0.75, gap / (2.0 * K));
     if (K == 1) { lam_out[0] = cert; return MRC_OK; }
     for (int j = 1; j < K; j++) lam_out[j - 1] = lo + gap * ((double)j / (double)K);
     lam_out[K - 1] = cert;
@@ -841,7 +836,7 @@ extern "C" int mrc_solve_exact(mrc_graph *g, int64_t max_den, int64_t max_steps,
                 break;
             }
             first = false;
-            if (r.verdict != MRC_V_NEG) return set_err(MRC_ERR_CONVERGENCE, "exact probe hit the pass limit without a cycle");
+            if (r.verdict != MRC_V_NEG) { strategy = 0; break; }   // pass limit without an extracted cycle: probe every step instead
             const ll gg = gcd_ll(r.isumc, r.isumt);
             a = r.isumc / gg; b = r.isumt / gg;   // Newton step: lambda <- ratio of the extracted cycle
         }

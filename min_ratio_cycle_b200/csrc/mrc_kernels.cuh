@@ -7,7 +7,7 @@
 //                        pointer doubling + a walk that sums cost/time over the edges actually used
 //   tight_mask_kernel <- equal_mask of _find_zero_cycle_exact (:878-879)
 //
-// Data layout in HBM (all structure-of-arrays, 16-byte aligned):
+// Data layout in HBM (all structure-of-arrays, 256-byte aligned):
 //   src,dst  int32[m]   destination-sorted (reference order, solver.py:476-478)
 //   cost,time f64[m]    /  icost,itime int64[m] (exact mode)            -> 24 B per edge per pass
 //   dist     T[n][KT]   candidate-minor: the KT lambdas of one vertex share a 32/64/128-B sector group,
@@ -44,16 +44,17 @@ struct RelaxArgs {
 };
 
 struct CycleOut {
-    int found, len, minv, pad;
+    int found, len, minv, pad;   // found: 0 none, 1 verified negative, 2 tie (rounding artefact)
     double sumc, sumt;   // numeric: sums along the predecessor walk
+    double maxabs;       // numeric: max |dist| over the cycle's vertices (bounds the rounding noise of the walk)
     ll isumc, isumt;     // exact
 };
 
 struct DevStatus {
     unsigned changed[MRC_MAX_BURST];
     unsigned alive[MRC_MAX_ROUNDS];
-    unsigned cyc_mask, rounds_run;
-    int rep[MRC_KMAX];
+    unsigned cyc_mask, rounds_run, pend, cuts;
+    int rep[MRC_KMAX * 6];   // [MRC_MAX_EXTRACT][MRC_KMAX]
     CycleOut out[MRC_KMAX];
 };
 
@@ -61,7 +62,8 @@ struct CheckArgs {
     const int *src;
     const double *cost, *time;
     const ll *icost, *itime;
-    const int *pred;
+    int *pred;           // written only to cut a false cycle
+    const void *dist;
     int *jump;
     int *cyc_edges;      // [KT][cap]
     DevStatus *st;
@@ -69,6 +71,8 @@ struct CheckArgs {
     int rounds;          // ceil(log2(n+1)) + 1
     unsigned active;
     int exact;
+    double lam[MRC_KMAX];
+    ll a[MRC_KMAX], b[MRC_KMAX];
 };
 
 // ---- cache-hinted accessors --------------------------------------------------------------------
@@ -86,9 +90,16 @@ template <> struct DistVec<2> {
         longlong2 v = __ldcg(reinterpret_cast<const longlong2 *>(p)); r[0] = v.x; r[1] = v.y;
     }
 };
+// 256-bit global loads (sm_100+, SASS LDG.E.256): the four candidates of a vertex arrive in ONE request,
+// so a K=4 gather costs the same L1TEX wavefront as a K=1 gather.
 template <> struct DistVec<4> {
-    template <typename T> static __device__ __forceinline__ void load(T *r, const T *p) {
-        DistVec<2>::load(r, p); DistVec<2>::load(r + 2, p + 2);
+    static __device__ __forceinline__ void load(double *r, const double *p) {
+        asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+    }
+    static __device__ __forceinline__ void load(ll *r, const ll *p) {
+        asm volatile("ld.global.cg.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3]) : "l"(p));
     }
 };
 template <> struct DistVec<8> {
@@ -97,90 +108,120 @@ template <> struct DistVec<8> {
     }
 };
 
-// ---- one edge, K candidates --------------------------------------------------------------------
+// ---- one row of 32 consecutive edges, K candidates ------------------------------------------------------
 // numeric: w = cost - lam*time with a rounded product and a rounded difference (no FMA), exactly as
 // NumPy evaluates `self._C - lam * self._T` (solver.py:1144); improve test `cand < dist[v] - slack`
 // (:1161).  dist <= 0 always (starts at +0.0, only decreases), so for negative doubles
 // "smaller value" == "larger bit pattern": atomicMax on the raw bits is a 64-bit atomic min.
-template <int K>
-__device__ __forceinline__ void relax_edge(const RelaxArgs &p, int e, int u, int v, double c, double t,
-                                           unsigned &chg) {
-    double du[K], dv[K];
-    double *dist = static_cast<double *>(p.dist);
-    DistVec<K>::load(du, dist + (size_t)u * K);
-    DistVec<K>::load(dv, dist + (size_t)v * K);
+// exact: w = b*icost - a*itime in int64 (solver.py:799-800), strict < without slack (:833).
+__device__ __forceinline__ double mrc_cand(const RelaxArgs &p, int k, double du, double c, double t) {
+    return __dadd_rn(du, __dsub_rn(c, __dmul_rn(p.lam[k], t)));
+}
+__device__ __forceinline__ ll mrc_cand(const RelaxArgs &p, int k, ll du, ll c, ll t) {
+    return du + (p.b[k] * c - p.a[k] * t);
+}
+__device__ __forceinline__ bool mrc_improves(const RelaxArgs &p, double cand, double dv) {
+    return cand < __dsub_rn(dv, p.slack);
+}
+__device__ __forceinline__ bool mrc_improves(const RelaxArgs &, ll cand, ll dv) { return cand < dv; }
+__device__ __forceinline__ bool mrc_atomic_lower(double *addr, double cand) {
+    const ull bits = (ull)__double_as_longlong(cand);
+    return atomicMax(reinterpret_cast<ull *>(addr), bits) < bits;
+}
+__device__ __forceinline__ bool mrc_atomic_lower(ll *addr, ll cand) { return cand < atomicMin(addr, cand); }
+
+// The row is warp-synchronous: every lane calls it (valid == false for lanes past the end).  Several
+// in-edges of one destination sit in adjacent lanes, and in the first passes several of them lower
+// dist[v] in the same instruction; only the lane holding the smallest candidate may write pred[v],
+// otherwise pred would name an edge that did NOT produce dist[v] and the predecessor graph could
+// close cycles that are not negative.  Rows without competing winners (almost all after the first
+// two passes) take the single-ballot fast path.
+template <int K, typename T>
+__device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int lane, int e, int u, int v, T c, T t,
+                                          unsigned &chg) {
+    T du[K], dv[K];
+    T *dist = static_cast<T *>(p.dist);
+    if (valid) {
+        DistVec<K>::load(du, dist + (size_t)u * K);
+        DistVec<K>::load(dv, dist + (size_t)v * K);
+    }
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        if (!((p.active >> k) & 1u)) continue;
-        double w = __dsub_rn(c, __dmul_rn(p.lam[k], t));
-        double cand = __dadd_rn(du[k], w);
-        if (cand < __dsub_rn(dv[k], p.slack)) {
-            ull bits = (ull)__double_as_longlong(cand);
-            ull old = atomicMax(reinterpret_cast<ull *>(dist + (size_t)v * K + k), bits);
-            if (old < bits) {
-                __stcg(p.pred + (size_t)v * K + k, e);
-                chg |= 1u << k;
+        if (!((p.active >> k) & 1u)) continue;   // warp-uniform
+        bool won = false;
+        T cand = 0;
+        if (valid) {
+            cand = mrc_cand(p, k, du[k], c, t);
+            if (mrc_improves(p, cand, dv[k])) won = mrc_atomic_lower(dist + (size_t)v * K + k, cand);
+        }
+        const unsigned wm = __ballot_sync(0xffffffffu, won);
+        if (wm == 0) continue;                   // warp-uniform
+        bool lose = false;
+        if (wm & (wm - 1)) {
+            unsigned rest = wm;
+            while (rest) {
+                const int l = __ffs(rest) - 1;
+                rest &= rest - 1;
+                const int vl = __shfl_sync(0xffffffffu, v, l);
+                const T cl = __shfl_sync(0xffffffffu, cand, l);
+                if (l != lane && vl == v && (cl < cand || (cl == cand && l < lane))) lose = true;
             }
         }
-    }
-}
-// exact: w = b*icost - a*itime in int64 (solver.py:799-800), strict < without slack (:833)
-template <int K>
-__device__ __forceinline__ void relax_edge(const RelaxArgs &p, int e, int u, int v, ll c, ll t, unsigned &chg) {
-    ll du[K], dv[K];
-    ll *dist = static_cast<ll *>(p.dist);
-    DistVec<K>::load(du, dist + (size_t)u * K);
-    DistVec<K>::load(dv, dist + (size_t)v * K);
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        if (!((p.active >> k) & 1u)) continue;
-        ll cand = du[k] + (p.b[k] * c - p.a[k] * t);
-        if (cand < dv[k]) {
-            ll old = atomicMin(dist + (size_t)v * K + k, cand);
-            if (cand < old) {
-                __stcg(p.pred + (size_t)v * K + k, e);
-                chg |= 1u << k;
-            }
+        if (won) {
+            chg |= 1u << k;
+            if (!lose) __stcg(p.pred + (size_t)v * K + k, e);
         }
     }
 }
 
-template <bool EXACT> struct WeightT { typedef double type; typedef double2 vec2; };
-template <> struct WeightT<true> { typedef ll type; typedef longlong2 vec2; };
+template <bool EXACT> struct WeightT { typedef double type; };
+template <> struct WeightT<true> { typedef ll type; };
 
-// Edge-parallel relaxation: each thread owns 4 consecutive edges per step (int4 src, int4 dst,
-// 2 x 16-B cost, 2 x 16-B time = 96 B of coalesced stream per thread), persistent grid-stride loop.
+// Edge-parallel relaxation.  A warp owns MRC_ROWS rows of 32 CONSECUTIVE edges per step; lane i takes edge
+// base + 32*j + i, so every edge-stream load is one fully coalesced 128/256-B request and -- because
+// the edges are destination-sorted -- the 32 dist[dst] reads of a row collapse to one or two lines.
+// What remains is exactly one random line per edge (dist[src]); the kernel is bound by that L1TEX
+// gather rate and by the 24 B/edge HBM stream.  Persistent grid: occupancy x 148 SMs, warps walk
+// consecutive chunks so DRAM pages are streamed in order.
+#define MRC_ROWS 4
 template <int K, bool EXACT>
 __global__ void __launch_bounds__(MRC_RELAX_THREADS) relax_kernel(const __grid_constant__ RelaxArgs p) {
     typedef typename WeightT<EXACT>::type W;
-    typedef typename WeightT<EXACT>::vec2 W2;
     const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
     const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
     unsigned chg = 0;
-    const ll nvec = p.m >> 2;
-    const ll stride = (ll)gridDim.x * blockDim.x;
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        const ll q = p.reverse ? (nvec - 1 - i) : i;
-        int4 s = __ldcs(reinterpret_cast<const int4 *>(p.src) + q);
-        int4 d = __ldcs(reinterpret_cast<const int4 *>(p.dst) + q);
-        W2 c01 = __ldcs(reinterpret_cast<const W2 *>(cost) + 2 * q);
-        W2 c23 = __ldcs(reinterpret_cast<const W2 *>(cost) + 2 * q + 1);
-        W2 t01 = __ldcs(reinterpret_cast<const W2 *>(time) + 2 * q);
-        W2 t23 = __ldcs(reinterpret_cast<const W2 *>(time) + 2 * q + 1);
-        const int e = (int)(q << 2);
-        relax_edge<K>(p, e + 0, s.x, d.x, c01.x, t01.x, chg);
-        relax_edge<K>(p, e + 1, s.y, d.y, c01.y, t01.y, chg);
-        relax_edge<K>(p, e + 2, s.z, d.z, c23.x, t23.x, chg);
-        relax_edge<K>(p, e + 3, s.w, d.w, c23.y, t23.y, chg);
-    }
-    // tail (m % 4 edges)
-    {
-        const ll e = (nvec << 2) + (ll)blockIdx.x * blockDim.x + threadIdx.x;
-        if (e < p.m) relax_edge<K>(p, (int)e, p.src[e], p.dst[e], cost[e], time[e], chg);
+    const int lane = threadIdx.x & 31;
+    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    constexpr ll CH = 32 * MRC_ROWS;
+    const ll nchunks = (p.m + CH - 1) / CH;
+    for (ll c = warp; c < nchunks; c += nwarps) {
+        const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
+        int s[MRC_ROWS], d[MRC_ROWS];
+        W cs[MRC_ROWS], tm[MRC_ROWS];
+        if (e0 - lane + CH <= p.m) {
+#pragma unroll
+            for (int j = 0; j < MRC_ROWS; j++) {
+                const ll e = e0 + 32 * j;
+                s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
+                cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
+            }
+#pragma unroll
+            for (int j = 0; j < MRC_ROWS; j++)
+                relax_row<K, W>(p, true, lane, (int)(e0 + 32 * j), s[j], d[j], cs[j], tm[j], chg);
+        } else {
+#pragma unroll
+            for (int j = 0; j < MRC_ROWS; j++) {
+                const ll e = e0 + 32 * j;
+                const bool ok = e < p.m;
+                relax_row<K, W>(p, ok, lane, (int)e, ok ? p.src[e] : 0, ok ? p.dst[e] : 0, ok ? cost[e] : W(0),
+                                ok ? time[e] : W(0), chg);
+            }
+        }
     }
     // changed flag: warp vote, one atomic per warp at most
     chg = __reduce_or_sync(0xffffffffu, chg);
-    if ((threadIdx.x & 31) == 0 && chg) atomicOr(p.changed, chg);
+    if (lane == 0 && chg) atomicOr(p.changed, chg);
 }
 
 // ---- predecessor-graph cycle check -----------------------------------------------------------------
@@ -190,8 +231,14 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS) relax_kernel(const __grid_c
 //      predecessor graph has collapsed to roots (it is a forest -> no cycle yet)
 //   2. any vertex still alive leads into a cycle; its jump target lies ON the cycle.  Per candidate
 //      the smallest such vertex picks the representative (deterministic for a given pred array)
-//   3. one thread per candidate walks the cycle from its smallest vertex, records the edge list and
-//      sums cost/time over exactly those edges.  The host verifies sum_cost - lam*sum_time < 0.
+//   3. one thread per candidate walks that cycle from its smallest vertex, records the edge list, sums
+//      cost/time over exactly those edges and tests sum_cost/sum_time < lambda (exact: b*C - a*T < 0).
+//      pred writes of different warps can still race, so a cycle of the predecessor graph need not be
+//      negative: such a cycle is CUT (pred of its smallest vertex reset to -1), its vertices are marked
+//      dead for this launch, and steps 2-3 repeat (<= MRC_MAX_EXTRACT times) on the remaining cycles.
+#define MRC_MAX_EXTRACT 6
+#define MRC_CYC_NEG 1
+#define MRC_CYC_TIE 2
 template <int K>
 __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant__ CheckArgs p) {
     cg::grid_group grid = cg::this_grid();
@@ -201,11 +248,12 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     DevStatus *st = p.st;
 
     if (blockIdx.x == 0 && threadIdx.x < MRC_MAX_ROUNDS) st->alive[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < MRC_KMAX * MRC_MAX_EXTRACT) st->rep[threadIdx.x] = 0x7fffffff;
     if (blockIdx.x == 0 && threadIdx.x < MRC_KMAX) {
-        st->rep[threadIdx.x] = 0x7fffffff;
         st->out[threadIdx.x].found = 0;
         st->out[threadIdx.x].len = 0;
     }
+    if (tid0 == 0) { st->cyc_mask = 0; st->pend = 0; st->cuts = 0; }
     for (ll i = tid0; i < total; i += stride) {
         const int k = (int)(i % K);
         int j = -1;
@@ -237,19 +285,19 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         alive_mask = __ldcg(&st->alive[r]);
         if (alive_mask == 0) break;
     }
-    if (alive_mask == 0) {
-        if (tid0 == 0) { st->cyc_mask = 0; st->rounds_run = (unsigned)r; }
-        return;
-    }
-    // candidates in alive_mask have a cycle: smallest vertex that still has a live jump pointer
-    {
+    if (tid0 == 0) { st->rounds_run = (unsigned)r; st->pend = alive_mask; }
+    if (alive_mask == 0) return;
+
+    unsigned pending = alive_mask;   // candidates whose predecessor graph still holds an unexamined cycle
+    for (int it = 0; it < MRC_MAX_EXTRACT && pending; it++) {
         int best[K];
 #pragma unroll
         for (int k = 0; k < K; k++) best[k] = 0x7fffffff;
         for (ll i = tid0; i < total; i += stride) {
             const int k = (int)(i % K);
-            if (!((alive_mask >> k) & 1u)) continue;
-            if (__ldcg(p.jump + i) >= 0) {
+            if (!((pending >> k) & 1u)) continue;
+            const int j = __ldcg(p.jump + i);
+            if (j >= 0 && __ldcg(p.jump + (ll)j * K + k) != -2) {
                 const int v = (int)(i / K);
 #pragma unroll
                 for (int kk = 0; kk < K; kk++)
@@ -258,48 +306,81 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         }
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            if (!((alive_mask >> k) & 1u)) continue;
+            if (!((pending >> k) & 1u)) continue;
             const int b = __reduce_min_sync(0xffffffffu, best[k]);
-            if ((threadIdx.x & 31) == 0 && b != 0x7fffffff) atomicMin(&st->rep[k], b);
+            if ((threadIdx.x & 31) == 0 && b != 0x7fffffff) atomicMin(&st->rep[it * MRC_KMAX + k], b);
         }
-    }
-    grid.sync();
-    if (threadIdx.x == 0 && blockIdx.x < K && ((alive_mask >> blockIdx.x) & 1u)) {
-        const int k = blockIdx.x;
-        const int rep = __ldcg(&st->rep[k]);
-        CycleOut o;
-        o.found = 0; o.len = 0; o.minv = -1; o.pad = 0; o.sumc = 0; o.sumt = 0; o.isumc = 0; o.isumt = 0;
-        if (rep != 0x7fffffff) {
-            const int x = __ldcg(p.jump + (ll)rep * K + k);   // on the cycle
-            int cur = x, minv = x;
-            ll len = 0;
-            bool ok = true;
-            do {
-                const int e = __ldcg(p.pred + (ll)cur * K + k);
-                if (e < 0) { ok = false; break; }
-                cur = __ldg(p.src + e);
-                len++;
-                if (cur < minv) minv = cur;
-            } while (cur != x && len <= p.n);
-            if (ok && cur == x) {
-                double sc = 0.0, stt = 0.0;
-                ll isc = 0, ist = 0, i = 0;
-                cur = minv;
+        grid.sync();
+        if (threadIdx.x == 0 && blockIdx.x < K && ((pending >> blockIdx.x) & 1u)) {
+            const int k = blockIdx.x;
+            const int rep = __ldcg(&st->rep[it * MRC_KMAX + k]);
+            bool settled = true;   // nothing left to examine for k unless a false cycle is cut below
+            if (rep != 0x7fffffff) {
+                const int x = __ldcg(p.jump + (ll)rep * K + k);   // on a cycle
+                int cur = x, minv = x;
+                ll len = 0;
+                bool ok = true;
                 do {
                     const int e = __ldcg(p.pred + (ll)cur * K + k);
-                    if (i < p.cap) p.cyc_edges[(ll)k * p.cap + i] = e;
-                    if (p.exact) { isc += __ldg(p.icost + e); ist += __ldg(p.itime + e); }
-                    else { sc += __ldg(p.cost + e); stt += __ldg(p.time + e); }
+                    if (e < 0) { ok = false; break; }
                     cur = __ldg(p.src + e);
-                    i++;
-                } while (cur != minv && i <= p.n);
-                o.found = 1; o.len = (int)i; o.minv = minv;
-                o.sumc = sc; o.sumt = stt; o.isumc = isc; o.isumt = ist;
+                    len++;
+                    if (cur < minv) minv = cur;
+                } while (cur != x && len <= p.n);
+                if (ok && cur == x) {
+                    double sc = 0.0, stt = 0.0, mabs = 0.0;
+                    ll isc = 0, ist = 0, i = 0;
+                    cur = minv;
+                    do {
+                        const int e = __ldcg(p.pred + (ll)cur * K + k);
+                        if (i < p.cap) p.cyc_edges[(ll)k * p.cap + i] = e;
+                        if (p.exact) { isc += __ldg(p.icost + e); ist += __ldg(p.itime + e); }
+                        else {
+                            sc += __ldg(p.cost + e); stt += __ldg(p.time + e);
+                            mabs = fmax(mabs, fabs(__ldcg(static_cast<const double *>(p.dist) + (ll)cur * K + k)));
+                        }
+                        cur = __ldg(p.src + e);
+                        i++;
+                    } while (cur != minv && i <= p.n);
+                    int kind = 0;
+                    if (p.exact) {
+                        if ((__int128)p.b[k] * isc - (__int128)p.a[k] * ist < 0) kind = MRC_CYC_NEG;
+                    } else if (stt > 0) {
+                        // r < lambda: negative.  r >= lambda but (r - lambda)*T inside the rounding noise of the
+                        // walk (len * eps * max|dist|, x8): a rounding artefact that would relax forever -> TIE.
+                        const double rr = sc / stt;
+                        if (rr < p.lam[k]) kind = MRC_CYC_NEG;
+                        else if ((rr - p.lam[k]) * stt <= 8.0 * (double)i * 2.220446049250313e-16 * mabs) kind = MRC_CYC_TIE;
+                    }
+                    if (kind) {
+                        CycleOut o;
+                        o.found = kind; o.len = (int)i; o.minv = minv; o.pad = 0;
+                        o.sumc = sc; o.sumt = stt; o.maxabs = mabs; o.isumc = isc; o.isumt = ist;
+                        st->out[k] = o;
+                    } else {
+                        // false cycle: mark its vertices dead for this launch and cut it for good
+                        cur = minv;
+                        ll g = 0;
+                        do {
+                            const int e = __ldcg(p.pred + (ll)cur * K + k);
+                            __stcg(p.jump + (ll)cur * K + k, -2);
+                            cur = __ldg(p.src + e);
+                            g++;
+                        } while (cur != minv && g <= p.n);
+                        __stcg(p.pred + (ll)minv * K + k, -1);
+                        atomicAdd(&st->cuts, 1u);
+                        settled = false;
+                    }
+                } else {
+                    // the chain left the cycle while we walked (cannot happen between launches); give up on k
+                }
             }
+            if (settled) atomicAnd(&st->pend, ~(1u << k));
         }
-        st->out[k] = o;
+        grid.sync();
+        pending = __ldcg(&st->pend);
     }
-    if (tid0 == 0) { st->cyc_mask = alive_mask; st->rounds_run = (unsigned)r; }
+    if (tid0 == 0) st->cyc_mask = alive_mask;
 }
 
 // gather (src, cost, time) of a recorded cycle edge list for the host
