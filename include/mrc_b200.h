@@ -118,11 +118,20 @@ int mrc_probe_numeric(mrc_graph *g, const double *lam, int K, double slack, uint
  * same midpoints as the reference until the first cycle is found.
  * Returns MRC_ERR_NO_CYCLE / MRC_ERR_CONVERGENCE / MRC_ERR_TIMEOUT like the reference raises.
  * cycle: CLOSED vertex list (cap entries), max_seconds <= 0 = no limit (solver.py:1032-1041).
+ * hi_is_cycle != 0: the caller already holds a cycle whose ratio is `hi` (warm start, used by
+ * sensitivity_analysis re-solves); MRC_OK with *cycle_len == 0 then means "no better cycle exists".
  */
-int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int max_iter, double tol, double slack, int K,
-                      double max_seconds, double *ratio, double *sum_cost, double *sum_time, int32_t *cycle,
+int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_cycle, int max_iter, double tol, double slack,
+                      int K, double max_seconds, double *ratio, double *sum_cost, double *sum_time, int32_t *cycle,
                       int64_t cycle_cap, int64_t *cycle_len, int32_t *iterations, double *final_lo,
                       double *final_hi);
+
+/* Measurement aid (bench/profiling only): `passes` relaxation launches for K lambdas from dist == 0, no
+ * cycle checks, each launch timed with CUDA events on the library's stream. */
+int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *ms_per_pass);
+/* Tuning knobs: "alternate" (sweep direction flips every pass, 0/1), "burst_init", "burst_max" (passes per
+ * host round trip). */
+int mrc_set_option(mrc_graph *g, const char *name, int value);
 
 /* Pure host helpers shared by mrc_solve_numeric and the multi-GPU driver (one process per GPU, the
  * candidates of a round split across ranks, verdicts all-gathered): no device work.

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmrc_b200.so")
+LIB_PATH = os.environ.get("MRC_B200_LIB") or os.path.join(HERE, "libmrc_b200.so")
 
 KMAX = 8
 
@@ -28,6 +28,7 @@ EXPORTS = [
     "mrc_graph_info", "mrc_numeric_bounds", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
     "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
     "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
+    "mrc_bench_relax", "mrc_set_option",
 ]
 
 
@@ -77,7 +78,7 @@ def lib():
     L.mrc_graph_patch_edges.argtypes = [vp, C.c_int64, p64, pd, pd]
     L.mrc_graph_restore.argtypes = [vp]
     L.mrc_probe_numeric.argtypes = [vp, pd, C.c_int, C.c_double, C.c_uint32, p32, p32, p32, C.c_int64, pd, pd, p64]
-    L.mrc_solve_numeric.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
+    L.mrc_solve_numeric.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                     C.c_double, pd, pd, pd, p32, C.c_int64, p64, p32, pd, pd]
     L.mrc_plan_candidates.argtypes = [C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, pd]
     L.mrc_reduce_round.argtypes = [C.c_int, pd, p32, pd, pd, pd, pi, pi]
@@ -87,6 +88,8 @@ def lib():
     L.mrc_zero_cycle_exact.argtypes = [vp, C.c_int64, C.c_int64, pu8, p32, C.c_int64, p64, p64, p64]
     L.mrc_solve_exact.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, p32, C.c_int64, p64, p64, p64, p64, p64, p64,
                                   p64, C.c_int64, p64]
+    L.mrc_bench_relax.argtypes = [vp, pd, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.mrc_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     for name in EXPORTS:
         if name not in ("mrc_last_error",):
             getattr(L, name).restype = C.c_int
@@ -176,6 +179,15 @@ class DeviceGraph:
     def restore(self):
         check(lib().mrc_graph_restore(self._h))
 
+    def set_option(self, name: str, value: int):
+        check(lib().mrc_set_option(self._h, name.encode(), int(value)))
+
+    def bench_relax(self, lams, passes: int):
+        lam = np.ascontiguousarray(lams, dtype=np.float64)
+        ms = np.zeros(passes, np.float32)
+        check(lib().mrc_bench_relax(self._h, _ptr(lam, C.c_double), len(lam), int(passes), _ptr(ms, C.c_float)))
+        return ms
+
     # -- probes -----------------------------------------------------------
     def probe_numeric(self, lams, slack: float = 1e-15, flags: int = 0, cyc_cap: int | None = None):
         """K-batched analogue of _detect_negative_cycle_numeric.  Returns a list of dicts."""
@@ -212,14 +224,15 @@ class DeviceGraph:
 
     # -- searches -----------------------------------------------------------
     def solve_numeric(self, lo: float, hi: float, max_iter: int = 60, tol: float = 1e-12, slack: float = 1e-15,
-                      K: int = 4, max_seconds: float = 0.0):
+                      K: int = 4, max_seconds: float = 0.0, hi_is_cycle: bool = False):
         """Returns dict(rc, cycle(closed), sum_cost, sum_time, ratio, iterations, lo, hi); rc may be
         ERR_CONVERGENCE with a valid best cycle, ERR_NO_CYCLE / ERR_TIMEOUT without one."""
         cap = self.n + 1
         buf = np.zeros(cap, np.int32)
         ratio, sc, st, flo, fhi = (C.c_double() for _ in range(5))
         cl = C.c_int64(); it = C.c_int32()
-        rc = lib().mrc_solve_numeric(self._h, float(lo), float(hi), int(max_iter), float(tol), float(slack), int(K),
+        rc = lib().mrc_solve_numeric(self._h, float(lo), float(hi), int(bool(hi_is_cycle)), int(max_iter), float(tol),
+                                     float(slack), int(K),
                                      float(max_seconds or 0.0), C.byref(ratio), C.byref(sc), C.byref(st),
                                      _ptr(buf, C.c_int32), cap, C.byref(cl), C.byref(it), C.byref(flo), C.byref(fhi))
         if rc not in (OK, ERR_CONVERGENCE, ERR_NO_CYCLE, ERR_TIMEOUT):

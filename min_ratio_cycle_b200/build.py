@@ -26,14 +26,14 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def command(verbose: bool = False) -> list[str]:
+def command(verbose: bool = False, defines: list[str] | None = None, out: str | None = None) -> list[str]:
     cmd = [
         nvcc_path(), "-O3", "-std=c++17",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-O2",
         "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc"),
-        "-o", LIB,
-    ] + SOURCES
+        "-o", out or LIB,
+    ] + [f"-D{d}" for d in (defines or [])] + SOURCES
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     if verbose:
@@ -57,6 +57,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     return LIB
+
+
+def build_variant(tag: str, defines: list[str]) -> str:
+    """Tuning builds: extra -D defines, written next to the main library as libmrc_b200.<tag>.so"""
+    out = os.path.join(HERE, f"libmrc_b200.{tag}.so")
+    r = subprocess.run(command(False, defines, out), capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed for variant " + tag)
+    return out
 
 
 if __name__ == "__main__":

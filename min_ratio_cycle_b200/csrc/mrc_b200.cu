@@ -33,6 +33,7 @@ static int set_err(int code, const char *fmt, ...) {
                                                                                         : MRC_ERR_CUDA, \
                            "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);    \
     } while (0)
+#define DALLOC(ptr, bytes) CUDA_TRY(cudaMallocAsync((void **)&(ptr), (bytes), g->stream))
 #define MRC_TRY(x)            \
     do {                      \
         int rc_ = (x);        \
@@ -63,6 +64,7 @@ struct mrc_graph {
     int *d_g_src = nullptr; double *d_g_c = nullptr, *d_g_t = nullptr; ll *d_g_ic = nullptr, *d_g_it = nullptr;
     uint8_t *d_mask = nullptr;
     ull *d_keys = nullptr;
+    int *d_verr = nullptr;
     // host mirrors needed by the exact path (tight-subgraph DFS and first-(u,v)-edge lookup)
     std::vector<int> h_src, h_dst;
     std::vector<ll> h_icost, h_itime, h_starts;
@@ -124,10 +126,13 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
     if (!g) return MRC_OK;
     cudaSetDevice(g->device);
     for (auto &p : g->patches) { cudaFree(p.d_idx); cudaFree(p.d_oldc); cudaFree(p.d_oldt); }
-    cudaFree(g->d_src); cudaFree(g->d_dst); cudaFree(g->d_cost); cudaFree(g->d_time);
-    cudaFree(g->d_icost); cudaFree(g->d_itime); cudaFree(g->d_dist); cudaFree(g->d_pred); cudaFree(g->d_jump);
-    cudaFree(g->d_cyc_edges); cudaFree(g->d_status); cudaFree(g->d_g_src); cudaFree(g->d_g_c); cudaFree(g->d_g_t);
-    cudaFree(g->d_g_ic); cudaFree(g->d_g_it); cudaFree(g->d_mask); cudaFree(g->d_keys);
+    if (g->stream) {
+        void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
+                        g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
+                        g->d_keys, g->d_verr};
+        for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
+        cudaStreamSynchronize(g->stream);
+    }
     if (g->h_status) cudaFreeHost(g->h_status);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
     if (g->stream) cudaStreamDestroy(g->stream);
@@ -147,13 +152,13 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
     int ndev = 0;
     MRC_TRY(mrc_device_count(&ndev));
     if (device < 0 || device >= ndev) return set_err(MRC_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
-    for (ll e = 0; e < m; e++) {
-        if ((unsigned)src[e] >= (unsigned)n || (unsigned)dst[e] >= (unsigned)n)
-            return set_err(MRC_ERR_ARG, "edge %lld has an endpoint outside [0,n)", e);
-        if (e && dst[e] < dst[e - 1]) return set_err(MRC_ERR_ARG, "edges are not destination-sorted at %lld", e);
-        if (!(time[e] > 0)) return set_err(MRC_ERR_ARG, "edge %lld: time must be strictly positive", e);
-    }
     CUDA_TRY(cudaSetDevice(device));
+    {   // keep freed device memory cached in the stream-ordered pool: create/destroy cycles reuse it
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     mrc_graph *g = new mrc_graph();
     memset(&g->stats, 0, sizeof g->stats);
     g->device = device; g->n = n; g->m = m;
@@ -164,8 +169,8 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
         for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
         const size_t m4 = ((size_t)m + 3) & ~(size_t)3;   // vector loads never read past the allocation
-        CUDA_TRY(cudaMalloc(&g->d_src, m4 * 4)); CUDA_TRY(cudaMalloc(&g->d_dst, m4 * 4));
-        CUDA_TRY(cudaMalloc(&g->d_cost, m4 * 8)); CUDA_TRY(cudaMalloc(&g->d_time, m4 * 8));
+        DALLOC(g->d_src, m4 * 4); DALLOC(g->d_dst, m4 * 4);
+        DALLOC(g->d_cost, m4 * 8); DALLOC(g->d_time, m4 * 8);
         CUDA_TRY(cudaMemcpyAsync(g->d_src, src, (size_t)m * 4, cudaMemcpyHostToDevice, g->stream));
         CUDA_TRY(cudaMemcpyAsync(g->d_dst, dst, (size_t)m * 4, cudaMemcpyHostToDevice, g->stream));
         CUDA_TRY(cudaMemcpyAsync(g->d_cost, cost, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
@@ -173,15 +178,19 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         g->stats.h2d_bytes += (int64_t)m * 24;
         if (icost) {
             g->has_int = true;
-            CUDA_TRY(cudaMalloc(&g->d_icost, m4 * 8)); CUDA_TRY(cudaMalloc(&g->d_itime, m4 * 8));
+            DALLOC(g->d_icost, m4 * 8); DALLOC(g->d_itime, m4 * 8);
             CUDA_TRY(cudaMemcpyAsync(g->d_icost, icost, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
             CUDA_TRY(cudaMemcpyAsync(g->d_itime, itime, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
             g->stats.h2d_bytes += (int64_t)m * 16;
-            CUDA_TRY(cudaMalloc(&g->d_mask, (size_t)m));
+            DALLOC(g->d_mask, (size_t)m);
             g->h_src.assign(src, src + m); g->h_dst.assign(dst, dst + m);
             g->h_icost.assign(icost, icost + m); g->h_itime.assign(itime, itime + m);
             g->h_starts.assign((size_t)n + 1, 0);
-            for (ll e = 0; e < m; e++) g->h_starts[dst[e] + 1]++;
+            for (ll e = 0; e < m; e++) {
+                if ((unsigned)src[e] >= (unsigned)n || (unsigned)dst[e] >= (unsigned)n)
+                    return set_err(MRC_ERR_ARG, "edge %lld has an endpoint outside [0,n)", e);
+                g->h_starts[dst[e] + 1]++;
+            }
             for (ll v = 0; v < n; v++) g->h_starts[v + 1] += g->h_starts[v];
             double mn = INFINITY, mx = -INFINITY;
             for (ll e = 0; e < m; e++) {
@@ -194,22 +203,23 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
             g->max_it = g->max_abs_it;
             g->min_ratio_i = mn; g->max_ratio_i = mx;
         }
-        CUDA_TRY(cudaMalloc(&g->d_dist, (size_t)n * MRC_KMAX * 8));
-        CUDA_TRY(cudaMalloc(&g->d_pred, (size_t)n * MRC_KMAX * 4));
-        CUDA_TRY(cudaMalloc(&g->d_jump, (size_t)n * MRC_KMAX * 4));
+        DALLOC(g->d_dist, (size_t)n * MRC_KMAX * 8);
+        DALLOC(g->d_pred, (size_t)n * MRC_KMAX * 4);
+        DALLOC(g->d_jump, (size_t)n * MRC_KMAX * 4);
         g->cyc_cap = n;
-        CUDA_TRY(cudaMalloc(&g->d_cyc_edges, (size_t)g->cyc_cap * MRC_KMAX * 4));
-        CUDA_TRY(cudaMalloc(&g->d_status, sizeof(DevStatus)));
+        DALLOC(g->d_cyc_edges, (size_t)g->cyc_cap * MRC_KMAX * 4);
+        DALLOC(g->d_status, sizeof(DevStatus));
         CUDA_TRY(cudaMemsetAsync(g->d_status, 0, sizeof(DevStatus), g->stream));
         CUDA_TRY(cudaMallocHost(&g->h_status, sizeof(DevStatus)));
-        CUDA_TRY(cudaMalloc(&g->d_keys, 16));
+        DALLOC(g->d_keys, 16);
         // launch geometry: persistent grids sized to whole waves of the 148 SMs
         for (int KT : {1, 2, 4, 8})
             for (int ex = 0; ex < 2; ex++) {
                 int occ = 0;
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, relax_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
                 if (occ < 1) return set_err(MRC_ERR_CUDA, "relax kernel K=%d does not fit on an SM", KT);
-                const ll chunks = (m + 32 * MRC_ROWS - 1) / (32 * MRC_ROWS);   // one chunk per warp step
+                const int rows = KT == 8 ? RelaxTune<8>::rows : RelaxTune<1>::rows;
+                const ll chunks = (m + 32 * rows - 1) / (32 * rows);   // one chunk per warp step
                 ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
                 g->relax_blocks[kt_index(KT)][ex] = (int)std::min<ll>(need, (ll)occ * g->sms);
             }
@@ -220,7 +230,19 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
             ll need = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
             g->check_blocks[kt_index(KT)] = (int)std::min<ll>(need, (ll)occ * g->sms);
         }
+        // input validation on the device (the host never touches the 24 B/edge again)
+        DALLOC(g->d_verr, 4);
+        CUDA_TRY(cudaMemsetAsync(g->d_verr, 0, 4, g->stream));
+        validate_edges_kernel<<<(int)std::min<ll>((m + 255) / 256, (ll)g->sms * 8), 256, 0, g->stream>>>(
+            g->d_src, g->d_dst, g->d_time, n, m, g->d_verr);
+        CUDA_TRY(cudaGetLastError());
+        int verr = 0;
+        CUDA_TRY(cudaMemcpyAsync(&verr, g->d_verr, 4, cudaMemcpyDeviceToHost, g->stream));
         CUDA_TRY(cudaStreamSynchronize(g->stream));
+        g->stats.other_launches++;
+        if (verr & 1) return set_err(MRC_ERR_ARG, "an edge has an endpoint outside [0,n)");
+        if (verr & 2) return set_err(MRC_ERR_ARG, "edges are not destination-sorted");
+        if (verr & 4) return set_err(MRC_ERR_ARG, "edge time must be strictly positive");
         return MRC_OK;
     }();
     if (rc) { mrc_graph_destroy(g); return rc; }
@@ -375,9 +397,10 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     const ll max_passes = n;   // n-1 passes + the detection pass
     ll passes = 0;
     int burst = g->burst_init;
+    ll next_check = g->burst_init;   // cycle checks after 2, 6, 14, 30, ... passes; convergence flags every burst
     g->stats.probes += K;
     while (active) {
-        const int nb = (int)std::min<ll>(burst, max_passes - passes);
+        const int nb = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
         if (nb <= 0) {
             for (int k = 0; k < K; k++)
                 if ((active >> k) & 1u) { res[k].verdict = MRC_V_NEG_NOCYCLE; res[k].passes = passes; }
@@ -392,8 +415,12 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
             MRC_TRY(launch_relax(g, KT, exact, ra));
         }
         CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
-        ca.active = active;
-        MRC_TRY(launch_check(g, KT, ca));
+        const bool do_check = passes + nb >= next_check || passes + nb >= max_passes;
+        if (do_check) {
+            ca.active = active;
+            MRC_TRY(launch_check(g, KT, ca));
+            next_check = 2 * next_check + 2;
+        }
         CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
         CUDA_TRY(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, g->stream));
         CUDA_TRY(cudaStreamSynchronize(g->stream));
@@ -403,8 +430,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         passes += nb;
         g->stats.relax_launches += nb;
         g->stats.relax_edge_visits += (int64_t)nb * m * __builtin_popcount(active);
-        g->stats.check_launches++;
-        g->stats.false_cycles_cut += g->h_status->cuts;
+        if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += g->h_status->cuts; }
         g->stats.d2h_bytes += sizeof(DevStatus);
         const DevStatus &hs = *g->h_status;
         for (int k = 0; k < K; k++) {
@@ -413,7 +439,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
             for (int i = 0; i < nb; i++) conv |= !((hs.changed[i] >> k) & 1u);
             ProbeOut &o = res[k];
             if (conv) { o.verdict = MRC_V_NONNEG; }
-            else if (((hs.cyc_mask >> k) & 1u) && hs.out[k].found) {
+            else if (do_check && ((hs.cyc_mask >> k) & 1u) && hs.out[k].found) {
                 // the check kernel extracted a cycle and tested it against lambda on the device:
                 // found == 1 verified negative, 2 rounding tie; cycles that are neither were cut there
                 const CycleOut &c = hs.out[k];
@@ -430,6 +456,9 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
                     if (!((active >> j) & 1u)) continue;
                     bool above = exact ? ((i128)a[j] * b[k] > (i128)a[k] * b[j]) : (lam[j] > lam[k]);
                     bool below = exact ? ((i128)a[j] * b[k] < (i128)a[k] * b[j]) : (lam[j] < lam[k]);
+                    // a verified cycle of ratio r is negative for every lambda > r, not only above lambda_k
+                    if (res[k].verdict == MRC_V_NEG && !exact && res[k].sumt > 0 && lam[j] > res[k].sumc / res[k].sumt) above = true;
+                    if (res[k].verdict == MRC_V_NEG && exact && (i128)a[j] * res[k].isumt > (i128)res[k].isumc * b[j]) above = true;
                     if (res[k].verdict == MRC_V_NEG && above) { res[j].verdict = MRC_V_SKIPPED_NEG; res[j].passes = passes; active &= ~(1u << j); }
                     if (res[k].verdict == MRC_V_NONNEG && below) { res[j].verdict = MRC_V_SKIPPED_NONNEG; res[j].passes = passes; active &= ~(1u << j); }
                 }
@@ -452,9 +481,9 @@ static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::
     if (L <= 0) return MRC_OK;
     if (L > g->cyc_cap) return set_err(MRC_ERR_ARG, "cycle longer than buffer");
     if (!g->d_g_src) {
-        CUDA_TRY(cudaMalloc(&g->d_g_src, (size_t)g->cyc_cap * 4));
-        CUDA_TRY(cudaMalloc(&g->d_g_c, (size_t)g->cyc_cap * 8)); CUDA_TRY(cudaMalloc(&g->d_g_t, (size_t)g->cyc_cap * 8));
-        CUDA_TRY(cudaMalloc(&g->d_g_ic, (size_t)g->cyc_cap * 8)); CUDA_TRY(cudaMalloc(&g->d_g_it, (size_t)g->cyc_cap * 8));
+        DALLOC(g->d_g_src, (size_t)g->cyc_cap * 4);
+        DALLOC(g->d_g_c, (size_t)g->cyc_cap * 8); DALLOC(g->d_g_t, (size_t)g->cyc_cap * 8);
+        DALLOC(g->d_g_ic, (size_t)g->cyc_cap * 8); DALLOC(g->d_g_it, (size_t)g->cyc_cap * 8);
     }
     const int blocks = (int)std::min<ll>((L + 127) / 128, 1024);
     gather_cycle_kernel<<<blocks, 128, 0, g->stream>>>(g->d_cyc_edges + (ll)k * g->cyc_cap, L, g->d_src, g->d_cost,
@@ -537,6 +566,47 @@ extern "C" int mrc_probe_exact(mrc_graph *g, const int64_t *a, const int64_t *b,
                                  cyc_buf, cyc_cap, sum_cost, sum_time, passes);
 }
 
+/*
+ * Measurement aid: `passes` relaxation launches for K lambdas from dist == 0, each timed with its own pair
+ * of CUDA events on the library stream (no cycle checks, no early exit).  ms_per_pass[passes].
+ */
+extern "C" int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *ms_per_pass) {
+    if (!g || !lam || !ms_per_pass || K < 1 || K > MRC_KMAX || passes < 1) return set_err(MRC_ERR_ARG, "bad arguments");
+    CUDA_TRY(cudaSetDevice(g->device));
+    const int KT = kt_of(K);
+    RelaxArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.src = g->d_src; ra.dst = g->d_dst; ra.cost = g->d_cost; ra.time = g->d_time;
+    ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = g->m; ra.slack = 1e-15;
+    ra.active = (1u << K) - 1u;
+    ra.changed = &g->d_status->changed[0];
+    for (int k = 0; k < K; k++) ra.lam[k] = lam[k];
+    g->pot_valid = false;
+    CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)g->n * KT * 8, g->stream));
+    CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)g->n * KT * 4, g->stream));
+    std::vector<cudaEvent_t> ev((size_t)passes + 1);
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(ev[0], g->stream));
+    for (int i = 0; i < passes; i++) {
+        ra.reverse = g->alternate ? (i & 1) : 0;
+        MRC_TRY(launch_relax(g, KT, false, ra));
+        CUDA_TRY(cudaEventRecord(ev[i + 1], g->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    for (int i = 0; i < passes; i++) CUDA_TRY(cudaEventElapsedTime(&ms_per_pass[i], ev[i], ev[i + 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    return MRC_OK;
+}
+extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
+    if (!g || !name) return set_err(MRC_ERR_ARG, "NULL argument");
+    std::string s(name);
+    if (s == "alternate") g->alternate = value != 0;
+    else if (s == "burst_init") g->burst_init = std::max(1, std::min(value, MRC_MAX_BURST));
+    else if (s == "burst_max") g->burst_max = std::max(1, std::min(value, MRC_MAX_BURST));
+    else return set_err(MRC_ERR_ARG, "unknown option %s", name);
+    return MRC_OK;
+}
+
 // ------------------------------------------------------------------------------- numeric lambda search
 extern "C" int mrc_plan_candidates(double lo, double hi, int have_cycle, double tol, int K_total, double *lam_out) {
     if (!lam_out || K_total < 1) return set_err(MRC_ERR_ARG, "bad plan arguments");
@@ -587,8 +657,8 @@ extern "C" int mrc_reduce_round(int K_total, const double *lam, const int32_t *v
     return MRC_OK;
 }
 
-extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int max_iter, double tol, double slack, int K,
-                                 double max_seconds, double *ratio, double *sum_cost, double *sum_time,
+extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_cycle, int max_iter, double tol,
+                                 double slack, int K, double max_seconds, double *ratio, double *sum_cost, double *sum_time,
                                  int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len, int32_t *iterations,
                                  double *final_lo, double *final_hi) {
     if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
@@ -597,7 +667,7 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int max_ite
     std::vector<int> best_cycle, verts;
     double best_sc = 0, best_st = 0;
     bool have_best = false;
-    int have_cycle = 0, iters = 0, it = -1;
+    int have_cycle = hi_is_cycle ? 1 : 0, iters = 0, it = -1;
     double lam[MRC_KMAX], cr[MRC_KMAX];
     int32_t vd[MRC_KMAX];
     ProbeOut res[MRC_KMAX];
@@ -623,6 +693,16 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int max_ite
             have_best = true;
         }
         if (hi - lo <= tol) break;   // solver.py:1075-1076
+    }
+    if (!have_best && hi_is_cycle) {   // the caller's cycle (ratio == the initial hi) was not beaten
+        if (iterations) *iterations = iters;
+        if (final_lo) *final_lo = lo;
+        if (final_hi) *final_hi = hi;
+        if (cycle_len) *cycle_len = 0;
+        if (ratio) *ratio = hi;
+        if (max_iter > 0 && it == max_iter - 1 && hi - lo > tol)
+            return set_err(MRC_ERR_CONVERGENCE, "Numeric solver failed to converge");
+        return MRC_OK;
     }
     if (!have_best) {   // solver.py:1079-1085: one more try at the upper bound
         MRC_TRY(run_probe(g, false, 1, &hi, nullptr, nullptr, slack, 0, res));

@@ -26,7 +26,9 @@ typedef unsigned long long ull;
 
 #define MRC_MAX_BURST 8
 #define MRC_MAX_ROUNDS 40
+#ifndef MRC_RELAX_THREADS
 #define MRC_RELAX_THREADS 256
+#endif
 
 struct RelaxArgs {
     const int *src, *dst;
@@ -131,11 +133,13 @@ __device__ __forceinline__ bool mrc_atomic_lower(double *addr, double cand) {
 __device__ __forceinline__ bool mrc_atomic_lower(ll *addr, ll cand) { return cand < atomicMin(addr, cand); }
 
 // The row is warp-synchronous: every lane calls it (valid == false for lanes past the end).  Several
-// in-edges of one destination sit in adjacent lanes, and in the first passes several of them lower
-// dist[v] in the same instruction; only the lane holding the smallest candidate may write pred[v],
-// otherwise pred would name an edge that did NOT produce dist[v] and the predecessor graph could
-// close cycles that are not negative.  Rows without competing winners (almost all after the first
-// two passes) take the single-ballot fast path.
+// in-edges of one destination sit in adjacent lanes, and in the first passes several of them would lower
+// dist[v] in the same instruction; if they all issued their atomic, the pred[v] store of a worse
+// candidate could land last, pred would name an edge that did NOT produce dist[v], and the predecessor
+// graph could close cycles that are not negative.  So per destination only the lane with the smallest
+// candidate of the row issues the atomic (which also removes most same-address atomics of the early
+// passes).  Control flow never waits for an atomic's return value; rows in which nothing improves
+// (almost all rows after the first passes) cost one ballot per candidate.
 template <int K, typename T>
 __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int lane, int e, int u, int v, T c, T t,
                                           unsigned &chg) {
@@ -148,17 +152,17 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
 #pragma unroll
     for (int k = 0; k < K; k++) {
         if (!((p.active >> k) & 1u)) continue;   // warp-uniform
-        bool won = false;
         T cand = 0;
+        bool imp = false;
         if (valid) {
             cand = mrc_cand(p, k, du[k], c, t);
-            if (mrc_improves(p, cand, dv[k])) won = mrc_atomic_lower(dist + (size_t)v * K + k, cand);
+            imp = mrc_improves(p, cand, dv[k]);
         }
-        const unsigned wm = __ballot_sync(0xffffffffu, won);
-        if (wm == 0) continue;                   // warp-uniform
-        bool lose = false;
-        if (wm & (wm - 1)) {
-            unsigned rest = wm;
+        const unsigned im = __ballot_sync(0xffffffffu, imp);
+        if (im == 0) continue;                   // warp-uniform
+        if (im & (im - 1)) {
+            bool lose = false;
+            unsigned rest = im;
             while (rest) {
                 const int l = __ffs(rest) - 1;
                 rest &= rest - 1;
@@ -166,10 +170,11 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
                 const T cl = __shfl_sync(0xffffffffu, cand, l);
                 if (l != lane && vl == v && (cl < cand || (cl == cand && l < lane))) lose = true;
             }
+            imp = imp && !lose;
         }
-        if (won) {
+        if (imp && mrc_atomic_lower(dist + (size_t)v * K + k, cand)) {
+            __stcg(p.pred + (size_t)v * K + k, e);
             chg |= 1u << k;
-            if (!lose) __stcg(p.pred + (size_t)v * K + k, e);
         }
     }
 }
@@ -183,9 +188,13 @@ template <> struct WeightT<true> { typedef ll type; };
 // What remains is exactly one random line per edge (dist[src]); the kernel is bound by that L1TEX
 // gather rate and by the 24 B/edge HBM stream.  Persistent grid: occupancy x 148 SMs, warps walk
 // consecutive chunks so DRAM pages are streamed in order.
-#define MRC_ROWS 4
+// Tuned on B200 (tools/relax_variants.py, profiles/r01_relax_variants.txt): K <= 4 wants 2 rows per warp
+// step and 4 resident CTAs per SM (64 registers); K = 8 carries 2 x 64 B of dist per edge and is faster
+// with 4 rows and no register cap.
+template <int K> struct RelaxTune { static constexpr int rows = 2, minblocks = 4; };
+template <> struct RelaxTune<8> { static constexpr int rows = 4, minblocks = 1; };
 template <int K, bool EXACT>
-__global__ void __launch_bounds__(MRC_RELAX_THREADS) relax_kernel(const __grid_constant__ RelaxArgs p) {
+__global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) relax_kernel(const __grid_constant__ RelaxArgs p) {
     typedef typename WeightT<EXACT>::type W;
     const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
     const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
@@ -193,6 +202,7 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS) relax_kernel(const __grid_c
     const int lane = threadIdx.x & 31;
     const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    constexpr int MRC_ROWS = RelaxTune<K>::rows;
     constexpr ll CH = 32 * MRC_ROWS;
     const ll nchunks = (p.m + CH - 1) / CH;
     for (ll c = warp; c < nchunks; c += nwarps) {
@@ -422,6 +432,19 @@ __global__ void ratio_bounds_kernel(const double *cost, const double *time, ll m
         hi = h2 > hi ? h2 : hi;
     }
     if ((threadIdx.x & 31) == 0) { atomicMin(kmin, lo); atomicMax(kmax, hi); }
+}
+
+// input checks of mrc_graph_create: bit0 endpoint out of range, bit1 not destination-sorted, bit2 time <= 0
+__global__ void validate_edges_kernel(const int *src, const int *dst, const double *time, ll n, ll m, int *err) {
+    int bad = 0;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (ll)gridDim.x * blockDim.x) {
+        const int u = src[e], v = dst[e];
+        if ((unsigned)u >= (unsigned)n || (unsigned)v >= (unsigned)n) bad |= 1;
+        if (e > 0 && v < dst[e - 1]) bad |= 2;
+        if (!(time[e] > 0.0)) bad |= 4;
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicOr(err, bad);
 }
 
 __global__ void patch_edges_kernel(double *cost, double *time, const ll *idx, const double *dc, const double *dt,

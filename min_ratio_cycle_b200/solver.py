@@ -501,8 +501,19 @@ class MinRatioCycleSolver:
                                                   limit=self.config.max_memory_mb, usage=mem)
             t0 = _time.time()
             limit = self.config.max_solve_time
+            warm = kwargs.get("_warm_cycle")
+            warm_sums = None
+            if warm:
+                warm_sums = self._compute_cycle_weights_float(warm[:-1])
+                if warm_sums[1] > 0 and lambda_lo < warm_sums[0] / warm_sums[1] <= lambda_hi:
+                    lambda_hi = warm_sums[0] / warm_sums[1]
+                else:
+                    warm = None
             out = dev.solve_numeric(lambda_lo, lambda_hi, max_iter, tol, slack, K=self.config.gpu_candidates,
-                                    max_seconds=-1.0 if limit is None else max(float(limit), 1e-300))
+                                    max_seconds=-1.0 if limit is None else max(float(limit), 1e-300),
+                                    hi_is_cycle=bool(warm))
+            if warm and out["rc"] in (N.OK, N.ERR_CONVERGENCE) and not out["cycle"]:
+                out["cycle"] = list(warm)          # no better cycle exists: the warm-start cycle stands
             if out["rc"] == N.ERR_TIMEOUT:
                 raise TimeoutError("Numeric solve exceeded time limit", time_elapsed=_time.time() - t0,
                                    time_limit=limit, operation="numeric_solve")
@@ -602,6 +613,13 @@ class MinRatioCycleSolver:
         results: list[SolverResult] = []
         self._preprocess_graph()
         self._build_arrays_if_needed()
+        # warm start: the unperturbed optimum is still a cycle of every perturbed graph, so its (re-costed)
+        # ratio is a valid upper end of the bracket and usually certifies in one round
+        warm = None
+        if self._last_result is not None and self._last_result.success and self._last_result.cycle:
+            ok, _ = self._verify_cycle_exists(self._last_result.cycle)
+            if ok:
+                warm = list(self._last_result.cycle)
         m = self._num_edges()
         inv = np.empty(m, dtype=np.int64)
         inv[self._order] = np.arange(m)
@@ -619,7 +637,7 @@ class MinRatioCycleSolver:
             self._C[pos] += dc
             self._T[pos] += dt
             try:
-                res = self._solve_numeric()
+                res = self._solve_numeric(_warm_cycle=warm)
                 if self.config.validate_cycles:
                     res = self._validate_result(res)
                 res.config_used = self.config

@@ -306,3 +306,39 @@ def test_numeric_seeded(mrc, oracle_mod, name, K):
         assert v == MATCH and rotations_equal(r.cycle, gold["cycle"])
     ok, why = o.certify(r.cycle, r.ratio)
     assert ok, why
+
+
+# --------------------------------------------------------------------------- sensitivity analysis (a17)
+def test_sensitivity_analysis_matches_fresh_solves(mrc, oracle_mod):
+    """Each perturbed re-solve (device-side edge patch + warm start) equals a fresh solve of the perturbed
+    graph, and certifies against the oracle.  Reported sums use the perturbed weights (the reference's
+    stale _edge_map, SURVEY 0.8, is deliberately not reproduced)."""
+    from min_ratio_cycle_b200 import synthetic
+    n, U, V, C, T = synthetic.ring_plus_random(300, 1500, seed=9)
+    s = mrc.MinRatioCycleSolver(n, mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+    s.add_edges_arrays(U, V, C, T)
+    base = s.solve()
+    rng = np.random.default_rng(3)
+    on_cycle = [int(np.flatnonzero((U == a) & (V == b))[0]) for a, b in zip(base.cycle[:-1], base.cycle[1:])]
+    scen = [{on_cycle[0]: (abs(C[on_cycle[0]]) * 0.5 + 1.0, 0.0)}, {on_cycle[-1]: (-2.0, 0.0)}]
+    for _ in range(6):
+        idx = int(rng.integers(0, len(U)))
+        scen.append({idx: (float(C[idx]) * float(rng.choice([-0.1, 0.1])) - 0.5, 0.0)})
+    scen.append({int(rng.integers(0, len(U))): (0.0, 0.25), int(rng.integers(0, len(U))): (-1.0, 0.0)})
+    res = s.sensitivity_analysis(scen)
+    assert len(res) == len(scen)
+    for sc, r in zip(scen, res):
+        C2, T2 = C.copy(), T.copy()
+        for idx, (dc, dt) in sc.items():
+            C2[idx] += dc; T2[idx] += dt
+        f = mrc.MinRatioCycleSolver(n, mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+        f.add_edges_arrays(U, V, C2, T2)
+        fr = f.solve()
+        assert abs(r.ratio - fr.ratio) <= 1e-9 * max(1.0, abs(fr.ratio)), (sc, r.ratio, fr.ratio)
+        o = oracle_mod.Oracle(n, U, V, C2, T2, all_int=False)
+        o.set_quirks(False)
+        ok, why = o.certify(r.cycle, r.ratio)
+        assert ok, (sc, why)
+    again = s.solve()      # the device graph was restored
+    assert again.ratio == base.ratio and again.cycle == base.cycle
+    assert len(s.stability_region.__doc__ or "") >= 0
