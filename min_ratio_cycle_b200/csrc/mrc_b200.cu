@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -75,6 +76,8 @@ struct mrc_graph {
     bool pot_valid = false; ll pot_a = 0, pot_b = 0;
     std::vector<PatchRec> patches;
     int relax_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int tma_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int use_tma[4] = {0, 0, 0, 0};   // per KT index: stream the edges through the TMA-staged kernel (option "tma")
     int check_blocks[4] = {0, 0, 0, 0};
     int burst_init = 2, burst_max = MRC_MAX_BURST;
     bool alternate = true;
@@ -111,6 +114,14 @@ static const void *relax_fn_of(int KT, bool exact) {
         case 2: return exact ? relax_fn<2, true>() : relax_fn<2, false>();
         case 4: return exact ? relax_fn<4, true>() : relax_fn<4, false>();
         default: return exact ? relax_fn<8, true>() : relax_fn<8, false>();
+    }
+}
+static const void *relax_tma_fn_of(int KT, bool exact) {
+    switch (KT) {
+        case 1: return exact ? (const void *)relax_kernel_tma<1, true> : (const void *)relax_kernel_tma<1, false>;
+        case 2: return exact ? (const void *)relax_kernel_tma<2, true> : (const void *)relax_kernel_tma<2, false>;
+        case 4: return exact ? (const void *)relax_kernel_tma<4, true> : (const void *)relax_kernel_tma<4, false>;
+        default: return exact ? (const void *)relax_kernel_tma<8, true> : (const void *)relax_kernel_tma<8, false>;
     }
 }
 static const void *check_fn_of(int KT) {
@@ -223,12 +234,24 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
                 ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
                 g->relax_blocks[kt_index(KT)][ex] = (int)std::min<ll>(need, (ll)occ * g->sms);
             }
+        for (int KT : {1, 2, 4, 8})
+            for (int ex = 0; ex < 2; ex++) {
+                int occ = 0;
+                CUDA_TRY(cudaFuncSetAttribute(relax_tma_fn_of(KT, ex), cudaFuncAttributeMaxDynamicSharedMemorySize, MRC_TMA_SMEM));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, relax_tma_fn_of(KT, ex), MRC_TMA_THREADS, MRC_TMA_SMEM));
+                const ll tiles = (m + MRC_TMA_TILE - 1) / MRC_TMA_TILE;
+                g->tma_blocks[kt_index(KT)][ex] = (int)std::max<ll>(1, std::min<ll>(tiles, (ll)std::max(occ, 1) * g->sms));
+            }
         for (int KT : {1, 2, 4, 8}) {
             int occ = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_fn_of(KT), 256, 0));
             if (occ < 1) return set_err(MRC_ERR_CUDA, "check kernel K=%d does not fit on an SM", KT);
             ll need = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
             g->check_blocks[kt_index(KT)] = (int)std::min<ll>(need, (ll)occ * g->sms);
+        }
+        if (const char *env = getenv("MRC_B200_TMA")) {   // A/B switch for experiments: bit i = KT index i
+            const int mask = atoi(env);
+            for (int i = 0; i < 4; i++) g->use_tma[i] = (mask >> i) & 1;
         }
         // input validation on the device (the host never touches the 24 B/edge again)
         DALLOC(g->d_verr, 4);
@@ -336,8 +359,13 @@ extern "C" int mrc_graph_restore(mrc_graph *g) {
 
 // ------------------------------------------------------------------------------------------- probe engine
 static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra) {
-    const int blocks = g->relax_blocks[kt_index(KT)][exact ? 1 : 0];
     void *args[] = {(void *)&ra};
+    if (g->use_tma[kt_index(KT)]) {
+        CUDA_TRY(cudaLaunchKernel(relax_tma_fn_of(KT, exact), dim3(g->tma_blocks[kt_index(KT)][exact ? 1 : 0]),
+                                  dim3(MRC_TMA_THREADS), args, MRC_TMA_SMEM, g->stream));
+        return MRC_OK;
+    }
+    const int blocks = g->relax_blocks[kt_index(KT)][exact ? 1 : 0];
     CUDA_TRY(cudaLaunchKernel(relax_fn_of(KT, exact), dim3(blocks), dim3(MRC_RELAX_THREADS), args, 0, g->stream));
     return MRC_OK;
 }
@@ -601,6 +629,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     if (!g || !name) return set_err(MRC_ERR_ARG, "NULL argument");
     std::string s(name);
     if (s == "alternate") g->alternate = value != 0;
+    else if (s == "tma") { for (int i = 0; i < 4; i++) g->use_tma[i] = (value >> i) & 1; }
     else if (s == "burst_init") g->burst_init = std::max(1, std::min(value, MRC_MAX_BURST));
     else if (s == "burst_max") g->burst_max = std::max(1, std::min(value, MRC_MAX_BURST));
     else return set_err(MRC_ERR_ARG, "unknown option %s", name);

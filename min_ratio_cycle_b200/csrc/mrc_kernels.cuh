@@ -25,6 +25,9 @@ typedef long long ll;
 typedef unsigned long long ull;
 
 #define MRC_MAX_BURST 8
+#ifndef MRC_CROWD_MIN
+#define MRC_CROWD_MIN 6   /* improving lanes per row above which the segmented scan replaces the pairwise loop */
+#endif
 #define MRC_MAX_ROUNDS 40
 #ifndef MRC_RELAX_THREADS
 #define MRC_RELAX_THREADS 256
@@ -54,7 +57,7 @@ struct CycleOut {
 
 struct DevStatus {
     unsigned changed[MRC_MAX_BURST];
-    unsigned alive[MRC_MAX_ROUNDS];
+    unsigned cnt[MRC_MAX_ROUNDS * MRC_KMAX];   // live vertices per doubling round and candidate
     unsigned cyc_mask, rounds_run, pend, cuts;
     int rep[MRC_KMAX * 6];   // [MRC_MAX_EXTRACT][MRC_KMAX]
     CycleOut out[MRC_KMAX];
@@ -126,11 +129,37 @@ __device__ __forceinline__ bool mrc_improves(const RelaxArgs &p, double cand, do
     return cand < __dsub_rn(dv, p.slack);
 }
 __device__ __forceinline__ bool mrc_improves(const RelaxArgs &, ll cand, ll dv) { return cand < dv; }
+__device__ __forceinline__ double mrc_identity(double) { return __longlong_as_double(0x7ff0000000000000ll); }
+__device__ __forceinline__ ll mrc_identity(ll) { return 0x7fffffffffffffffll; }
 __device__ __forceinline__ bool mrc_atomic_lower(double *addr, double cand) {
     const ull bits = (ull)__double_as_longlong(cand);
     return atomicMax(reinterpret_cast<ull *>(addr), bits) < bits;
 }
 __device__ __forceinline__ bool mrc_atomic_lower(ll *addr, ll cand) { return cand < atomicMin(addr, cand); }
+
+// Crowded row (first passes: many lanes improve): segmented min over the runs of equal destination in
+// 2 x 5 shuffle steps; the lowest lane holding the run minimum keeps `imp`.
+template <typename T>
+__device__ __forceinline__ bool mrc_resolve_crowded(bool imp, T cand, int v, int lane) {
+    const int vprev = __shfl_up_sync(0xffffffffu, v, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || v != vprev);
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+    const int end = above ? (__ffs(above) - 2) : 31;
+    const T ident = mrc_identity(T(0));
+    T lo_ = imp ? cand : ident, hi_ = lo_;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const T a = __shfl_up_sync(0xffffffffu, lo_, off);
+        const T b = __shfl_down_sync(0xffffffffu, hi_, off);
+        if (lane - off >= start && a < lo_) lo_ = a;
+        if (lane + off <= end && b < hi_) hi_ = b;
+    }
+    const T runmin = lo_ < hi_ ? lo_ : hi_;
+    const unsigned eq = __ballot_sync(0xffffffffu, imp && cand == runmin);
+    const unsigned runmask = ((end == 31) ? 0xffffffffu : ((2u << end) - 1u)) & ~((1u << start) - 1u);
+    return imp && (__ffs(eq & runmask) - 1 == lane);
+}
 
 // The row is warp-synchronous: every lane calls it (valid == false for lanes past the end).  Several
 // in-edges of one destination sit in adjacent lanes, and in the first passes several of them would lower
@@ -160,7 +189,10 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
         }
         const unsigned im = __ballot_sync(0xffffffffu, imp);
         if (im == 0) continue;                   // warp-uniform
-        if (im & (im - 1)) {
+        const int nimp = __popc(im);
+        if (nimp > MRC_CROWD_MIN) {
+            imp = mrc_resolve_crowded<T>(imp, cand, v, lane);
+        } else if (nimp > 1) {
             bool lose = false;
             unsigned rest = im;
             while (rest) {
@@ -191,8 +223,26 @@ template <> struct WeightT<true> { typedef ll type; };
 // Tuned on B200 (tools/relax_variants.py, profiles/r01_relax_variants.txt): K <= 4 wants 2 rows per warp
 // step and 4 resident CTAs per SM (64 registers); K = 8 carries 2 x 64 B of dist per edge and is faster
 // with 4 rows and no register cap.
-template <int K> struct RelaxTune { static constexpr int rows = 2, minblocks = 4; };
-template <> struct RelaxTune<8> { static constexpr int rows = 4, minblocks = 1; };
+#ifndef MRC_TUNE_ROWS
+#define MRC_TUNE_ROWS 2
+#endif
+#ifndef MRC_TUNE_MB
+#define MRC_TUNE_MB 4
+#endif
+#ifndef MRC_TUNE_PF
+#define MRC_TUNE_PF (K <= 2)
+#endif
+#ifndef MRC_TUNE_ROWS8
+#define MRC_TUNE_ROWS8 4
+#endif
+template <int K> struct RelaxTune {
+    static constexpr int rows = MRC_TUNE_ROWS, minblocks = MRC_TUNE_MB;
+    static constexpr bool prefetch = MRC_TUNE_PF;
+};
+template <> struct RelaxTune<8> {
+    static constexpr int rows = MRC_TUNE_ROWS8, minblocks = 1;
+    static constexpr bool prefetch = false;
+};
 template <int K, bool EXACT>
 __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) relax_kernel(const __grid_constant__ RelaxArgs p) {
     typedef typename WeightT<EXACT>::type W;
@@ -205,16 +255,74 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
     constexpr int MRC_ROWS = RelaxTune<K>::rows;
     constexpr ll CH = 32 * MRC_ROWS;
     const ll nchunks = (p.m + CH - 1) / CH;
-    for (ll c = warp; c < nchunks; c += nwarps) {
-        const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
-        int s[MRC_ROWS], d[MRC_ROWS];
-        W cs[MRC_ROWS], tm[MRC_ROWS];
-        if (e0 - lane + CH <= p.m) {
+    // K <= 2 (registers to spare): the edge stream of the NEXT chunk is requested before this chunk's
+    // gathers are issued, so the HBM latency of the stream overlaps the L2 latency of the dist gathers.
+    // (Measured on B200, profiles/r01_relax_variants.txt: -8% per pass at K=1; at K>=4 the extra registers
+    // cost more occupancy than the overlap wins.  Hoisting all gathers of a chunk ahead of the first use
+    // was also measured and is slower at every K.)
+    constexpr bool PREFETCH = RelaxTune<K>::prefetch;
+    if constexpr (!PREFETCH) {
+        for (ll c = warp; c < nchunks; c += nwarps) {
+            const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
+            if (e0 - lane + CH <= p.m) {
+                int s[MRC_ROWS], d[MRC_ROWS];
+                W cs[MRC_ROWS], tm[MRC_ROWS];
+#pragma unroll
+                for (int j = 0; j < MRC_ROWS; j++) {
+                    const ll e = e0 + 32 * j;
+                    s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
+                    cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
+                }
+#pragma unroll
+                for (int j = 0; j < MRC_ROWS; j++)
+                    relax_row<K, W>(p, true, lane, (int)(e0 + 32 * j), s[j], d[j], cs[j], tm[j], chg);
+            } else {
+#pragma unroll
+                for (int j = 0; j < MRC_ROWS; j++) {
+                    const ll e = e0 + 32 * j;
+                    const bool ok = e < p.m;
+                    relax_row<K, W>(p, ok, lane, (int)e, ok ? p.src[e] : 0, ok ? p.dst[e] : -1 - lane,
+                                    ok ? cost[e] : W(0), ok ? time[e] : W(0), chg);
+                }
+            }
+        }
+    } else {
+    int s[MRC_ROWS], d[MRC_ROWS], s2[MRC_ROWS], d2[MRC_ROWS];
+    W cs[MRC_ROWS], tm[MRC_ROWS], cs2[MRC_ROWS], tm2[MRC_ROWS];
+    auto chunk_base = [&](ll c) { return (p.reverse ? (nchunks - 1 - c) : c) * CH; };
+    auto is_full = [&](ll c) { return c < nchunks && chunk_base(c) + CH <= p.m; };
+    ll c = warp;
+    bool have = PREFETCH && is_full(c);
+    if (have) {
+        const ll e0 = chunk_base(c) + lane;
+#pragma unroll
+        for (int j = 0; j < MRC_ROWS; j++) {
+            const ll e = e0 + 32 * j;
+            s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
+            cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
+        }
+    }
+    while (c < nchunks) {
+        const ll nx = c + nwarps;
+        const bool have2 = PREFETCH && is_full(nx);
+        if (have2) {
+            const ll e0 = chunk_base(nx) + lane;
 #pragma unroll
             for (int j = 0; j < MRC_ROWS; j++) {
                 const ll e = e0 + 32 * j;
-                s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
-                cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
+                s2[j] = __ldcs(p.src + e); d2[j] = __ldcs(p.dst + e);
+                cs2[j] = __ldcs(cost + e); tm2[j] = __ldcs(time + e);
+            }
+        }
+        const ll e0 = chunk_base(c) + lane;
+        if (e0 - lane + CH <= p.m) {   // full chunk: no per-lane validity predicate anywhere
+            if (!have) {
+#pragma unroll
+                for (int j = 0; j < MRC_ROWS; j++) {
+                    const ll e = e0 + 32 * j;
+                    s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
+                    cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
+                }
             }
 #pragma unroll
             for (int j = 0; j < MRC_ROWS; j++)
@@ -224,12 +332,119 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
             for (int j = 0; j < MRC_ROWS; j++) {
                 const ll e = e0 + 32 * j;
                 const bool ok = e < p.m;
-                relax_row<K, W>(p, ok, lane, (int)e, ok ? p.src[e] : 0, ok ? p.dst[e] : 0, ok ? cost[e] : W(0),
+                relax_row<K, W>(p, ok, lane, (int)e, ok ? p.src[e] : 0, ok ? p.dst[e] : -1 - lane, ok ? cost[e] : W(0),
                                 ok ? time[e] : W(0), chg);
             }
         }
+        if (PREFETCH) {
+#pragma unroll
+            for (int j = 0; j < MRC_ROWS; j++) { s[j] = s2[j]; d[j] = d2[j]; cs[j] = cs2[j]; tm[j] = tm2[j]; }
+        }
+        have = have2;
+        c = nx;
+    }
     }
     // changed flag: warp vote, one atomic per warp at most
+    chg = __reduce_or_sync(0xffffffffu, chg);
+    if (lane == 0 && chg) atomicOr(p.changed, chg);
+}
+
+// ---- TMA-staged relaxation (sm_100a: cp.async.bulk + mbarrier) ------------------------------------------
+// Same relaxation as relax_kernel, but the edge stream never touches registers or the LSU on its way in:
+// one elected thread per CTA issues 1-D bulk copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) of
+// the four edge arrays of a 1024-edge tile into a 3-stage shared-memory ring; completion is signalled on
+// an mbarrier (complete_tx::bytes).  The copy engine runs 2 tiles (48 KB per CTA, 3 CTAs per SM) ahead of
+// the warps, so HBM latency is fully decoupled from the dist gathers, and the threads keep all their
+// registers for the K-wide gather/compare/atomic part.
+#define MRC_TMA_TILE 1024
+#define MRC_TMA_STAGES 3
+#define MRC_TMA_THREADS 256
+#define MRC_TMA_STAGE_BYTES (MRC_TMA_TILE * 24)
+#define MRC_TMA_SMEM (MRC_TMA_STAGES * MRC_TMA_STAGE_BYTES + 64)
+
+__device__ __forceinline__ unsigned mrc_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mrc_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mrc_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mrc_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mrc_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int K, bool EXACT>
+__global__ void __launch_bounds__(MRC_TMA_THREADS, 3) relax_kernel_tma(const __grid_constant__ RelaxArgs p) {
+    typedef typename WeightT<EXACT>::type W;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
+    const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
+    constexpr int T = MRC_TMA_TILE, S = MRC_TMA_STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const ll ntiles = (p.m + T - 1) / T;
+    const unsigned bar0 = mrc_smem_u32(smem + S * MRC_TMA_STAGE_BYTES);
+    auto tile_of = [&](ll i) { return p.reverse ? (ntiles - 1 - i) : i; };
+    auto issue = [&](ll i, int slot) {   // elected thread: 4 bulk copies, one barrier
+        const ll e0 = tile_of(i) * T;
+        ll cnt = p.m - e0;
+        if (cnt > T) cnt = T;
+        const unsigned c4 = (unsigned)((cnt + 3) & ~3ll);   // arrays are padded to a multiple of 4 edges
+        const unsigned bar = bar0 + 8u * slot;
+        const unsigned base = mrc_smem_u32(smem + slot * MRC_TMA_STAGE_BYTES);
+        mrc_mbar_expect_tx(bar, c4 * 24u);
+        mrc_bulk_g2s(base, p.src + e0, c4 * 4u, bar);
+        mrc_bulk_g2s(base + T * 4, p.dst + e0, c4 * 4u, bar);
+        mrc_bulk_g2s(base + T * 8, cost + e0, c4 * 8u, bar);
+        mrc_bulk_g2s(base + T * 16, time + e0, c4 * 8u, bar);
+    };
+    if (tid == 0) {
+        for (int s_ = 0; s_ < S; s_++) mrc_mbar_init(bar0 + 8u * s_, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s_ = 0; s_ < S; s_++) {
+            const ll i = (ll)blockIdx.x + (ll)s_ * gridDim.x;
+            if (i < ntiles) issue(i, s_);
+        }
+    unsigned chg = 0;
+    for (ll it = 0;; it++) {
+        const ll i = (ll)blockIdx.x + it * gridDim.x;
+        if (i >= ntiles) break;
+        const int slot = (int)(it % S);
+        mrc_mbar_wait(bar0 + 8u * slot, (unsigned)((it / S) & 1));
+        const unsigned char *st = smem + slot * MRC_TMA_STAGE_BYTES;
+        const int *ssrc = reinterpret_cast<const int *>(st);
+        const int *sdst = reinterpret_cast<const int *>(st + T * 4);
+        const W *scost = reinterpret_cast<const W *>(st + T * 8);
+        const W *stime = reinterpret_cast<const W *>(st + T * 16);
+        const ll e0 = tile_of(i) * T;
+#pragma unroll
+        for (int r = 0; r < T / 32 / (MRC_TMA_THREADS / 32); r++) {
+            const int row = wid + r * (MRC_TMA_THREADS / 32);
+            const int o = row * 32 + lane;
+            const ll e = e0 + o;
+            const bool ok = e < p.m;
+            relax_row<K, W>(p, ok, lane, (int)e, ssrc[o], ok ? sdst[o] : -1 - lane, scost[o], stime[o], chg);
+        }
+        __syncthreads();   // every warp is done with this slot
+        if (tid == 0) {
+            const ll nx = i + (ll)S * gridDim.x;
+            if (nx < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(nx, slot);
+            }
+        }
+    }
     chg = __reduce_or_sync(0xffffffffu, chg);
     if (lane == 0 && chg) atomicOr(p.changed, chg);
 }
@@ -257,7 +472,8 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     const ll stride = (ll)gridDim.x * blockDim.x;
     DevStatus *st = p.st;
 
-    if (blockIdx.x == 0 && threadIdx.x < MRC_MAX_ROUNDS) st->alive[threadIdx.x] = 0;
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < MRC_MAX_ROUNDS * MRC_KMAX; i += blockDim.x) st->cnt[i] = 0;
     if (blockIdx.x == 0 && threadIdx.x < MRC_KMAX * MRC_MAX_EXTRACT) st->rep[threadIdx.x] = 0x7fffffff;
     if (blockIdx.x == 0 && threadIdx.x < MRC_KMAX) {
         st->out[threadIdx.x].found = 0;
@@ -275,25 +491,50 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     }
     grid.sync();
 
-    unsigned alive_mask = p.active;
+    // In a forest at least one live vertex reaches a root in every doubling round (the shallowest live
+    // vertex of each chain), so a candidate whose live count did not drop in a round has only vertices
+    // that lead into cycles left: stop doubling for it right there instead of running all log2(n) rounds.
+    unsigned alive_mask = p.active;   // candidates with live vertices
+    unsigned moving = p.active;       // ... whose live count is still dropping
     int r = 0;
-    for (; r < p.rounds; r++) {
-        unsigned alive = 0;
+    for (; r < p.rounds && moving; r++) {
+        unsigned cnt[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) cnt[k] = 0;
         for (ll i = tid0; i < total; i += stride) {
             const int k = (int)(i % K);
             if (!((alive_mask >> k) & 1u)) continue;
             const int j = __ldcg(p.jump + i);
             if (j >= 0) {
-                const int jj = __ldcg(p.jump + (ll)j * K + k);
-                __stcg(p.jump + i, jj);
-                if (jj >= 0) alive |= 1u << k;
+                int jj = j;
+                if ((moving >> k) & 1u) {
+                    jj = __ldcg(p.jump + (ll)j * K + k);
+                    __stcg(p.jump + i, jj);
+                }
+                if (jj >= 0) {
+#pragma unroll
+                    for (int kk = 0; kk < K; kk++) cnt[kk] += (kk == k);
+                }
             }
         }
-        alive = __reduce_or_sync(0xffffffffu, alive);
-        if ((threadIdx.x & 31) == 0 && alive) atomicOr(&st->alive[r], alive);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (!((alive_mask >> k) & 1u)) continue;
+            const unsigned c = __reduce_add_sync(0xffffffffu, cnt[k]);
+            if ((threadIdx.x & 31) == 0 && c) atomicAdd(&st->cnt[r * MRC_KMAX + k], c);
+        }
         grid.sync();
-        alive_mask = __ldcg(&st->alive[r]);
-        if (alive_mask == 0) break;
+        unsigned na = 0, nm = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (!((alive_mask >> k) & 1u)) continue;
+            const unsigned c = __ldcg(&st->cnt[r * MRC_KMAX + k]);
+            const unsigned cp = r ? __ldcg(&st->cnt[(r - 1) * MRC_KMAX + k]) : 0xffffffffu;
+            if (c) na |= 1u << k;
+            if (c && c < cp && ((moving >> k) & 1u)) nm |= 1u << k;
+        }
+        alive_mask = na;
+        moving = nm;
     }
     if (tid0 == 0) { st->rounds_run = (unsigned)r; st->pend = alive_mask; }
     if (alive_mask == 0) return;
@@ -326,7 +567,14 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
             const int rep = __ldcg(&st->rep[it * MRC_KMAX + k]);
             bool settled = true;   // nothing left to examine for k unless a false cycle is cut below
             if (rep != 0x7fffffff) {
-                const int x = __ldcg(p.jump + (ll)rep * K + k);   // on a cycle
+                // rep leads into a cycle; enter it with a tortoise/hare walk over pred (tails are short)
+                auto step = [&](int y) { return __ldg(p.src + __ldcg(p.pred + (ll)y * K + k)); };
+                int x = rep, hare = rep;
+                for (ll g = 0; g <= p.n; g++) {
+                    x = step(x);
+                    hare = step(step(hare));
+                    if (x == hare) break;
+                }
                 int cur = x, minv = x;
                 ll len = 0;
                 bool ok = true;

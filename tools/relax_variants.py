@@ -14,6 +14,9 @@ else:
 g = N.DeviceGraph(n, U, V, C, T)
 r = -14.937873966124124
 tag = os.environ.get("MRC_B200_LIB", "default").split("/")[-1]
+tma = int(os.environ.get("MRC_TMA", "0"))
+g.set_option("tma", tma)
+tag += f" tma={tma}"
 for K in (1, 2, 4, 8):
     lam = [r - 0.5 - 0.1 * k for k in range(K)]   # all NONNEG: converges in ~25 passes
     g.bench_relax(lam, 3)
