@@ -179,6 +179,19 @@ int mrc_solve_exact(mrc_graph *g, int64_t max_den, int64_t max_steps, int strate
                     int64_t *b_out, int64_t *iterations, int64_t *probes_ab, int64_t probes_cap,
                     int64_t *nprobes);
 
+/* ---- batches of small graphs -------------------------------------------------------------------
+ * Replaces a loop of B independent solve() calls (each _solve_numeric, solver.py:1001-1122) for graphs that
+ * fit one SM's shared memory (n <= 65535, 20*m + 28*K*n bytes <= ~220 KB; BASELINE config 4: n=64, m=4032):
+ * one CTA per graph runs the whole multisection search on the device.  Graph g owns edges
+ * [edge_off[g], edge_off[g+1]) of the concatenated arrays, destination-sorted, with LOCAL vertex ids.
+ * Outputs per graph: status (MRC_OK / MRC_ERR_NO_CYCLE / MRC_ERR_CONVERGENCE), ratio, sums, closed cycle
+ * (cycle_buf[g*cycle_cap ..)), rounds.  stats_out (may be NULL): kernel time and relaxation count. */
+int mrc_batch_solve_numeric(int64_t B, const int32_t *nverts, const int64_t *edge_off, const int32_t *src,
+                            const int32_t *dst, const double *cost, const double *time, int max_iter, double tol,
+                            double slack, int K, int device, double *ratio, double *sum_cost, double *sum_time,
+                            int32_t *cycle_len, int32_t *cycle_buf, int64_t cycle_cap, int32_t *iterations,
+                            int32_t *status, mrc_stats *stats_out);
+
 #ifdef __cplusplus
 }
 #endif

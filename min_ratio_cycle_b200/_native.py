@@ -28,7 +28,7 @@ EXPORTS = [
     "mrc_graph_info", "mrc_numeric_bounds", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
     "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
     "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
-    "mrc_bench_relax", "mrc_set_option",
+    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric",
 ]
 
 
@@ -90,6 +90,8 @@ def lib():
                                   p64, C.c_int64, p64]
     L.mrc_bench_relax.argtypes = [vp, pd, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.mrc_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    L.mrc_batch_solve_numeric.argtypes = [C.c_int64, p32, p64, p32, p32, pd, pd, C.c_int, C.c_double, C.c_double, C.c_int,
+                                          C.c_int, pd, pd, pd, p32, p32, C.c_int64, p32, p32, C.POINTER(Stats)]
     for name in EXPORTS:
         if name not in ("mrc_last_error",):
             getattr(L, name).restype = C.c_int
@@ -301,3 +303,30 @@ def reduce_round(lam, verdict, cyc_ratio, lo: float, hi: float, have_cycle: bool
     check(lib().mrc_reduce_round(len(lam), _ptr(lam, C.c_double), _ptr(vd, C.c_int32), _ptr(cr, C.c_double),
                                  C.byref(clo), C.byref(chi), C.byref(hc), C.byref(best)))
     return clo.value, chi.value, bool(hc.value), best.value
+
+
+def batch_solve_numeric(nverts, edge_off, src, dst, cost, time, max_iter: int = 60, tol: float = 1e-12,
+                        slack: float = 1e-15, K: int = 4, device: int = 0):
+    """
+    mrc_batch_solve_numeric: B small graphs (concatenated, each destination-sorted with local ids), one CTA
+    per graph.  Returns dict of per-graph arrays + stats.
+    """
+    nv = np.ascontiguousarray(nverts, dtype=np.int32)
+    off = np.ascontiguousarray(edge_off, dtype=np.int64)
+    s_ = np.ascontiguousarray(src, dtype=np.int32); d_ = np.ascontiguousarray(dst, dtype=np.int32)
+    c_ = np.ascontiguousarray(cost, dtype=np.float64); t_ = np.ascontiguousarray(time, dtype=np.float64)
+    B = len(nv)
+    cap = int(nv.max()) + 1
+    ratio = np.zeros(B); sc = np.zeros(B); st = np.zeros(B)
+    clen = np.zeros(B, np.int32); cbuf = np.zeros(B * cap, np.int32); it = np.zeros(B, np.int32)
+    status = np.zeros(B, np.int32)
+    stats = Stats()
+    check(lib().mrc_batch_solve_numeric(B, _ptr(nv, C.c_int32), _ptr(off, C.c_int64), _ptr(s_, C.c_int32),
+                                        _ptr(d_, C.c_int32), _ptr(c_, C.c_double), _ptr(t_, C.c_double), int(max_iter),
+                                        float(tol), float(slack), int(K), int(device), _ptr(ratio, C.c_double),
+                                        _ptr(sc, C.c_double), _ptr(st, C.c_double), _ptr(clen, C.c_int32),
+                                        _ptr(cbuf, C.c_int32), cap, _ptr(it, C.c_int32), _ptr(status, C.c_int32),
+                                        C.byref(stats)))
+    cycles = [cbuf[g * cap: g * cap + clen[g]].tolist() for g in range(B)]
+    return dict(status=status, ratio=ratio, sum_cost=sc, sum_time=st, cycles=cycles, iterations=it,
+                stats=stats.as_dict())

@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libmrc_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "mrc_b200.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "mrc_kernels.cuh"), os.path.join(ROOT, "include", "mrc_b200.h")]
+DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("mrc_kernels.cuh", "mrc_batch.cuh", "mrc_search.h")] + [
+    os.path.join(ROOT, "include", "mrc_b200.h")]
 
 
 def nvcc_path() -> str:

@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "mrc_kernels.cuh"
+#include "mrc_search.h"
+#include "mrc_batch.cuh"
 
 typedef __int128 i128;
 
@@ -639,20 +641,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
 // ------------------------------------------------------------------------------- numeric lambda search
 extern "C" int mrc_plan_candidates(double lo, double hi, int have_cycle, double tol, int K_total, double *lam_out) {
     if (!lam_out || K_total < 1) return set_err(MRC_ERR_ARG, "bad plan arguments");
-    const double gap = hi - lo;
-    const int K = K_total;
-    if (!have_cycle) {
-        if (K == 1) { lam_out[0] = (lo + hi) / 2.0; return MRC_OK; }   // the reference's midpoint, solver.py:1053
-        for (int j = 1; j <= K; j++) lam_out[j - 1] = lo + gap * ((double)j / (double)(K + 1));
-        return MRC_OK;
-    }
-    // hi is the ratio of a known cycle: K-1 interior points + the certifier just below hi.  If the
-    // certifier has no negative cycle, the known cycle is optimal to within tol and the search ends.
-    const double cert = hi - std::min(tol * 0.75, gap / (2.0 * K));
-    if (K == 1) { lam_out[0] = cert; return MRC_OK; }
-    for (int j = 1; j < K; j++) lam_out[j - 1] = lo + gap * ((double)j / (double)K);
-    lam_out[K - 1] = cert;
-    if (K >= 2 && lam_out[K - 2] >= cert) lam_out[K - 2] = lo + (cert - lo) * 0.5;
+    mrc_plan(lo, hi, have_cycle, tol, K_total, lam_out);
     return MRC_OK;
 }
 
@@ -660,29 +649,7 @@ extern "C" int mrc_reduce_round(int K_total, const double *lam, const int32_t *v
                                 double *lo, double *hi, int *have_cycle, int *best_idx) {
     if (!lam || !verdict || !cyc_ratio || !lo || !hi || !have_cycle || !best_idx)
         return set_err(MRC_ERR_ARG, "NULL argument");
-    double nlo = *lo, nhi = *hi;
-    int best = -1, hc = *have_cycle;
-    double best_ratio = hc ? *hi : INFINITY;
-    for (int k = 0; k < K_total; k++) {
-        switch (verdict[k]) {
-            case MRC_V_NEG:
-            case MRC_V_TIE:
-                if (cyc_ratio[k] < best_ratio) { best_ratio = cyc_ratio[k]; best = k; }
-                if (verdict[k] == MRC_V_TIE) nlo = std::max(nlo, lam[k]);
-                break;
-            case MRC_V_NEG_NOCYCLE:   // reference: hi = mid without a cycle (solver.py:1057-1060)
-                if (lam[k] < nhi) { nhi = lam[k]; }
-                break;
-            case MRC_V_NONNEG:
-                nlo = std::max(nlo, lam[k]);
-                break;
-            default: break;
-        }
-    }
-    if (best >= 0 && best_ratio <= nhi) { nhi = best_ratio; hc = 1; }
-    else if (nhi < *hi) hc = 0;   // upper end moved without a cycle to show for it
-    if (nlo > nhi) nlo = nhi;     // rounding noise near lambda*
-    *lo = nlo; *hi = nhi; *have_cycle = hc; *best_idx = best;
+    *best_idx = mrc_reduce(K_total, lam, verdict, cyc_ratio, lo, hi, have_cycle);
     return MRC_OK;
 }
 
@@ -1006,4 +973,112 @@ extern "C" int mrc_solve_exact(mrc_graph *g, int64_t max_den, int64_t max_steps,
         aL = aM; bL = bM;                           // :795
     }
     return set_err(MRC_ERR_SB_STEPS, "Stern-Brocot search did not converge");   // :797
+}
+
+// ------------------------------------------------------------------------------------ small-graph batches
+static const void *batch_fn_of(int KT) {
+    switch (KT) {
+        case 1: return (const void *)batch_solve_kernel<1>;
+        case 2: return (const void *)batch_solve_kernel<2>;
+        case 4: return (const void *)batch_solve_kernel<4>;
+        default: return (const void *)batch_solve_kernel<8>;
+    }
+}
+
+/*
+ * B independent small graphs, one CTA each, the whole lambda search on the device (mrc_batch.cuh).
+ * Replaces a Python loop of B solve() calls (BASELINE config 4).  Every graph is destination-sorted with
+ * LOCAL vertex ids; edge_off[B+1] delimits the graphs in the concatenated arrays.
+ */
+extern "C" int mrc_batch_solve_numeric(int64_t B, const int32_t *nverts, const int64_t *edge_off, const int32_t *src,
+                                       const int32_t *dst, const double *cost, const double *time, int max_iter,
+                                       double tol, double slack, int K, int device, double *ratio, double *sum_cost,
+                                       double *sum_time, int32_t *cycle_len, int32_t *cycle_buf, int64_t cycle_cap,
+                                       int32_t *iterations, int32_t *status, mrc_stats *stats_out) {
+    if (B <= 0 || !nverts || !edge_off || !src || !dst || !cost || !time || !ratio || !sum_cost || !sum_time ||
+        !cycle_len || !cycle_buf || !iterations || !status)
+        return set_err(MRC_ERR_ARG, "NULL or empty batch argument");
+    if (K < 1 || K > MRC_KMAX) return set_err(MRC_ERR_ARG, "K must be in [1,%d]", MRC_KMAX);
+    int ndev = 0;
+    MRC_TRY(mrc_device_count(&ndev));
+    if (device < 0 || device >= ndev) return set_err(MRC_ERR_ARG, "device %d out of range", device);
+    const int KT = kt_of(K);
+    int n_max = 1, m_max = 1;
+    const ll M = edge_off[B];
+    for (ll g = 0; g < B; g++) {
+        const ll mg = edge_off[g + 1] - edge_off[g];
+        if (nverts[g] <= 0 || nverts[g] > 65535 || mg <= 0 || mg > 0x7fffffff)
+            return set_err(MRC_ERR_ARG, "graph %lld: batch solver needs 1 <= n <= 65535 and m >= 1", g);
+        n_max = std::max(n_max, (int)nverts[g]); m_max = std::max<ll>(m_max, mg);
+        for (ll e = edge_off[g]; e < edge_off[g + 1]; e++) {
+            if ((unsigned)src[e] >= (unsigned)nverts[g] || (unsigned)dst[e] >= (unsigned)nverts[g])
+                return set_err(MRC_ERR_ARG, "graph %lld: endpoint outside [0,n)", g);
+            if (!(time[e] > 0)) return set_err(MRC_ERR_ARG, "graph %lld: time must be strictly positive", g);
+        }
+    }
+    n_max = (n_max + 3) & ~3; m_max = (m_max + 3) & ~3;
+    const size_t smem = mrc_batch_smem(n_max, m_max, KT);
+    CUDA_TRY(cudaSetDevice(device));
+    int smem_cap = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (smem > (size_t)smem_cap - 4096)
+        return set_err(MRC_ERR_ARG, "largest graph of the batch (n=%d, m=%d) needs %zu B of shared memory (> %d): use mrc_graph_create",
+                       n_max, m_max, smem, smem_cap);
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    BatchArgs a;
+    memset(&a, 0, sizeof a);
+    ll *d_off; int *d_nv, *d_src, *d_dst, *d_len, *d_buf, *d_it, *d_status; double *d_c, *d_t, *d_r, *d_sc, *d_st; ull *d_cnt;
+    cudaEvent_t e0, e1;
+    int rc = [&]() -> int {
+        CUDA_TRY(cudaMallocAsync((void **)&d_off, (B + 1) * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_nv, B * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_src, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_dst, M * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_c, M * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_t, M * 8, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_r, B * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_sc, B * 8, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_st, B * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_len, B * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_buf, B * cycle_cap * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_it, B * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_status, B * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_cnt, 8, st));
+        CUDA_TRY(cudaMemcpyAsync(d_off, edge_off, (B + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_nv, nverts, B * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_src, src, M * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_dst, dst, M * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_c, cost, M * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_t, time, M * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
+        CUDA_TRY(cudaMemsetAsync(d_buf, 0, B * cycle_cap * 4, st));
+        a.B = (int)B; a.edge_off = d_off; a.nverts = d_nv; a.src = d_src; a.dst = d_dst; a.cost = d_c; a.time = d_t;
+        a.tol = tol; a.slack = slack; a.max_iter = max_iter; a.K = K;
+        a.ratio = d_r; a.sum_cost = d_sc; a.sum_time = d_st; a.cyc_len = d_len; a.cyc_buf = d_buf; a.cyc_cap = cycle_cap;
+        a.iters = d_it; a.status = d_status; a.relax_count = d_cnt; a.n_max = n_max; a.m_max = m_max;
+        CUDA_TRY(cudaFuncSetAttribute(batch_fn_of(KT), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+        void *args[] = {(void *)&a};
+        CUDA_TRY(cudaEventRecord(e0, st));
+        CUDA_TRY(cudaLaunchKernel(batch_fn_of(KT), dim3((unsigned)B), dim3(MRC_BATCH_THREADS), args, smem, st));
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaMemcpyAsync(ratio, d_r, B * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(sum_cost, d_sc, B * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(sum_time, d_st, B * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(cycle_len, d_len, B * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(cycle_buf, d_buf, B * cycle_cap * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(iterations, d_it, B * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(status, d_status, B * 4, cudaMemcpyDeviceToHost, st));
+        ull cnt = 0;
+        CUDA_TRY(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (stats_out) {
+            memset(stats_out, 0, sizeof *stats_out);
+            stats_out->relax_launches = 1; stats_out->relax_edge_visits = (int64_t)cnt; stats_out->relax_ms = ms;
+            stats_out->probes = B * K; stats_out->h2d_bytes = M * 24 + B * 12; stats_out->d2h_bytes = B * (36 + cycle_cap * 4);
+        }
+        void *ptrs[] = {d_off, d_nv, d_src, d_dst, d_c, d_t, d_r, d_sc, d_st, d_len, d_buf, d_it, d_status, d_cnt};
+        for (void *q : ptrs) cudaFreeAsync(q, st);
+        cudaStreamSynchronize(st);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return MRC_OK;
+    }();
+    cudaStreamDestroy(st);
+    return rc;
 }

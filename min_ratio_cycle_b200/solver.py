@@ -116,6 +116,37 @@ class SolverResult:
         return iter((self.cycle, self.sum_cost, self.sum_time, self.ratio))
 
 
+def dominated_mask(n: int, U, V, Cw, Tw):
+    """
+    Boolean mask of edges the reference's _remove_dominated_edges (solver.py:531-575) would delete: another
+    edge with the same (u,v) has cost <= and time <= with one strict.  None when nothing is dominated.
+    Vectorised: only (u,v) groups with more than one member are examined.
+    """
+    m = len(U)
+    if m < 2:
+        return None
+    key = U * n + V
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    dup = np.zeros(m, dtype=bool)
+    same = ks[1:] == ks[:-1]
+    dup[1:] |= same
+    dup[:-1] |= same
+    if not dup.any():
+        return None
+    drop = np.zeros(m, dtype=bool)
+    idx = order[dup]
+    kd = ks[dup]
+    bounds = np.flatnonzero(np.concatenate([[True], kd[1:] != kd[:-1], [True]]))
+    for s, e in zip(bounds[:-1], bounds[1:]):
+        grp = idx[s:e]
+        c, t = Cw[grp], Tw[grp]
+        le = (c[:, None] <= c[None, :]) & (t[:, None] <= t[None, :])
+        lt = (c[:, None] < c[None, :]) | (t[:, None] < t[None, :])
+        drop[grp[(le & lt).any(axis=0)]] = True
+    return drop if drop.any() else None
+
+
 def _is_integral(x) -> bool:
     """`_all_int` rule of the reference (solver.py:289-298): int, Fraction, or an integral float."""
     return isinstance(x, (int, Fraction)) or (isinstance(x, float) and x.is_integer())
@@ -332,26 +363,8 @@ class MinRatioCycleSolver:
         if m < 2:
             return
         U, V, Cw, Tw = self._insertion_arrays()
-        key = U * self.n + V
-        order = np.argsort(key, kind="stable")
-        ks = key[order]
-        dup = np.zeros(m, dtype=bool)
-        same = ks[1:] == ks[:-1]
-        dup[1:] |= same
-        dup[:-1] |= same
-        if not dup.any():
-            return
-        drop = np.zeros(m, dtype=bool)
-        idx = order[dup]
-        kd = ks[dup]
-        bounds = np.flatnonzero(np.concatenate([[True], kd[1:] != kd[:-1], [True]]))
-        for s, e in zip(bounds[:-1], bounds[1:]):
-            grp = idx[s:e]
-            c, t = Cw[grp], Tw[grp]
-            le = (c[:, None] <= c[None, :]) & (t[:, None] <= t[None, :])
-            lt = (c[:, None] < c[None, :]) | (t[:, None] < t[None, :])
-            drop[grp[(le & lt).any(axis=0)]] = True
-        if not drop.any():
+        drop = dominated_mask(self.n, U, V, Cw, Tw)
+        if drop is None:
             return
         m1 = len(self._edges)
         self._edges = [e for i, e in enumerate(self._edges) if not drop[i]]

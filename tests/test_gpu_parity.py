@@ -342,3 +342,58 @@ def test_sensitivity_analysis_matches_fresh_solves(mrc, oracle_mod):
     again = s.solve()      # the device graph was restored
     assert again.ratio == base.ratio and again.cycle == base.cycle
     assert len(s.stability_region.__doc__ or "") >= 0
+
+
+# --------------------------------------------------------------------------- batches of small graphs (config 4)
+def test_batch_currency_graphs(mrc, oracle_mod):
+    """32 currency graphs (n=64, m=4032) in one launch: each certified by the oracle; the two with a reference
+    solve in the fixtures match it; the batch equals the single-graph GPU path."""
+    from min_ratio_cycle_b200 import batch, synthetic
+    seeds = list(range(1000, 1032))
+    graphs = [synthetic.currency_graph(64, s) for s in seeds]
+    res, stats = batch.solve_min_ratio_cycle_batch(graphs, mrc.SolverConfig(log_level=mrc.LogLevel.NONE), return_stats=True)
+    assert len(res) == 32 and stats["relax_edge_visits"] > 0
+    for s, gph, r in zip(seeds, graphs, res):
+        n, U, V, C, T = gph
+        assert r.success and r.cycle[0] == r.cycle[-1] == min(r.cycle)
+        o = oracle_mod.Oracle(n, U, V, C, T, all_int=False)
+        o.set_quirks(False)
+        ok, why = o.certify(r.cycle, r.ratio)
+        assert ok, (s, why)
+        key = f"currency_{s}"
+        if key in SEEDED:
+            gold = SEEDED[key]["solve"]
+            assert abs(r.ratio - gold["ratio"]) <= 1e-9 * max(1.0, abs(gold["ratio"])), key
+    n, U, V, C, T = graphs[0]
+    s1 = mrc.MinRatioCycleSolver(n, mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+    s1.add_edges_arrays(U, V, C, T)
+    r1 = s1.solve()
+    assert abs(r1.ratio - res[0].ratio) <= 1e-12 and r1.cycle == res[0].cycle
+
+
+def test_batch_mixed_small_graphs(mrc, oracle_mod):
+    """Ragged batch: the 120 small random fixtures (n 2..14, self-loops, parallel edges, acyclic ones)."""
+    from min_ratio_cycle_b200 import batch
+    names = sorted(SMALL)
+    graphs = []
+    for nm in names:
+        U, V, C, T = edges_to_arrays(SMALL[nm]["edges"])
+        graphs.append((SMALL[nm]["n"], U, V, C, T))
+    for K in (1, 4):
+        res = batch.solve_min_ratio_cycle_batch(graphs, mrc.SolverConfig(log_level=mrc.LogLevel.NONE, gpu_candidates=K))
+        nfail = 0
+        for nm, r in zip(names, res):
+            rec = SMALL[nm]
+            chk = checker(oracle_mod, rec)
+            if not r.success:
+                nfail += 1
+                # no cycle at all: the quirk-free detector must agree at the top of the bracket
+                lo, hi = chk.bounds()
+                assert chk.detect_negative_cycle_numeric(hi, 1e-15, True).has_neg == 0, nm
+                continue
+            ok, why = chk.certify(r.cycle, r.ratio)
+            assert ok, (nm, K, why)
+            if rec["solve"]["ok"]:
+                v, why = three_way(chk, {"cycle": r.cycle, "ratio": r.ratio}, rec["solve"])
+                assert v in (MATCH, REF_SUBOPTIMAL), (nm, K, why)
+        assert nfail <= 10
