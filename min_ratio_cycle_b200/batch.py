@@ -40,6 +40,16 @@ def _prepare(graphs, preprocess: bool):
             np.concatenate(Cs), np.concatenate(Ts))
 
 
+def _cycle_weights_float(closed_cycle, src, dst, cost, time):
+    sc = st = 0.0
+    for u, v in zip(closed_cycle[:-1], closed_cycle[1:]):
+        a, b = np.searchsorted(dst, v, "left"), np.searchsorted(dst, v, "right")
+        hit = a + np.flatnonzero(src[a:b] == u)
+        k = hit[int(np.argmin(cost[hit] / time[hit]))] if hit.size > 1 else hit[0]
+        sc += float(cost[k]); st += float(time[k])
+    return sc, st
+
+
 def solve_min_ratio_cycle_batch(graphs, config: SolverConfig | None = None, return_stats: bool = False):
     """
     graphs: sequence of (n_vertices, U, V, cost, time) arrays in insertion order.
@@ -52,6 +62,12 @@ def solve_min_ratio_cycle_batch(graphs, config: SolverConfig | None = None, retu
     results = []
     for g in range(len(nv)):
         st = int(out["status"][g])
+        if st != N.ERR_NO_CYCLE:
+            # reported sums follow the reference's hop rule (_compute_cycle_weights_float, solver.py:1296-1327):
+            # among parallel (u,v) edges the first with minimal cost/time, accumulated in cycle order
+            lo, hi = int(off[g]), int(off[g + 1])
+            sc, stt = _cycle_weights_float(out["cycles"][g], S[lo:hi], D[lo:hi], Cs[lo:hi], Ts[lo:hi])
+            out["sum_cost"][g], out["sum_time"][g], out["ratio"][g] = sc, stt, sc / stt
         if st == N.ERR_NO_CYCLE:
             results.append(SolverResult([], 0, 0, float("inf"), success=False, error_message="No negative cycle found"))
             continue
