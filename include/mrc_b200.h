@@ -110,6 +110,10 @@ int mrc_probe_numeric(mrc_graph *g, const double *lam, int K, double slack, uint
                       int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap, double *sum_cost, double *sum_time,
                       int64_t *passes);
 
+/* Full cycle of candidate k of the LAST probe (numeric or exact), for callers that probed with a small
+ * cyc_cap: CLOSED vertex list; *cycle_len = 0 if that candidate extracted none. */
+int mrc_fetch_cycle(mrc_graph *g, int k, int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len);
+
 /* ---- numeric lambda search -----------------------------------------------------------------
  * Replaces the bisection of _solve_numeric (solver.py:1017-1117) by K-way multisection: every round
  * evaluates K lambdas of the bracket in one batched probe; a verified negative cycle tightens the upper

@@ -28,7 +28,7 @@ EXPORTS = [
     "mrc_graph_info", "mrc_numeric_bounds", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
     "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
     "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
-    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric",
+    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
     L.mrc_zero_cycle_exact.argtypes = [vp, C.c_int64, C.c_int64, pu8, p32, C.c_int64, p64, p64, p64]
     L.mrc_solve_exact.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, p32, C.c_int64, p64, p64, p64, p64, p64, p64,
                                   p64, C.c_int64, p64]
+    L.mrc_fetch_cycle.argtypes = [vp, C.c_int, p32, C.c_int64, p64]
     L.mrc_bench_relax.argtypes = [vp, pd, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.mrc_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.mrc_batch_solve_numeric.argtypes = [C.c_int64, p32, p64, p32, p32, pd, pd, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -195,15 +196,15 @@ class DeviceGraph:
         """K-batched analogue of _detect_negative_cycle_numeric.  Returns a list of dicts."""
         lam = np.ascontiguousarray(lams, dtype=np.float64)
         K = len(lam)
-        cap = int(cyc_cap if cyc_cap is not None else self.n + 1)
-        vd = np.zeros(K, np.int32); cl = np.zeros(K, np.int32); buf = np.zeros(K * cap, np.int32)
+        cap = int(cyc_cap if cyc_cap is not None else min(self.n + 1, 1024))   # longer cycles are fetched below
+        vd = np.zeros(K, np.int32); cl = np.zeros(K, np.int32); buf = np.empty(K * cap, np.int32)
         sc = np.zeros(K); st = np.zeros(K); ps = np.zeros(K, np.int64)
         check(lib().mrc_probe_numeric(self._h, _ptr(lam, C.c_double), K, float(slack), int(flags), _ptr(vd, C.c_int32),
                                       _ptr(cl, C.c_int32), _ptr(buf, C.c_int32), cap, _ptr(sc, C.c_double),
                                       _ptr(st, C.c_double), _ptr(ps, C.c_int64)))
         out = []
         for k in range(K):
-            cyc = buf[k * cap: k * cap + min(cl[k], cap)].tolist() if cl[k] else None
+            cyc = self._cycle_of(k, buf, cap, int(cl[k]))
             out.append(dict(lam=float(lam[k]), verdict=int(vd[k]), cycle=cyc, cycle_len=int(cl[k]),
                             sum_cost=float(sc[k]), sum_time=float(st[k]), passes=int(ps[k])))
         return out
@@ -211,18 +212,28 @@ class DeviceGraph:
     def probe_exact(self, a, b, flags: int = 0, cyc_cap: int | None = None):
         a = np.ascontiguousarray(a, dtype=np.int64); b = np.ascontiguousarray(b, dtype=np.int64)
         K = len(a)
-        cap = int(cyc_cap if cyc_cap is not None else self.n + 1)
-        vd = np.zeros(K, np.int32); cl = np.zeros(K, np.int32); buf = np.zeros(K * cap, np.int32)
+        cap = int(cyc_cap if cyc_cap is not None else min(self.n + 1, 1024))
+        vd = np.zeros(K, np.int32); cl = np.zeros(K, np.int32); buf = np.empty(K * cap, np.int32)
         sc = np.zeros(K, np.int64); st = np.zeros(K, np.int64); ps = np.zeros(K, np.int64)
         check(lib().mrc_probe_exact(self._h, _ptr(a, C.c_int64), _ptr(b, C.c_int64), K, int(flags), _ptr(vd, C.c_int32),
                                     _ptr(cl, C.c_int32), _ptr(buf, C.c_int32), cap, _ptr(sc, C.c_int64),
                                     _ptr(st, C.c_int64), _ptr(ps, C.c_int64)))
         out = []
         for k in range(K):
-            cyc = buf[k * cap: k * cap + min(cl[k], cap)].tolist() if cl[k] else None
+            cyc = self._cycle_of(k, buf, cap, int(cl[k]))
             out.append(dict(a=int(a[k]), b=int(b[k]), verdict=int(vd[k]), cycle=cyc, cycle_len=int(cl[k]),
                             sum_cost=int(sc[k]), sum_time=int(st[k]), passes=int(ps[k])))
         return out
+
+    def _cycle_of(self, k: int, buf, cap: int, length: int):
+        if not length:
+            return None
+        if length <= cap:
+            return buf[k * cap: k * cap + length].tolist()
+        full = np.empty(length, np.int32)
+        n = C.c_int64()
+        check(lib().mrc_fetch_cycle(self._h, k, _ptr(full, C.c_int32), length, C.byref(n)))
+        return full[: n.value].tolist()
 
     # -- searches -----------------------------------------------------------
     def solve_numeric(self, lo: float, hi: float, max_iter: int = 60, tol: float = 1e-12, slack: float = 1e-15,

@@ -49,6 +49,15 @@ struct PatchRec {
     double *d_oldc, *d_oldt;
 };
 
+struct ProbeOut {
+    int verdict = -1;
+    int len = 0;
+    int minv = -1;
+    double sumc = 0, sumt = 0;   // predecessor-walk order (device)
+    ll isumc = 0, isumt = 0;
+    ll passes = 0;
+};
+
 struct mrc_graph {
     int device = 0, sms = 0;
     cudaStream_t stream = nullptr;
@@ -59,7 +68,7 @@ struct mrc_graph {
     ll *d_icost = nullptr, *d_itime = nullptr;
     // workspace
     void *d_dist = nullptr;      // [n][KT] f64 or i64
-    int *d_pred = nullptr;       // [n][KT]
+    ull *d_pred = nullptr;       // [n][KT] (src vertex << 32 | edge index)
     int *d_jump = nullptr;       // [n][KT]
     int *d_cyc_edges = nullptr;  // [KMAX][cap]
     ll cyc_cap = 0;
@@ -77,6 +86,8 @@ struct mrc_graph {
     // dist cache: the last exact K=1 probe that converged left potentials in d_dist
     bool pot_valid = false; ll pot_a = 0, pot_b = 0;
     std::vector<PatchRec> patches;
+    ProbeOut last_res[MRC_KMAX];   // last probe's per-candidate results (cycles stay on the device until the next probe)
+    bool last_exact = false; int last_K = 0;
     int relax_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     int tma_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     int use_tma[4] = {0, 0, 0, 0};   // per KT index: stream the edges through the TMA-staged kernel (option "tma")
@@ -84,15 +95,6 @@ struct mrc_graph {
     int burst_init = 2, burst_max = MRC_MAX_BURST;
     bool alternate = true;
     mrc_stats stats;
-};
-
-struct ProbeOut {
-    int verdict = -1;
-    int len = 0;
-    int minv = -1;
-    double sumc = 0, sumt = 0;   // predecessor-walk order (device)
-    ll isumc = 0, isumt = 0;
-    ll passes = 0;
 };
 
 extern "C" int mrc_abi_version(void) { return MRC_ABI_VERSION; }
@@ -133,6 +135,30 @@ static const void *check_fn_of(int KT) {
         case 4: return (const void *)cycle_check_kernel<4>;
         default: return (const void *)cycle_check_kernel<8>;
     }
+}
+
+// Device facts that do not depend on the graph are queried once per process and device.
+struct DeviceInfo {
+    bool ready = false;
+    int sms = 0, occ_relax[4][2], occ_tma[4][2], occ_check[4];
+};
+static DeviceInfo g_devinfo[64];
+static int device_info(int device, const DeviceInfo **out) {
+    DeviceInfo &d = g_devinfo[device & 63];
+    if (!d.ready) {
+        CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device));
+        for (int KT : {1, 2, 4, 8})
+            for (int ex = 0; ex < 2; ex++) {
+                const int i = kt_index(KT);
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_relax[i][ex], relax_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
+                CUDA_TRY(cudaFuncSetAttribute(relax_tma_fn_of(KT, ex), cudaFuncAttributeMaxDynamicSharedMemorySize, MRC_TMA_SMEM));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_tma[i][ex], relax_tma_fn_of(KT, ex), MRC_TMA_THREADS, MRC_TMA_SMEM));
+                if (ex == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_check[i], check_fn_of(KT), 256, 0));
+            }
+        d.ready = true;
+    }
+    *out = &d;
+    return MRC_OK;
 }
 
 extern "C" int mrc_graph_destroy(mrc_graph *g) {
@@ -176,9 +202,9 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
     memset(&g->stats, 0, sizeof g->stats);
     g->device = device; g->n = n; g->m = m;
     int rc = [&]() -> int {
-        cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-        g->sms = prop.multiProcessorCount;
+        const DeviceInfo *di = nullptr;
+        MRC_TRY(device_info(device, &di));
+        g->sms = di->sms;
         CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
         for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
         const size_t m4 = ((size_t)m + 3) & ~(size_t)3;   // vector loads never read past the allocation
@@ -217,7 +243,7 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
             g->min_ratio_i = mn; g->max_ratio_i = mx;
         }
         DALLOC(g->d_dist, (size_t)n * MRC_KMAX * 8);
-        DALLOC(g->d_pred, (size_t)n * MRC_KMAX * 4);
+        DALLOC(g->d_pred, (size_t)n * MRC_KMAX * 8);
         DALLOC(g->d_jump, (size_t)n * MRC_KMAX * 4);
         g->cyc_cap = n;
         DALLOC(g->d_cyc_edges, (size_t)g->cyc_cap * MRC_KMAX * 4);
@@ -228,29 +254,17 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         // launch geometry: persistent grids sized to whole waves of the 148 SMs
         for (int KT : {1, 2, 4, 8})
             for (int ex = 0; ex < 2; ex++) {
-                int occ = 0;
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, relax_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
-                if (occ < 1) return set_err(MRC_ERR_CUDA, "relax kernel K=%d does not fit on an SM", KT);
+                const int i = kt_index(KT);
+                if (di->occ_relax[i][ex] < 1 || di->occ_check[i] < 1) return set_err(MRC_ERR_CUDA, "kernel K=%d does not fit on an SM", KT);
                 const int rows = KT == 8 ? RelaxTune<8>::rows : RelaxTune<1>::rows;
                 const ll chunks = (m + 32 * rows - 1) / (32 * rows);   // one chunk per warp step
-                ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
-                g->relax_blocks[kt_index(KT)][ex] = (int)std::min<ll>(need, (ll)occ * g->sms);
-            }
-        for (int KT : {1, 2, 4, 8})
-            for (int ex = 0; ex < 2; ex++) {
-                int occ = 0;
-                CUDA_TRY(cudaFuncSetAttribute(relax_tma_fn_of(KT, ex), cudaFuncAttributeMaxDynamicSharedMemorySize, MRC_TMA_SMEM));
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, relax_tma_fn_of(KT, ex), MRC_TMA_THREADS, MRC_TMA_SMEM));
+                const ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
+                g->relax_blocks[i][ex] = (int)std::min<ll>(need, (ll)di->occ_relax[i][ex] * g->sms);
                 const ll tiles = (m + MRC_TMA_TILE - 1) / MRC_TMA_TILE;
-                g->tma_blocks[kt_index(KT)][ex] = (int)std::max<ll>(1, std::min<ll>(tiles, (ll)std::max(occ, 1) * g->sms));
+                g->tma_blocks[i][ex] = (int)std::max<ll>(1, std::min<ll>(tiles, (ll)std::max(di->occ_tma[i][ex], 1) * g->sms));
+                const ll needc = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
+                g->check_blocks[i] = (int)std::min<ll>(needc, (ll)di->occ_check[i] * g->sms);
             }
-        for (int KT : {1, 2, 4, 8}) {
-            int occ = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_fn_of(KT), 256, 0));
-            if (occ < 1) return set_err(MRC_ERR_CUDA, "check kernel K=%d does not fit on an SM", KT);
-            ll need = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
-            g->check_blocks[kt_index(KT)] = (int)std::min<ll>(need, (ll)occ * g->sms);
-        }
         if (const char *env = getenv("MRC_B200_TMA")) {   // A/B switch for experiments: bit i = KT index i
             const int mask = atoi(env);
             for (int i = 0; i < 4; i++) g->use_tma[i] = (mask >> i) & 1;
@@ -422,7 +436,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     { int r = 1; while (((ll)1 << r) < n + 1) r++; ca.rounds = std::min(r + 1, MRC_MAX_ROUNDS); }
 
     CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)n * KT * 8, g->stream));      // dist = 0 (:1148 / :829)
-    CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)n * KT * 4, g->stream));   // pred = -1 (:1154)
+    CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)n * KT * 8, g->stream));   // pred = none (:1154)
     unsigned active = (1u << K) - 1u;
     const ll max_passes = n;   // n-1 passes + the detection pass
     ll passes = 0;
@@ -497,6 +511,8 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         burst = std::min(burst * 2, g->burst_max);
     }
     if (exact && K == 1 && res[0].verdict == MRC_V_NONNEG) { g->pot_valid = true; g->pot_a = a[0]; g->pot_b = b[0]; }
+    for (int k = 0; k < K; k++) g->last_res[k] = res[k];
+    g->last_exact = exact; g->last_K = K;
     return MRC_OK;
 }
 
@@ -581,6 +597,19 @@ static int probe_common(mrc_graph *g, bool exact, const double *lam, const ll *a
     return MRC_OK;
 }
 
+extern "C" int mrc_fetch_cycle(mrc_graph *g, int k, int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len) {
+    if (!g || !cycle_len) return set_err(MRC_ERR_ARG, "NULL argument");
+    if (k < 0 || k >= g->last_K) return set_err(MRC_ERR_ARG, "candidate index out of range of the last probe");
+    const ProbeOut &o = g->last_res[k];
+    if (o.verdict != MRC_V_NEG && o.verdict != MRC_V_TIE) { *cycle_len = 0; return MRC_OK; }
+    CUDA_TRY(cudaSetDevice(g->device));
+    std::vector<int> verts;
+    MRC_TRY(fetch_cycle(g, g->last_exact, k, o, verts, nullptr, nullptr, nullptr, nullptr));
+    *cycle_len = (int64_t)verts.size();
+    if (cycle) for (size_t i = 0; i < verts.size() && (int64_t)i < cycle_cap; i++) cycle[i] = verts[i];
+    return MRC_OK;
+}
+
 extern "C" int mrc_probe_numeric(mrc_graph *g, const double *lam, int K, double slack, uint32_t flags,
                                  int32_t *verdict, int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap,
                                  double *sum_cost, double *sum_time, int64_t *passes) {
@@ -613,7 +642,7 @@ extern "C" int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passe
     for (int k = 0; k < K; k++) ra.lam[k] = lam[k];
     g->pot_valid = false;
     CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)g->n * KT * 8, g->stream));
-    CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)g->n * KT * 4, g->stream));
+    CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)g->n * KT * 8, g->stream));
     std::vector<cudaEvent_t> ev((size_t)passes + 1);
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaEventRecord(ev[0], g->stream));

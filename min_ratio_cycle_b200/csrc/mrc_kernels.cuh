@@ -12,7 +12,9 @@
 //   cost,time f64[m]    /  icost,itime int64[m] (exact mode)            -> 24 B per edge per pass
 //   dist     T[n][KT]   candidate-minor: the KT lambdas of one vertex share a 32/64/128-B sector group,
 //                       so ONE random gather per edge serves every candidate
-//   pred     int32[n][KT]  edge index that last lowered dist (racy by design, verified on extraction)
+//   pred     u64[n][KT]   (src vertex << 32 | edge index) of the relaxation that last lowered dist, one
+//                       8-byte store so vertex and edge always belong together (cross-warp order is still
+//                       racy by design; cycles are verified on extraction)
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -38,7 +40,7 @@ struct RelaxArgs {
     const double *cost, *time;
     const ll *icost, *itime;
     void *dist;
-    int *pred;
+    ull *pred;           // [n][KT]: (src vertex << 32) | edge index of the relaxation that last lowered dist; ~0 = none
     unsigned *changed;   // one word: bit k set when candidate k lowered some dist in this pass
     ll m;
     double lam[MRC_KMAX];
@@ -67,7 +69,7 @@ struct CheckArgs {
     const int *src;
     const double *cost, *time;
     const ll *icost, *itime;
-    int *pred;           // written only to cut a false cycle
+    ull *pred;           // written only to cut a false cycle
     const void *dist;
     int *jump;
     int *cyc_edges;      // [KT][cap]
@@ -205,7 +207,7 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
             imp = imp && !lose;
         }
         if (imp && mrc_atomic_lower(dist + (size_t)v * K + k, cand)) {
-            __stcg(p.pred + (size_t)v * K + k, e);
+            __stcg(p.pred + (size_t)v * K + k, ((ull)(unsigned)u << 32) | (unsigned)e);
             chg |= 1u << k;
         }
     }
@@ -480,12 +482,14 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         st->out[threadIdx.x].len = 0;
     }
     if (tid0 == 0) { st->cyc_mask = 0; st->pend = 0; st->cuts = 0; }
+    // jump = grandparent (two predecessor steps straight from pred, which nobody writes during this
+    // phase): saves the separate init sweep, its grid sync and the src[] gather of an edge-only pred
     for (ll i = tid0; i < total; i += stride) {
         const int k = (int)(i % K);
         int j = -1;
         if ((p.active >> k) & 1u) {
-            const int e = __ldcg(p.pred + i);
-            if (e >= 0) j = __ldg(p.src + e);
+            const int u = (int)(__ldcg(p.pred + i) >> 32);
+            if (u >= 0) j = (int)(__ldcg(p.pred + (ll)u * K + k) >> 32);
         }
         __stcg(p.jump + i, j);
     }
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
             bool settled = true;   // nothing left to examine for k unless a false cycle is cut below
             if (rep != 0x7fffffff) {
                 // rep leads into a cycle; enter it with a tortoise/hare walk over pred (tails are short)
-                auto step = [&](int y) { return __ldg(p.src + __ldcg(p.pred + (ll)y * K + k)); };
+                auto step = [&](int y) { return y < 0 ? -1 : (int)(__ldcg(p.pred + (ll)y * K + k) >> 32); };
                 int x = rep, hare = rep;
                 for (ll g = 0; g <= p.n; g++) {
                     x = step(x);
@@ -577,11 +581,10 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                 }
                 int cur = x, minv = x;
                 ll len = 0;
-                bool ok = true;
-                do {
-                    const int e = __ldcg(p.pred + (ll)cur * K + k);
-                    if (e < 0) { ok = false; break; }
-                    cur = __ldg(p.src + e);
+                bool ok = x >= 0;
+                if (ok) do {
+                    cur = step(cur);
+                    if (cur < 0) { ok = false; break; }
                     len++;
                     if (cur < minv) minv = cur;
                 } while (cur != x && len <= p.n);
@@ -590,14 +593,15 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                     ll isc = 0, ist = 0, i = 0;
                     cur = minv;
                     do {
-                        const int e = __ldcg(p.pred + (ll)cur * K + k);
+                        const ull pe = __ldcg(p.pred + (ll)cur * K + k);
+                        const int e = (int)(unsigned)pe;
                         if (i < p.cap) p.cyc_edges[(ll)k * p.cap + i] = e;
                         if (p.exact) { isc += __ldg(p.icost + e); ist += __ldg(p.itime + e); }
                         else {
                             sc += __ldg(p.cost + e); stt += __ldg(p.time + e);
                             mabs = fmax(mabs, fabs(__ldcg(static_cast<const double *>(p.dist) + (ll)cur * K + k)));
                         }
-                        cur = __ldg(p.src + e);
+                        cur = (int)(pe >> 32);
                         i++;
                     } while (cur != minv && i <= p.n);
                     int kind = 0;
@@ -620,12 +624,12 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                         cur = minv;
                         ll g = 0;
                         do {
-                            const int e = __ldcg(p.pred + (ll)cur * K + k);
+                            const int nxt = step(cur);
                             __stcg(p.jump + (ll)cur * K + k, -2);
-                            cur = __ldg(p.src + e);
+                            cur = nxt;
                             g++;
-                        } while (cur != minv && g <= p.n);
-                        __stcg(p.pred + (ll)minv * K + k, -1);
+                        } while (cur != minv && cur >= 0 && g <= p.n);
+                        __stcg(p.pred + (ll)minv * K + k, ~0ull);
                         atomicAdd(&st->cuts, 1u);
                         settled = false;
                     }
