@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_VERT)
     ap.add_argument("--m", type=int, default=N_EDGE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frontier", action="store_true", help="enable the active-source filter (not the headline config)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -181,6 +182,8 @@ def main():
     pin = [torch.from_numpy(a).pin_memory() for a in (U.astype(np.int32), V.astype(np.int32), C, T)]
     pU, pV, pC, pT = [p.numpy() for p in pin]
     g = N.DeviceGraph(n, pU, pV, pC, pT, device=local_rank)
+    if args.frontier:
+        g.set_option("frontier", 1)
     lo0, hi0 = g.bounds()
     K = args.klocal
     tol, slack, max_iter = 1e-12, 1e-15, 60
@@ -246,6 +249,8 @@ def main():
             barrier()
             t0 = time.perf_counter()
         g2 = N.DeviceGraph(n, pU, pV, pC, pT, device=local_rank)
+        if args.frontier:
+            g2.set_option("frontier", 1)
         o2 = one_solve(g2)
         if i >= 1:
             e2e_relax += g2.stats()["relax_edge_visits"]
@@ -279,7 +284,7 @@ def main():
             "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3 random digraph n=1M m=10M f64, numeric multisection", "n": n, "m": m,
-                       "seed": SEED, "lambda_candidates_per_gpu": K, "tolerance": tol,
+                       "seed": SEED, "lambda_candidates_per_gpu": K, "tolerance": tol, "frontier_filter": bool(args.frontier),
                        "l2": "edge arrays 240 MB > 126 MB L2, streamed every pass (no flush needed)",
                        "parallelism": f"lambda-candidate sharding x{world}"},
             "solve_ms": 1e3 * t_max / args.steps, "ratio": out["ratio"], "rounds": out["iterations"],

@@ -58,7 +58,7 @@ typedef struct mrc_graph mrc_graph;
 
 typedef struct mrc_stats {
     int64_t relax_launches;       /* relaxation kernel launches */
-    int64_t relax_edge_visits;    /* sum over launches of m * (active candidates) = edge relaxations */
+    int64_t relax_edge_visits;    /* edge relaxations actually evaluated (dense launch: m per candidate; frontier launch: edges with an active source) */
     int64_t check_launches;       /* predecessor-graph cycle checks */
     int64_t probes;               /* candidate lambdas evaluated */
     int64_t rounds;               /* outer search rounds */
@@ -68,6 +68,7 @@ typedef struct mrc_stats {
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     int64_t false_cycles_cut;     /* predecessor-graph cycles that did not verify negative and were cut */
+    int64_t relax_edge_slots;     /* sum over launches of m * (active candidates), whether or not an edge was skipped */
 } mrc_stats;
 
 int mrc_abi_version(void);
@@ -134,7 +135,8 @@ int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_cycle, int m
  * cycle checks, each launch timed with CUDA events on the library's stream. */
 int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *ms_per_pass);
 /* Tuning knobs: "alternate" (sweep direction flips every pass, 0/1), "burst_init", "burst_max" (passes per
- * host round trip). */
+ * host round trip), "tma" (bit mask over K in {1,2,4,8}: TMA-staged edge stream), "frontier" (0/1: launches
+ * from "frontier_from" on skip edges whose source vertex was not lowered by the previous launch). */
 int mrc_set_option(mrc_graph *g, const char *name, int value);
 
 /* Pure host helpers shared by mrc_solve_numeric and the multi-GPU driver (one process per GPU, the

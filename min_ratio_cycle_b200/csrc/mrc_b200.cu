@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -90,6 +91,10 @@ struct mrc_graph {
     bool last_exact = false; int last_K = 0;
     int relax_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     int tma_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int frontier = 0;            // option "frontier": passes >= frontier_from use relax_kernel_frontier
+    int frontier_from = 5;
+    unsigned *d_act[2] = {nullptr, nullptr};   // active-vertex bitmaps (previous / current launch)
+    size_t act_bytes = 0;
     int use_tma[4] = {0, 0, 0, 0};   // per KT index: stream the edges through the TMA-staged kernel (option "tma")
     int check_blocks[4] = {0, 0, 0, 0};
     int burst_init = 2, burst_max = MRC_MAX_BURST;
@@ -126,6 +131,14 @@ static const void *relax_tma_fn_of(int KT, bool exact) {
         case 2: return exact ? (const void *)relax_kernel_tma<2, true> : (const void *)relax_kernel_tma<2, false>;
         case 4: return exact ? (const void *)relax_kernel_tma<4, true> : (const void *)relax_kernel_tma<4, false>;
         default: return exact ? (const void *)relax_kernel_tma<8, true> : (const void *)relax_kernel_tma<8, false>;
+    }
+}
+static const void *relax_frontier_fn_of(int KT, bool exact) {
+    switch (KT) {
+        case 1: return exact ? (const void *)relax_kernel_frontier<1, true> : (const void *)relax_kernel_frontier<1, false>;
+        case 2: return exact ? (const void *)relax_kernel_frontier<2, true> : (const void *)relax_kernel_frontier<2, false>;
+        case 4: return exact ? (const void *)relax_kernel_frontier<4, true> : (const void *)relax_kernel_frontier<4, false>;
+        default: return exact ? (const void *)relax_kernel_frontier<8, true> : (const void *)relax_kernel_frontier<8, false>;
     }
 }
 static const void *check_fn_of(int KT) {
@@ -168,7 +181,7 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
     if (g->stream) {
         void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
                         g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
-                        g->d_keys, g->d_verr};
+                        g->d_keys, g->d_verr, g->d_act[0], g->d_act[1]};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
         cudaStreamSynchronize(g->stream);
     }
@@ -269,6 +282,10 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
             const int mask = atoi(env);
             for (int i = 0; i < 4; i++) g->use_tma[i] = (mask >> i) & 1;
         }
+        g->act_bytes = (((size_t)n + 31) / 32 * 4 + 15) & ~(size_t)15;
+        DALLOC(g->d_act[0], g->act_bytes); DALLOC(g->d_act[1], g->act_bytes);
+        if (const char *env = getenv("MRC_B200_FRONTIER"))   // A/B switch for experiments and the parity suite
+            g->frontier = atoi(env) != 0 && g->act_bytes + 2048 <= 227 * 1024;
         // input validation on the device (the host never touches the 24 B/edge again)
         DALLOC(g->d_verr, 4);
         CUDA_TRY(cudaMemsetAsync(g->d_verr, 0, 4, g->stream));
@@ -374,8 +391,18 @@ extern "C" int mrc_graph_restore(mrc_graph *g) {
 }
 
 // ------------------------------------------------------------------------------------------- probe engine
-static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra) {
+static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra, bool frontier_pass = false) {
     void *args[] = {(void *)&ra};
+    if (frontier_pass) {
+        const size_t smem = g->act_bytes;
+        static bool attr_set[4][2] = {{false, false}, {false, false}, {false, false}, {false, false}};
+        if (!attr_set[kt_index(KT)][exact ? 1 : 0]) {
+            CUDA_TRY(cudaFuncSetAttribute(relax_frontier_fn_of(KT, exact), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+            attr_set[kt_index(KT)][exact ? 1 : 0] = true;
+        }
+        CUDA_TRY(cudaLaunchKernel(relax_frontier_fn_of(KT, exact), dim3(g->sms), dim3(MRC_FRONTIER_THREADS), args, smem, g->stream));
+        return MRC_OK;
+    }
     if (g->use_tma[kt_index(KT)]) {
         CUDA_TRY(cudaLaunchKernel(relax_tma_fn_of(KT, exact), dim3(g->tma_blocks[kt_index(KT)][exact ? 1 : 0]),
                                   dim3(MRC_TMA_THREADS), args, MRC_TMA_SMEM, g->stream));
@@ -423,7 +450,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     memset(&ra, 0, sizeof ra);
     ra.src = g->d_src; ra.dst = g->d_dst; ra.cost = g->d_cost; ra.time = g->d_time;
     ra.icost = g->d_icost; ra.itime = g->d_itime; ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = m;
-    ra.slack = slack;
+    ra.slack = slack; ra.n = n; ra.examined = &g->d_status->examined;
     CheckArgs ca;
     memset(&ca, 0, sizeof ca);
     for (int k = 0; k < K; k++) {
@@ -450,13 +477,24 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
                 if ((active >> k) & 1u) { res[k].verdict = MRC_V_NEG_NOCYCLE; res[k].passes = passes; }
             break;
         }
-        CUDA_TRY(cudaMemsetAsync(g->d_status->changed, 0, sizeof(unsigned) * MRC_MAX_BURST, g->stream));
+        CUDA_TRY(cudaMemsetAsync(g->d_status, 0, offsetof(DevStatus, cnt), g->stream));   // changed[] + examined
         CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
         ra.active = active;
+        int dense_launches = 0;
         for (int i = 0; i < nb; i++) {
             ra.changed = &g->d_status->changed[i];
             ra.reverse = g->alternate ? (int)((passes + i) & 1) : 0;
-            MRC_TRY(launch_relax(g, KT, exact, ra));
+            bool fpass = false;
+            if (g->frontier) {
+                // bitmap written by launch p is read by launch p+1; launches before frontier_from sweep densely
+                const ll pidx = passes + i;
+                ra.act_out = g->d_act[pidx & 1];
+                ra.act_in = g->d_act[(pidx + 1) & 1];
+                CUDA_TRY(cudaMemsetAsync(ra.act_out, 0, g->act_bytes, g->stream));
+                fpass = pidx + 1 >= g->frontier_from;
+            }
+            if (!fpass) dense_launches++;
+            MRC_TRY(launch_relax(g, KT, exact, ra, fpass));
         }
         CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
         const bool do_check = passes + nb >= next_check || passes + nb >= max_passes;
@@ -473,7 +511,8 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
         passes += nb;
         g->stats.relax_launches += nb;
-        g->stats.relax_edge_visits += (int64_t)nb * m * __builtin_popcount(active);
+        g->stats.relax_edge_visits += ((int64_t)dense_launches * m + (int64_t)g->h_status->examined) * __builtin_popcount(active);
+        g->stats.relax_edge_slots += (int64_t)nb * m * __builtin_popcount(active);
         if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += g->h_status->cuts; }
         g->stats.d2h_bytes += sizeof(DevStatus);
         const DevStatus &hs = *g->h_status;
@@ -646,9 +685,17 @@ extern "C" int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passe
     std::vector<cudaEvent_t> ev((size_t)passes + 1);
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaEventRecord(ev[0], g->stream));
+    ra.n = g->n; ra.examined = &g->d_status->examined;
     for (int i = 0; i < passes; i++) {
         ra.reverse = g->alternate ? (i & 1) : 0;
-        MRC_TRY(launch_relax(g, KT, false, ra));
+        bool fpass = false;
+        if (g->frontier) {
+            ra.act_out = g->d_act[i & 1];
+            ra.act_in = g->d_act[(i + 1) & 1];
+            CUDA_TRY(cudaMemsetAsync(ra.act_out, 0, g->act_bytes, g->stream));
+            fpass = i + 1 >= g->frontier_from;
+        }
+        MRC_TRY(launch_relax(g, KT, false, ra, fpass));
         CUDA_TRY(cudaEventRecord(ev[i + 1], g->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(g->stream));
@@ -661,6 +708,12 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     std::string s(name);
     if (s == "alternate") g->alternate = value != 0;
     else if (s == "tma") { for (int i = 0; i < 4; i++) g->use_tma[i] = (value >> i) & 1; }
+    else if (s == "frontier") {
+        if (value && g->act_bytes + 2048 > 227 * 1024)
+            return set_err(MRC_ERR_ARG, "frontier mode keeps n/8 bytes of shared memory per SM: n too large");
+        g->frontier = value != 0;
+    }
+    else if (s == "frontier_from") g->frontier_from = std::max(1, value);
     else if (s == "burst_init") g->burst_init = std::max(1, std::min(value, MRC_MAX_BURST));
     else if (s == "burst_max") g->burst_max = std::max(1, std::min(value, MRC_MAX_BURST));
     else return set_err(MRC_ERR_ARG, "unknown option %s", name);

@@ -48,6 +48,11 @@ struct RelaxArgs {
     double slack;
     unsigned active;     // bit k: candidate k still undecided
     int reverse;         // sweep the edge stream back to front (L2 reuse between consecutive passes)
+    // frontier mode (optional): one bit per vertex, "dist[v] was lowered for some candidate"
+    unsigned *act_out;         // set by this launch (NULL = not tracked)
+    const unsigned *act_in;    // set by the previous launch; read only by relax_kernel_frontier
+    ull *examined;             // edges actually relaxed by relax_kernel_frontier launches
+    ll n;
 };
 
 struct CycleOut {
@@ -59,6 +64,7 @@ struct CycleOut {
 
 struct DevStatus {
     unsigned changed[MRC_MAX_BURST];
+    ull examined;                              // frontier launches: edges whose source was active (cleared with `changed`)
     unsigned cnt[MRC_MAX_ROUNDS * MRC_KMAX];   // live vertices per doubling round and candidate
     unsigned cyc_mask, rounds_run, pend, cuts;
     int rep[MRC_KMAX * 6];   // [MRC_MAX_EXTRACT][MRC_KMAX]
@@ -208,6 +214,7 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
         }
         if (imp && mrc_atomic_lower(dist + (size_t)v * K + k, cand)) {
             __stcg(p.pred + (size_t)v * K + k, ((ull)(unsigned)u << 32) | (unsigned)e);
+            if (p.act_out) atomicOr(p.act_out + (v >> 5), 1u << (v & 31));
             chg |= 1u << k;
         }
     }
@@ -349,6 +356,64 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
     // changed flag: warp vote, one atomic per warp at most
     chg = __reduce_or_sync(0xffffffffu, chg);
     if (lane == 0 && chg) atomicOr(p.changed, chg);
+}
+
+// ---- frontier relaxation ------------------------------------------------------------------------------
+// After the first passes only a few per cent of the vertices still change, and an edge can only improve
+// its destination if its SOURCE was lowered since the edge was last looked at.  This variant keeps the
+// edge-parallel sweep but consults a one-bit-per-vertex "lowered in the previous launch" map, held in
+// shared memory (n/8 bytes, one 1024-thread CTA per SM): a row of 32 edges whose sources are all inactive
+// costs 128 B of src stream and nothing else; dst/cost/time and the dist gathers are issued for active lanes
+// only.  A launch that lowers nothing is still a true fixed point (an edge skipped now was examined after its
+// source's last change), so verdicts, potentials and parity are unchanged.  Requires n <= 8 * (smem - 1 KB).
+#define MRC_FRONTIER_THREADS 1024
+#ifndef MRC_FRONTIER_ROWS
+#define MRC_FRONTIER_ROWS 8
+#endif
+template <int K, bool EXACT>
+__global__ void __launch_bounds__(MRC_FRONTIER_THREADS, 1) relax_kernel_frontier(const __grid_constant__ RelaxArgs p) {
+    typedef typename WeightT<EXACT>::type W;
+    extern __shared__ __align__(16) unsigned s_act[];
+    const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
+    const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
+    const int words = (int)((p.n + 31) >> 5);
+    for (int i = threadIdx.x; i < words; i += MRC_FRONTIER_THREADS) s_act[i] = __ldcg(p.act_in + i);
+    __syncthreads();
+    unsigned chg = 0, seen = 0;
+    const int lane = threadIdx.x & 31;
+    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    constexpr int R = MRC_FRONTIER_ROWS;
+    constexpr ll CH = 32 * R;
+    const ll nchunks = (p.m + CH - 1) / CH;
+    for (ll c = warp; c < nchunks; c += nwarps) {
+        const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
+        int s[R];
+        bool act[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const ll e = e0 + 32 * j;
+            s[j] = e < p.m ? __ldcs(p.src + e) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < R; j++) act[j] = s[j] >= 0 && ((s_act[s[j] >> 5] >> (s[j] & 31)) & 1u);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const unsigned am = __ballot_sync(0xffffffffu, act[j]);
+            if (am == 0) continue;   // warp-uniform: the whole row is skipped
+            seen += __popc(am);
+            const ll e = e0 + 32 * j;
+            int d = -1 - lane;
+            W cs = W(0), tm = W(0);
+            if (act[j]) { d = __ldcs(p.dst + e); cs = __ldcs(cost + e); tm = __ldcs(time + e); }
+            relax_row<K, W>(p, act[j], lane, (int)e, s[j], d, cs, tm, chg);
+        }
+    }
+    chg = __reduce_or_sync(0xffffffffu, chg);
+    if (lane == 0) {
+        if (chg) atomicOr(p.changed, chg);
+        if (seen) atomicAdd(p.examined, (ull)seen);
+    }
 }
 
 // ---- TMA-staged relaxation (sm_100a: cp.async.bulk + mbarrier) ------------------------------------------

@@ -72,6 +72,7 @@ class SolverConfig:
     gpu_device: int = 0
     gpu_candidates: int = 4            # lambdas evaluated per relaxation launch (1..8)
     gpu_exact_strategy: int = 1        # 0: every Stern-Brocot step probes the GPU; 1: Newton + replay
+    gpu_frontier: bool = False         # skip edges whose source was not lowered by the previous pass (same results)
     honor_mode: bool = False           # True: solve(mode="exact") really runs _solve_exact (reference ignores mode)
 
 
@@ -335,6 +336,8 @@ class MinRatioCycleSolver:
             self._dev.close()
         self._dev = N.DeviceGraph(self.n, self._U, self._V, self._C, self._T, self._Ci, self._Ti,
                                   device=self.config.gpu_device)
+        if self.config.gpu_frontier and self.n <= 1_700_000:
+            self._dev.set_option("frontier", 1)
         self._arrays_built = True
         if self._metrics:
             self._metrics.preprocessing_time = _time.time() - t0

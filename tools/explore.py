@@ -21,6 +21,8 @@ def main():
     g = N.DeviceGraph(n, U, V, C, T)
     print(f"upload {time.time()-t0:.3f}s", flush=True)
     lo, hi = g.bounds()
+    if os.environ.get("MRC_FRONTIER"): g.set_option("frontier", int(os.environ["MRC_FRONTIER"]))
+    if os.environ.get("MRC_FFROM"): g.set_option("frontier_from", int(os.environ["MRC_FFROM"]))
     if os.environ.get("MRC_BURST"): g.set_option("burst_init", int(os.environ["MRC_BURST"]))
     print("bounds", lo, hi)
     for K in (1, 2, 4, 4, 4):

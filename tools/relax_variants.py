@@ -16,11 +16,12 @@ r = -14.937873966124124
 tag = os.environ.get("MRC_B200_LIB", "default").split("/")[-1]
 tma = int(os.environ.get("MRC_TMA", "0"))
 g.set_option("tma", tma)
+if os.environ.get("MRC_FRONTIER"): g.set_option("frontier", 1); tag += " frontier"
 tag += f" tma={tma}"
 for K in (1, 2, 4, 8):
     lam = [r - 0.5 - 0.1 * k for k in range(K)]   # all NONNEG: converges in ~25 passes
     g.bench_relax(lam, 3)
-    ms = g.bench_relax(lam, 30)
+    ms = g.bench_relax(lam, 40)
     us = ms * 1e3
     print(f"{tag:28s} K={K} pass1={us[0]:.0f} pass2={us[1]:.0f} pass3={us[2]:.0f} p5={us[4]:.0f} p10={us[9]:.0f} "
-          f"p20={us[19]:.0f} p30={us[29]:.0f} mean={us.mean():.1f} late_mean={us[20:].mean():.1f}", flush=True)
+          f"p4={us[3]:.0f} p6={us[5]:.0f} p8={us[7]:.0f} p15={us[14]:.0f} p20={us[19]:.0f} p30={us[29]:.0f} p40={us[39]:.0f} mean={us.mean():.1f} late_mean={us[20:].mean():.1f}", flush=True)
