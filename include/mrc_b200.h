@@ -50,9 +50,13 @@ extern "C" {
 #define MRC_V_TIE 3            /* extracted cycle has ratio >= lambda within rounding: lambda ~ ratio of that cycle */
 #define MRC_V_SKIPPED_NEG 4    /* not evaluated to the end: a smaller lambda of the batch was already negative */
 #define MRC_V_SKIPPED_NONNEG 5 /* not evaluated to the end: a larger lambda of the batch already had no negative cycle */
+#define MRC_V_ABANDONED 6      /* not evaluated to the end and nothing implied (MRC_F_STOP_ON_NEG) */
 
 /* probe flags */
 #define MRC_F_MONOTONE_PRUNE 1u /* stop candidates whose verdict is implied by monotonicity in lambda */
+#define MRC_F_STOP_ON_NEG 2u     /* end the probe at the first cycle check that verifies a negative cycle: the search only
+                                   needs that cycle's ratio to tighten the bracket; the candidates still relaxing are
+                                   reported MRC_V_ABANDONED */
 
 typedef struct mrc_graph mrc_graph;
 

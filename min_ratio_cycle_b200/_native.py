@@ -20,8 +20,9 @@ KMAX = 8
 OK, ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_OVERFLOW, ERR_NO_CYCLE, ERR_CONVERGENCE = range(7)
 ERR_LOWER_NEG, ERR_UPPER_NONNEG, ERR_SB_STEPS, ERR_NOT_INTEGER, ERR_TIMEOUT, ERR_EDGE_MISSING = range(7, 13)
 
-V_NONNEG, V_NEG, V_NEG_NOCYCLE, V_TIE, V_SKIPPED_NEG, V_SKIPPED_NONNEG = range(6)
+V_NONNEG, V_NEG, V_NEG_NOCYCLE, V_TIE, V_SKIPPED_NEG, V_SKIPPED_NONNEG, V_ABANDONED = range(7)
 F_MONOTONE_PRUNE = 1
+F_STOP_ON_NEG = 2
 
 EXPORTS = [
     "mrc_abi_version", "mrc_last_error", "mrc_device_count", "mrc_graph_create", "mrc_graph_destroy",

@@ -47,6 +47,7 @@ def test_status_codes_match_header(native):
     assert int(defs["MRC_ERR_SB_STEPS"]) == native.ERR_SB_STEPS
     assert int(defs["MRC_V_TIE"]) == native.V_TIE
     assert int(defs["MRC_V_SKIPPED_NONNEG"]) == native.V_SKIPPED_NONNEG
+    assert int(defs["MRC_V_ABANDONED"]) == native.V_ABANDONED and int(defs["MRC_F_STOP_ON_NEG"]) == native.F_STOP_ON_NEG
     assert int(defs["MRC_KMAX"]) == native.KMAX
 
 
