@@ -173,3 +173,18 @@ def test_dominated_edge_removal_matches_oracle(oracle_mod):
         exp = o.ins
         for a, b in zip(got, exp):
             assert np.array_equal(a, b), trial
+
+
+def test_dimacs_loader_and_regression_helpers(tmp_path):
+    """Host-only parts of benchmarks.py (reference benchmarks.py:19-66, :143-234)."""
+    from min_ratio_cycle_b200 import benchmarks as B
+    lines = ["c unit triangle", "p sp 3 3", "a 1 2 1 1", "a 2 3 1 1", "", "a 3 1 1 1"]
+    s = B.load_dimacs_graph(lines)
+    assert s.n == 3 and [(e.u, e.v, e.cost, e.time) for e in s._edges] == [(0, 1, 1.0, 1.0), (1, 2, 1.0, 1.0), (2, 0, 1.0, 1.0)]
+    assert B.load_dimacs_graph(["p 5 0"]).n == 5
+    p = tmp_path / "sub" / "base.json"
+    B.save_baseline(p, {"ratio": 1.0, "times": [0.01, 0.012, 0.011]})
+    base = B.load_baseline(p)
+    assert B.regression_check([0.011, 0.0105, 0.012], 1.0, base) == {"performance": False, "quality": False}
+    assert B.regression_check([0.5, 0.6, 0.55], 1.0 + 1e-6, base) == {"performance": True, "quality": True}
+    assert B.regression_check([0.5], 1.0, base)["performance"] is True          # < 2 samples: 1.5x mean rule

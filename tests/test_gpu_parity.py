@@ -400,3 +400,29 @@ def test_batch_mixed_small_graphs(mrc, oracle_mod):
                 v, why = three_way(chk, {"cycle": r.cycle, "ratio": r.ratio}, rec["solve"])
                 assert v in (MATCH, REF_SUBOPTIMAL) or not simple, (nm, K, why)
         assert nfail <= 10
+
+
+# --------------------------------------------------------------------------- callers either side of the path
+def test_dimacs_benchmark_and_convenience(mrc):
+    """tests/test_analytics.py:50-78 and tests/test_regression.py of the reference, against the GPU path."""
+    from min_ratio_cycle_b200 import benchmarks as B
+    tri = ["p sp 3 3", "a 1 2 1 1", "a 2 3 1 1", "a 3 1 1 1"]
+    out = B.benchmark_solver(B.load_dimacs_graph(tri, mrc.SolverConfig(log_level=mrc.LogLevel.NONE)), compare=False)
+    assert abs(out["ratio"] - 1.0) <= 1e-9 and out["diff"] is None and out["time"] < 1.0
+    five = ["p sp 5 7", "a 1 2 2 1", "a 2 3 2 1", "a 3 1 2 1", "a 3 4 1 1", "a 4 5 1 1", "a 5 3 1 1", "a 1 4 5 2"]
+    out = B.benchmark_solver(B.load_dimacs_graph(five, mrc.SolverConfig(log_level=mrc.LogLevel.NONE)), compare=True)
+    assert out["diff"] <= 1e-9
+    r = mrc.solve_min_ratio_cycle([(0, 1, -2, 1), (1, 2, -1, 1), (2, 0, 1, 1)], config=mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+    assert abs(r.ratio - (-2.0 / 3.0)) <= 1e-12 and r.cycle[0] == r.cycle[-1]
+    s = mrc.MinRatioCycleSolver(4, mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+    s.add_edges([(0, 1, 1.0, 1.0), (1, 2, 1.0, 1.0), (2, 0, 1.0, 1.0), (2, 3, 5.0, 1.0), (3, 2, 5.0, 1.0)])
+    stab = s.stability_region(0.01)
+    assert set(stab) == {0, 1, 2, 3, 4} and all(isinstance(v, bool) for v in stab.values()) and stab[3] and stab[4]
+    props = s.get_graph_properties()
+    assert props["vertices"] == 4 and props["edges"] == 5 and props["connectivity"]["max_in_degree"] == 2
+    assert s.health_check()["summary"]["overall_status"] in ("PASS", "WARN")
+    assert "Ratio" in s.get_debug_info()
+    sh = mrc.MinRatioCycleSolver(3, mrc.SolverConfig(log_level=mrc.LogLevel.NONE, honor_mode=True))
+    sh.add_edges([(0, 1, 2, 1), (1, 2, 3, 2), (2, 0, 1, 1)])
+    re = sh.solve(mode="exact")
+    assert re.metrics.mode_used == "exact" and re.cycle == [1, 2, 0, 1] and re.ratio == 1.5   # README.md:66 of the reference
