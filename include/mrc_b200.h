@@ -189,6 +189,16 @@ int mrc_solve_exact(mrc_graph *g, int64_t max_den, int64_t max_steps, int strate
                     int64_t *b_out, int64_t *iterations, int64_t *probes_ab, int64_t probes_cap,
                     int64_t *nprobes);
 
+/* ---- device-side array build -------------------------------------------------------------------
+ * The stable sort by destination of _build_arrays_if_needed (np.argsort(V, kind="stable") + gathers,
+ * solver.py:476-478) as one radix sort + one gather sweep on the device.  Host arrays in insertion order in,
+ * destination-sorted host arrays out (ready for mrc_graph_create); order_out[i] (may be NULL) = insertion index of
+ * sorted edge i; dup_pairs_out (may be NULL) = number of edges whose (u,v) also occurs earlier (0 means
+ * _remove_dominated_edges, solver.py:531-575, has nothing to examine). */
+int mrc_sort_edges_by_dst(int64_t n, int64_t m, const int32_t *src, const int32_t *dst, const double *cost,
+                          const double *time, int device, int32_t *src_out, int32_t *dst_out, double *cost_out,
+                          double *time_out, int32_t *order_out, int64_t *dup_pairs_out);
+
 /* ---- batches of small graphs -------------------------------------------------------------------
  * Replaces a loop of B independent solve() calls (each _solve_numeric, solver.py:1001-1122) for graphs that
  * fit one SM's shared memory (n <= 65535, 20*m + 28*K*n bytes <= ~220 KB; BASELINE config 4: n=64, m=4032):

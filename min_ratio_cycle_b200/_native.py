@@ -29,7 +29,7 @@ EXPORTS = [
     "mrc_graph_info", "mrc_numeric_bounds", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
     "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
     "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
-    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle",
+    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle", "mrc_sort_edges_by_dst",
 ]
 
 
@@ -89,6 +89,7 @@ def lib():
     L.mrc_zero_cycle_exact.argtypes = [vp, C.c_int64, C.c_int64, pu8, p32, C.c_int64, p64, p64, p64]
     L.mrc_solve_exact.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, p32, C.c_int64, p64, p64, p64, p64, p64, p64,
                                   p64, C.c_int64, p64]
+    L.mrc_sort_edges_by_dst.argtypes = [C.c_int64, C.c_int64, p32, p32, pd, pd, C.c_int, p32, p32, pd, pd, p32, p64]
     L.mrc_fetch_cycle.argtypes = [vp, C.c_int, p32, C.c_int64, p64]
     L.mrc_bench_relax.argtypes = [vp, pd, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.mrc_set_option.argtypes = [vp, C.c_char_p, C.c_int]
@@ -342,3 +343,18 @@ def batch_solve_numeric(nverts, edge_off, src, dst, cost, time, max_iter: int = 
     cycles = [cbuf[g * cap: g * cap + clen[g]].tolist() for g in range(B)]
     return dict(status=status, ratio=ratio, sum_cost=sc, sum_time=st, cycles=cycles, iterations=it,
                 stats=stats.as_dict())
+
+
+def sort_edges_by_dst(n, U, V, Cw, Tw, device: int = 0, count_dups: bool = True):
+    """mrc_sort_edges_by_dst: (src, dst, cost, time, order, dup_pairs) with dst stably sorted on the device."""
+    src = np.ascontiguousarray(U, dtype=np.int32); dst = np.ascontiguousarray(V, dtype=np.int32)
+    cost = np.ascontiguousarray(Cw, dtype=np.float64); time = np.ascontiguousarray(Tw, dtype=np.float64)
+    m = len(src)
+    so = np.empty(m, np.int32); do = np.empty(m, np.int32); co = np.empty(m); to = np.empty(m)
+    order = np.empty(m, np.int32)
+    dups = C.c_int64(-1)
+    check(lib().mrc_sort_edges_by_dst(int(n), m, _ptr(src, C.c_int32), _ptr(dst, C.c_int32), _ptr(cost, C.c_double),
+                                      _ptr(time, C.c_double), int(device), _ptr(so, C.c_int32), _ptr(do, C.c_int32),
+                                      _ptr(co, C.c_double), _ptr(to, C.c_double), _ptr(order, C.c_int32),
+                                      C.byref(dups) if count_dups else None))
+    return so, do, co, to, order, dups.value

@@ -16,33 +16,11 @@
 #include "mrc_kernels.cuh"
 #include "mrc_search.h"
 #include "mrc_batch.cuh"
+#include "mrc_host.h"
 
 typedef __int128 i128;
 
-static thread_local std::string g_err;
-static int set_err(int code, const char *fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
-}
-#define CUDA_TRY(x)                                                                                     \
-    do {                                                                                                \
-        cudaError_t e_ = (x);                                                                           \
-        if (e_ != cudaSuccess)                                                                          \
-            return set_err(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? MRC_ERR_NO_DEVICE \
-                                                                                        : MRC_ERR_CUDA, \
-                           "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);    \
-    } while (0)
-#define DALLOC(ptr, bytes) CUDA_TRY(cudaMallocAsync((void **)&(ptr), (bytes), g->stream))
-#define MRC_TRY(x)            \
-    do {                      \
-        int rc_ = (x);        \
-        if (rc_) return rc_;  \
-    } while (0)
+thread_local std::string g_mrc_err;
 
 struct PatchRec {
     ll k;
@@ -103,7 +81,7 @@ struct mrc_graph {
 };
 
 extern "C" int mrc_abi_version(void) { return MRC_ABI_VERSION; }
-extern "C" const char *mrc_last_error(void) { return g_err.c_str(); }
+extern "C" const char *mrc_last_error(void) { return g_mrc_err.c_str(); }
 extern "C" int mrc_device_count(int *count) {
     if (!count) return set_err(MRC_ERR_ARG, "count is NULL");
     int c = 0;
@@ -1186,3 +1164,4 @@ extern "C" int mrc_batch_solve_numeric(int64_t B, const int32_t *nverts, const i
     cudaStreamDestroy(st);
     return rc;
 }
+

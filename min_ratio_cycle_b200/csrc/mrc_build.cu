@@ -1,0 +1,80 @@
+// mrc_build.cu -- device-side array build entry point (own translation unit: CUB is slow to compile).
+#include <algorithm>
+
+#include "mrc_build.cuh"
+#include "mrc_host.h"
+
+// ---------------------------------------------------------------------------------------- device-side array build
+/*
+ * Stable sort of insertion-order edges by destination on the device (replaces np.argsort(V, kind="stable") and
+ * the gathers of _build_arrays_if_needed, solver.py:476-478).  Host arrays in, host arrays out; `order_out[i]` is
+ * the insertion index of sorted edge i.  dup_pairs_out (may be NULL): number of edges whose (u,v) pair also occurs
+ * earlier -- 0 means _remove_dominated_edges (:531-575) has nothing to do.
+ */
+extern "C" int mrc_sort_edges_by_dst(int64_t n, int64_t m, const int32_t *src, const int32_t *dst, const double *cost,
+                                     const double *time, int device, int32_t *src_out, int32_t *dst_out,
+                                     double *cost_out, double *time_out, int32_t *order_out, int64_t *dup_pairs_out) {
+    if (n <= 0 || m <= 0 || n > 0x7ffffff0ll || m > 0x7ffffff0ll) return set_err(MRC_ERR_ARG, "n, m must be positive and fit int32");
+    if (!src || !dst || !cost || !time || !src_out || !dst_out || !cost_out || !time_out)
+        return set_err(MRC_ERR_ARG, "NULL array");
+    int ndev = 0;
+    MRC_TRY(mrc_device_count(&ndev));
+    if (device < 0 || device >= ndev) return set_err(MRC_ERR_ARG, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int *d_src = nullptr, *d_dst = nullptr, *d_dst2 = nullptr, *d_idx = nullptr, *d_ord = nullptr, *d_src2 = nullptr;
+    double *d_c = nullptr, *d_t = nullptr, *d_c2 = nullptr, *d_t2 = nullptr;
+    ull *d_k = nullptr, *d_k2 = nullptr, *d_cnt = nullptr;
+    void *d_tmp = nullptr;
+    int rc = [&]() -> int {
+        const size_t M = (size_t)m;
+        CUDA_TRY(cudaMallocAsync((void **)&d_src, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_dst, M * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_dst2, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_idx, M * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_ord, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_src2, M * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_c, M * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_t, M * 8, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_c2, M * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_t2, M * 8, st));
+        CUDA_TRY(cudaMemcpyAsync(d_src, src, M * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_dst, dst, M * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_c, cost, M * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_t, time, M * 8, cudaMemcpyHostToDevice, st));
+        const int blocks = (int)std::min<ll>((m + 255) / 256, 148 * 16);
+        build_iota_kernel<<<blocks, 256, 0, st>>>(d_idx, m);
+        int bits = 1;
+        while (((ll)1 << bits) < n) bits++;
+        size_t tmp_bytes = 0, tmp2 = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_dst, d_dst2, d_idx, d_ord, (int)m, 0, bits, st));
+        if (dup_pairs_out) {
+            CUDA_TRY(cudaMallocAsync((void **)&d_k, M * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_k2, M * 8, st));
+            CUDA_TRY(cudaMallocAsync((void **)&d_cnt, 8, st));
+            CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp2, d_k, d_k2, (int)m, 0, 32 + bits, st));
+        }
+        tmp_bytes = std::max(tmp_bytes, tmp2);
+        CUDA_TRY(cudaMallocAsync(&d_tmp, tmp_bytes, st));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_dst, d_dst2, d_idx, d_ord, (int)m, 0, bits, st));
+        build_gather_kernel<<<blocks, 256, 0, st>>>(d_ord, d_src, d_c, d_t, d_src2, d_c2, d_t2, m);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(src_out, d_src2, M * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(dst_out, d_dst2, M * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(cost_out, d_c2, M * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(time_out, d_t2, M * 8, cudaMemcpyDeviceToHost, st));
+        if (order_out) CUDA_TRY(cudaMemcpyAsync(order_out, d_ord, M * 4, cudaMemcpyDeviceToHost, st));
+        ull dups = 0;
+        if (dup_pairs_out) {
+            CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
+            build_pair_keys_kernel<<<blocks, 256, 0, st>>>(d_src, d_dst, d_k, m);
+            CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_k, d_k2, (int)m, 0, 32 + bits, st));
+            build_count_dups_kernel<<<blocks, 256, 0, st>>>(d_k2, m, d_cnt);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(&dups, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (dup_pairs_out) *dup_pairs_out = (int64_t)dups;
+        return MRC_OK;
+    }();
+    void *ptrs[] = {d_src, d_dst, d_dst2, d_idx, d_ord, d_src2, d_c, d_t, d_c2, d_t2, d_k, d_k2, d_cnt, d_tmp};
+    for (void *q : ptrs) if (q) cudaFreeAsync(q, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}

@@ -1,0 +1,35 @@
+// mrc_host.h -- host-side error plumbing shared by the translation units of libmrc_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "mrc_b200.h"
+
+extern thread_local std::string g_mrc_err;   // defined in mrc_b200.cu; read by mrc_last_error()
+
+static inline int set_err(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_mrc_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e_ = (x);                                                                           \
+        if (e_ != cudaSuccess)                                                                          \
+            return set_err(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? MRC_ERR_NO_DEVICE \
+                                                                                        : MRC_ERR_CUDA, \
+                           "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+    } while (0)
+#define DALLOC(ptr, bytes) CUDA_TRY(cudaMallocAsync((void **)&(ptr), (bytes), g->stream))
+#define MRC_TRY(x)            \
+    do {                      \
+        int rc_ = (x);        \
+        if (rc_) return rc_;  \
+    } while (0)

@@ -34,6 +34,8 @@ from .exceptions import ConvergenceError, NumericalInstabilityError, ResourceExh
 
 __version__ = "0.1.0"
 
+_DEVICE_BUILD_MIN_EDGES = 200_000   # above this the stable sort by destination runs on the GPU
+
 
 class SolverMode(Enum):
     AUTO = "auto"
@@ -163,6 +165,7 @@ class MinRatioCycleSolver:
         self.config = config or SolverConfig()
         self._edges: list[Edge] = []
         self._bulk: list[tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = []
+        self._presorted = None
         self._setup_logging()
         self._arrays_built = False
         self._U = self._V = self._C = self._T = self._Ci = self._Ti = None
@@ -191,6 +194,7 @@ class MinRatioCycleSolver:
 
     def _invalidate(self) -> None:
         self._arrays_built = False
+        self._presorted = None
 
     def _num_edges(self) -> int:
         return len(self._edges) + sum(len(b[0]) for b in self._bulk)
@@ -318,9 +322,22 @@ class MinRatioCycleSolver:
         if self._num_edges() == 0:
             self.logger.warning("No edges to build arrays from")
             return
-        U, V, Cw, Tw = self._insertion_arrays()
-        order = np.argsort(V, kind="stable")
-        self._U, self._V, self._C, self._T = U[order], V[order], Cw[order], Tw[order]
+        if self._presorted is not None:
+            so, do, co, to, order = self._presorted            # device sort already done by _preprocess_graph
+            self._presorted = None
+        elif self._num_edges() >= _DEVICE_BUILD_MIN_EDGES:
+            U, V, Cw, Tw = self._insertion_arrays()
+            so, do, co, to, order, _ = N.sort_edges_by_dst(self.n, U, V, Cw, Tw, device=self.config.gpu_device,
+                                                           count_dups=False)
+        else:
+            so = None
+        if so is not None:                                     # stable radix sort on the GPU (mrc_sort_edges_by_dst)
+            self._U, self._V, self._C, self._T = so.astype(np.int64), do.astype(np.int64), co, to
+            order = order.astype(np.int64)
+        else:
+            U, V, Cw, Tw = self._insertion_arrays()
+            order = np.argsort(V, kind="stable")
+            self._U, self._V, self._C, self._T = U[order], V[order], Cw[order], Tw[order]
         self._order = order
         self._counts = np.bincount(self._V, minlength=self.n)
         self._starts = np.zeros(self.n, dtype=np.int64)
@@ -331,7 +348,7 @@ class MinRatioCycleSolver:
             self._Ti = np.trunc(self._T).astype(np.int64)
         else:
             self._Ci = self._Ti = None
-        self._is_sparse = len(U) / (self.n * self.n) < self.config.sparse_threshold
+        self._is_sparse = len(self._U) / (self.n * self.n) < self.config.sparse_threshold
         if self._dev is not None:
             self._dev.close()
         self._dev = N.DeviceGraph(self.n, self._U, self._V, self._C, self._T, self._Ci, self._Ti,
@@ -352,6 +369,15 @@ class MinRatioCycleSolver:
         if not self.config.enable_preprocessing:
             return
         before = self._num_edges()
+        if before >= _DEVICE_BUILD_MIN_EDGES and not self._arrays_built:
+            # Large graph: one device pass sorts by destination AND counts repeated (u,v) pairs.  Without repeats
+            # nothing can be dominated (:531-575 only compares edges of the same pair) and the sorted arrays are
+            # kept for _build_arrays_if_needed; with repeats the host path below runs as usual.
+            U, V, Cw, Tw = self._insertion_arrays()
+            so, do, co, to, order, dups = N.sort_edges_by_dst(self.n, U, V, Cw, Tw, device=self.config.gpu_device)
+            if dups == 0:
+                self._presorted = (so, do, co, to, order)
+                return
         self._remove_dominated_edges()
         if self._num_edges() != before:
             self.logger.info("Preprocessing removed %d dominated edges", before - self._num_edges())

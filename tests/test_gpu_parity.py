@@ -426,3 +426,32 @@ def test_dimacs_benchmark_and_convenience(mrc):
     sh.add_edges([(0, 1, 2, 1), (1, 2, 3, 2), (2, 0, 1, 1)])
     re = sh.solve(mode="exact")
     assert re.metrics.mode_used == "exact" and re.cycle == [1, 2, 0, 1] and re.ratio == 1.5   # README.md:66 of the reference
+
+
+def test_device_sort_matches_numpy(mrc):
+    """mrc_sort_edges_by_dst == np.argsort(V, kind='stable') + gathers (solver.py:476-478), incl. the dup census."""
+    from min_ratio_cycle_b200 import _native as N
+    rng = np.random.default_rng(11)
+    for n, m, dup in [(1, 5, True), (7, 50, True), (1000, 300_000, True), (50_000, 400_000, False)]:
+        U = rng.integers(0, n, m); V = rng.integers(0, n, m)
+        if not dup:
+            from min_ratio_cycle_b200 import synthetic
+            U, V = synthetic._simple_pairs(n, m, rng)
+        C = rng.uniform(-5, 5, m); T = rng.uniform(0.1, 2, m)
+        so, do, co, to, order, dups = N.sort_edges_by_dst(n, U, V, C, T)
+        ref = np.argsort(V, kind="stable")
+        assert np.array_equal(order, ref) and np.array_equal(so, U[ref]) and np.array_equal(do, V[ref])
+        assert np.array_equal(co, C[ref]) and np.array_equal(to, T[ref])
+        key = U.astype(np.int64) * n + V
+        assert dups == m - len(np.unique(key))
+    # the facade takes the device path above 200k edges and must expose the same private arrays
+    n, m = 20_000, 250_000
+    from min_ratio_cycle_b200 import synthetic
+    _, U, V, C, T = synthetic.random_float(n, m, seed=4)
+    s = mrc.MinRatioCycleSolver(n, mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+    s.add_edges_arrays(U, V, C, T)
+    s.solve()
+    ref = np.argsort(V, kind="stable")
+    assert np.array_equal(s._U, U[ref]) and np.array_equal(s._V, V[ref]) and np.array_equal(s._C, C[ref])
+    assert np.array_equal(s._order, ref) and s._U.dtype == np.int64
+    assert np.array_equal(s._counts, np.bincount(V, minlength=n))
