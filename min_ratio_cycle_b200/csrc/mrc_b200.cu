@@ -155,7 +155,7 @@ static int device_info(int device, const DeviceInfo **out) {
 extern "C" int mrc_graph_destroy(mrc_graph *g) {
     if (!g) return MRC_OK;
     cudaSetDevice(g->device);
-    for (auto &p : g->patches) { cudaFree(p.d_idx); cudaFree(p.d_oldc); cudaFree(p.d_oldt); }
+    for (auto &p : g->patches) { cudaFreeAsync(p.d_idx, g->stream); cudaFreeAsync(p.d_oldc, g->stream); cudaFreeAsync(p.d_oldt, g->stream); }
     if (g->stream) {
         void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
                         g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
@@ -335,17 +335,16 @@ extern "C" int mrc_graph_patch_edges(mrc_graph *g, int64_t k, const int64_t *idx
     PatchRec p;
     p.k = k;
     double *d_dc, *d_dt;
-    CUDA_TRY(cudaMalloc(&p.d_idx, (size_t)k * 8)); CUDA_TRY(cudaMalloc(&p.d_oldc, (size_t)k * 8));
-    CUDA_TRY(cudaMalloc(&p.d_oldt, (size_t)k * 8));
-    CUDA_TRY(cudaMalloc(&d_dc, (size_t)k * 8)); CUDA_TRY(cudaMalloc(&d_dt, (size_t)k * 8));
+    DALLOC(p.d_idx, (size_t)k * 8); DALLOC(p.d_oldc, (size_t)k * 8); DALLOC(p.d_oldt, (size_t)k * 8);
+    DALLOC(d_dc, (size_t)k * 8); DALLOC(d_dt, (size_t)k * 8);
     CUDA_TRY(cudaMemcpyAsync(p.d_idx, idx, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
     CUDA_TRY(cudaMemcpyAsync(d_dc, dcost, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
     CUDA_TRY(cudaMemcpyAsync(d_dt, dtime, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
     patch_edges_kernel<<<(int)((k + 127) / 128), 128, 0, g->stream>>>(g->d_cost, g->d_time, p.d_idx, d_dc, d_dt, k,
                                                                       p.d_oldc, p.d_oldt);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(g->stream));
-    cudaFree(d_dc); cudaFree(d_dt);
+    cudaFreeAsync(d_dc, g->stream); cudaFreeAsync(d_dt, g->stream);
+    CUDA_TRY(cudaStreamSynchronize(g->stream));   // the host delta arrays may be reused by the caller
     g->patches.push_back(p);
     g->pot_valid = false;
     g->stats.other_launches++;
@@ -361,8 +360,7 @@ extern "C" int mrc_graph_restore(mrc_graph *g) {
         unpatch_edges_kernel<<<(int)((p.k + 127) / 128), 128, 0, g->stream>>>(g->d_cost, g->d_time, p.d_idx, p.k,
                                                                               p.d_oldc, p.d_oldt);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(g->stream));
-        cudaFree(p.d_idx); cudaFree(p.d_oldc); cudaFree(p.d_oldt);
+        cudaFreeAsync(p.d_idx, g->stream); cudaFreeAsync(p.d_oldc, g->stream); cudaFreeAsync(p.d_oldt, g->stream);
         g->stats.other_launches++;
     }
     return MRC_OK;

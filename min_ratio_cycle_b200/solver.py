@@ -166,6 +166,8 @@ class MinRatioCycleSolver:
         self._edges: list[Edge] = []
         self._bulk: list[tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = []
         self._presorted = None
+        self._no_repeated_pairs = False
+        self._hop_cache: dict = {}
         self._setup_logging()
         self._arrays_built = False
         self._U = self._V = self._C = self._T = self._Ci = self._Ti = None
@@ -195,6 +197,7 @@ class MinRatioCycleSolver:
     def _invalidate(self) -> None:
         self._arrays_built = False
         self._presorted = None
+        self._no_repeated_pairs = False
 
     def _num_edges(self) -> int:
         return len(self._edges) + sum(len(b[0]) for b in self._bulk)
@@ -339,6 +342,7 @@ class MinRatioCycleSolver:
             order = np.argsort(V, kind="stable")
             self._U, self._V, self._C, self._T = U[order], V[order], Cw[order], Tw[order]
         self._order = order
+        self._hop_cache = {}
         self._counts = np.bincount(self._V, minlength=self.n)
         self._starts = np.zeros(self.n, dtype=np.int64)
         if self.n > 1:
@@ -368,6 +372,8 @@ class MinRatioCycleSolver:
     def _preprocess_graph(self) -> None:
         if not self.config.enable_preprocessing:
             return
+        if self._no_repeated_pairs:          # census already done for this edge set: nothing can be dominated
+            return
         before = self._num_edges()
         if before >= _DEVICE_BUILD_MIN_EDGES and not self._arrays_built:
             # Large graph: one device pass sorts by destination AND counts repeated (u,v) pairs.  Without repeats
@@ -377,6 +383,7 @@ class MinRatioCycleSolver:
             so, do, co, to, order, dups = N.sort_edges_by_dst(self.n, U, V, Cw, Tw, device=self.config.gpu_device)
             if dups == 0:
                 self._presorted = (so, do, co, to, order)
+                self._no_repeated_pairs = True
                 return
         self._remove_dominated_edges()
         if self._num_edges() != before:
@@ -586,6 +593,16 @@ class MinRatioCycleSolver:
             return True, None
         return True, (cycle, sc, st, sc / st)
 
+    def _hop_edges(self, u: int, v: int):
+        """Sorted-array indices of the edges u -> v (CSR segment of v), memoised per array build."""
+        key = (u, v)
+        hit = self._hop_cache.get(key)
+        if hit is None:
+            s = int(self._starts[v])
+            hit = s + np.flatnonzero(self._U[s: s + int(self._counts[v])] == u)
+            self._hop_cache[key] = hit
+        return hit
+
     def _compute_cycle_weights_float(self, cycle):
         """
         Per hop, among parallel (u,v) edges the first with minimal cost/time (:1309-1313), summed in cycle
@@ -597,25 +614,17 @@ class MinRatioCycleSolver:
         L = len(cycle)
         for i in range(L):
             u, v = cycle[i], cycle[(i + 1) % L]
-            s = int(self._starts[v])
-            hit = np.flatnonzero(self._U[s: s + int(self._counts[v])] == u)
+            hit = self._hop_edges(u, v)
             if hit.size == 0:
                 raise RuntimeError(f"Edge {u} -> {v} not found in cycle")
-            if hit.size > 1:
-                k = s + hit[int(np.argmin(self._C[s + hit] / self._T[s + hit]))]
-            else:
-                k = s + hit[0]
+            k = hit[int(np.argmin(self._C[hit] / self._T[hit]))] if hit.size > 1 else hit[0]
             sc += float(self._C[k])
             st += float(self._T[k])
         return sc, st
 
     # ------------------------------------------------------------------ validation (:1495-1582)
     def _verify_cycle_exists(self, cycle):
-        issues = []
-        for u, v in zip(cycle[:-1], cycle[1:]):
-            s = int(self._starts[v])
-            if not np.any(self._U[s: s + int(self._counts[v])] == u):
-                issues.append(f"Missing edge {u} -> {v}")
+        issues = [f"Missing edge {u} -> {v}" for u, v in zip(cycle[:-1], cycle[1:]) if self._hop_edges(u, v).size == 0]
         return not issues, issues
 
     def _validate_result(self, result: SolverResult) -> SolverResult:
