@@ -115,6 +115,15 @@ int mrc_probe_numeric(mrc_graph *g, const double *lam, int K, double slack, uint
                       int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap, double *sum_cost, double *sum_time,
                       int64_t *passes);
 
+/* Scenario batching for sensitivity_analysis (solver.py:1699-1729): candidate k is evaluated on the graph with
+ * ONE edge perturbed, patch_edge[k] (dst-sorted index, -1 = none) with cost + dcost[k], time + dtime[k]; the K
+ * scenarios share every edge read.  Same outputs as mrc_probe_numeric (sums include the perturbation).  The
+ * device-resident edge arrays are not modified. */
+int mrc_probe_numeric_scenarios(mrc_graph *g, const double *lam, int K, double slack, uint32_t flags,
+                                const int64_t *patch_edge, const double *dcost, const double *dtime, int32_t *verdict,
+                                int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap, double *sum_cost,
+                                double *sum_time, int64_t *passes);
+
 /* Full cycle of candidate k of the LAST probe (numeric or exact), for callers that probed with a small
  * cyc_cap: CLOSED vertex list; *cycle_len = 0 if that candidate extracted none. */
 int mrc_fetch_cycle(mrc_graph *g, int k, int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len);

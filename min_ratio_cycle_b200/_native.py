@@ -29,7 +29,7 @@ EXPORTS = [
     "mrc_graph_info", "mrc_numeric_bounds", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
     "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
     "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
-    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle", "mrc_sort_edges_by_dst",
+    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle", "mrc_sort_edges_by_dst", "mrc_probe_numeric_scenarios",
 ]
 
 
@@ -90,6 +90,8 @@ def lib():
     L.mrc_solve_exact.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, p32, C.c_int64, p64, p64, p64, p64, p64, p64,
                                   p64, C.c_int64, p64]
     L.mrc_sort_edges_by_dst.argtypes = [C.c_int64, C.c_int64, p32, p32, pd, pd, C.c_int, p32, p32, pd, pd, p32, p64]
+    L.mrc_probe_numeric_scenarios.argtypes = [vp, pd, C.c_int, C.c_double, C.c_uint32, p64, pd, pd, p32, p32, p32, C.c_int64,
+                                              pd, pd, p64]
     L.mrc_fetch_cycle.argtypes = [vp, C.c_int, p32, C.c_int64, p64]
     L.mrc_bench_relax.argtypes = [vp, pd, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.mrc_set_option.argtypes = [vp, C.c_char_p, C.c_int]
@@ -210,6 +212,22 @@ class DeviceGraph:
             out.append(dict(lam=float(lam[k]), verdict=int(vd[k]), cycle=cyc, cycle_len=int(cl[k]),
                             sum_cost=float(sc[k]), sum_time=float(st[k]), passes=int(ps[k])))
         return out
+
+    def probe_numeric_scenarios(self, lams, patch_edge, dcost, dtime, slack: float = 1e-15, cyc_cap: int | None = None):
+        """K single-edge perturbation scenarios in one batched probe (mrc_probe_numeric_scenarios)."""
+        lam = np.ascontiguousarray(lams, dtype=np.float64)
+        pe = np.ascontiguousarray(patch_edge, dtype=np.int64)
+        dc = np.ascontiguousarray(dcost, dtype=np.float64); dt = np.ascontiguousarray(dtime, dtype=np.float64)
+        K = len(lam)
+        cap = int(cyc_cap if cyc_cap is not None else min(self.n + 1, 1024))
+        vd = np.zeros(K, np.int32); cl = np.zeros(K, np.int32); buf = np.empty(K * cap, np.int32)
+        sc = np.zeros(K); st = np.zeros(K); ps = np.zeros(K, np.int64)
+        check(lib().mrc_probe_numeric_scenarios(self._h, _ptr(lam, C.c_double), K, float(slack), 0, _ptr(pe, C.c_int64),
+                                                _ptr(dc, C.c_double), _ptr(dt, C.c_double), _ptr(vd, C.c_int32),
+                                                _ptr(cl, C.c_int32), _ptr(buf, C.c_int32), cap, _ptr(sc, C.c_double),
+                                                _ptr(st, C.c_double), _ptr(ps, C.c_int64)))
+        return [dict(lam=float(lam[k]), verdict=int(vd[k]), cycle=self._cycle_of(k, buf, cap, int(cl[k])),
+                     sum_cost=float(sc[k]), sum_time=float(st[k]), passes=int(ps[k])) for k in range(K)]
 
     def probe_exact(self, a, b, flags: int = 0, cyc_cap: int | None = None):
         a = np.ascontiguousarray(a, dtype=np.int64); b = np.ascontiguousarray(b, dtype=np.int64)

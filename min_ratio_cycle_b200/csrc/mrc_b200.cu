@@ -67,6 +67,7 @@ struct mrc_graph {
     std::vector<PatchRec> patches;
     ProbeOut last_res[MRC_KMAX];   // last probe's per-candidate results (cycles stay on the device until the next probe)
     bool last_exact = false; int last_K = 0;
+    bool scen_on = false; int scen_pe[MRC_KMAX]; double scen_dc[MRC_KMAX], scen_dt[MRC_KMAX];   // scenario batching of the current probe
     int relax_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     int tma_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     int frontier = 0;            // option "frontier": passes >= frontier_from use relax_kernel_frontier
@@ -433,6 +434,12 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         if (exact) { ra.a[k] = ca.a[k] = a[k]; ra.b[k] = ca.b[k] = b[k]; } else ra.lam[k] = ca.lam[k] = lam[k];
         res[k] = ProbeOut();
     }
+    ra.scen = ca.scen = (!exact && g->scen_on) ? 1 : 0;
+    for (int k = 0; k < MRC_KMAX; k++) {
+        ra.pe[k] = ca.pe[k] = (ra.scen && k < K) ? g->scen_pe[k] : -1;
+        ra.pdc[k] = ca.pdc[k] = (ra.scen && k < K) ? g->scen_dc[k] : 0.0;
+        ra.pdt[k] = ca.pdt[k] = (ra.scen && k < K) ? g->scen_dt[k] : 0.0;
+    }
     ca.src = g->d_src; ca.cost = g->d_cost; ca.time = g->d_time; ca.icost = g->d_icost; ca.itime = g->d_itime;
     ca.pred = g->d_pred; ca.dist = g->d_dist; ca.jump = g->d_jump; ca.cyc_edges = g->d_cyc_edges; ca.st = g->d_status;
     ca.n = n; ca.cap = g->cyc_cap; ca.exact = exact;
@@ -561,7 +568,7 @@ static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::
     if (L <= 0) return MRC_OK;
     if (L > g->cyc_cap) return set_err(MRC_ERR_ARG, "cycle longer than buffer");
     if (!g->d_g_src) {
-        DALLOC(g->d_g_src, (size_t)g->cyc_cap * 4);
+        DALLOC(g->d_g_src, (size_t)g->cyc_cap * 8);
         DALLOC(g->d_g_c, (size_t)g->cyc_cap * 8); DALLOC(g->d_g_t, (size_t)g->cyc_cap * 8);
         DALLOC(g->d_g_ic, (size_t)g->cyc_cap * 8); DALLOC(g->d_g_it, (size_t)g->cyc_cap * 8);
     }
@@ -570,10 +577,10 @@ static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::
                                                        g->d_time, g->d_icost, g->d_itime, exact, g->d_g_src, g->d_g_c,
                                                        g->d_g_t, g->d_g_ic, g->d_g_it);
     CUDA_TRY(cudaGetLastError());
-    std::vector<int> hsrc((size_t)L);
+    std::vector<int> hsrc((size_t)L * 2);
     std::vector<double> hc, ht;
     std::vector<ll> hic, hit;
-    CUDA_TRY(cudaMemcpyAsync(hsrc.data(), g->d_g_src, (size_t)L * 4, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(hsrc.data(), g->d_g_src, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
     if (exact) {
         hic.resize(L); hit.resize(L);
         CUDA_TRY(cudaMemcpyAsync(hic.data(), g->d_g_ic, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
@@ -598,7 +605,11 @@ static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::
         if (ist) *ist = t;
     } else {
         double c = 0.0, t = 0.0;
-        for (ll j = L - 1; j >= 0; j--) { c += hc[j]; t += ht[j]; }
+        for (ll j = L - 1; j >= 0; j--) {
+            double ce = hc[j], te = ht[j];
+            if (g->scen_on && hsrc[L + j] == g->scen_pe[k]) { ce += g->scen_dc[k]; te += g->scen_dt[k]; }
+            c += ce; t += te;
+        }
         if (sc) *sc = c;
         if (st) *st = t;
     }
@@ -651,6 +662,25 @@ extern "C" int mrc_probe_numeric(mrc_graph *g, const double *lam, int K, double 
     return probe_common<double>(g, false, lam, nullptr, nullptr, K, slack, flags, verdict, cyc_len, cyc_buf, cyc_cap,
                                 sum_cost, sum_time, passes);
 }
+extern "C" int mrc_probe_numeric_scenarios(mrc_graph *g, const double *lam, int K, double slack, uint32_t flags,
+                                           const int64_t *patch_edge, const double *dcost, const double *dtime,
+                                           int32_t *verdict, int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap,
+                                           double *sum_cost, double *sum_time, int64_t *passes) {
+    if (!g || !lam || !patch_edge || !dcost || !dtime) return set_err(MRC_ERR_ARG, "NULL argument");
+    if (K < 1 || K > MRC_KMAX) return set_err(MRC_ERR_ARG, "K must be in [1,%d]", MRC_KMAX);
+    for (int k = 0; k < K; k++) {
+        if (patch_edge[k] >= g->m) return set_err(MRC_ERR_ARG, "edge index out of range");
+        g->scen_pe[k] = patch_edge[k] < 0 ? -1 : (int)patch_edge[k];
+        g->scen_dc[k] = dcost[k]; g->scen_dt[k] = dtime[k];
+    }
+    g->scen_on = true;
+    // pruning by monotonicity is meaningless here: the candidates belong to K different graphs
+    const int rc = probe_common<double>(g, false, lam, nullptr, nullptr, K, slack, flags & ~MRC_F_MONOTONE_PRUNE, verdict,
+                                        cyc_len, cyc_buf, cyc_cap, sum_cost, sum_time, passes);
+    g->scen_on = false;
+    return rc;
+}
+
 extern "C" int mrc_probe_exact(mrc_graph *g, const int64_t *a, const int64_t *b, int K, uint32_t flags,
                                int32_t *verdict, int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap,
                                int64_t *sum_cost, int64_t *sum_time, int64_t *passes) {

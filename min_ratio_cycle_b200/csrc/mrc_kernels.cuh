@@ -53,6 +53,10 @@ struct RelaxArgs {
     const unsigned *act_in;    // set by the previous launch; read only by relax_kernel_frontier
     ull *examined;             // edges actually relaxed by relax_kernel_frontier launches
     ll n;
+    // scenario batching (numeric only): candidate k sees edge pe[k] with cost + pdc[k], time + pdt[k]
+    int scen;
+    int pe[MRC_KMAX];
+    double pdc[MRC_KMAX], pdt[MRC_KMAX];
 };
 
 struct CycleOut {
@@ -86,6 +90,9 @@ struct CheckArgs {
     int exact;
     double lam[MRC_KMAX];
     ll a[MRC_KMAX], b[MRC_KMAX];
+    int scen;
+    int pe[MRC_KMAX];
+    double pdc[MRC_KMAX], pdt[MRC_KMAX];
 };
 
 // ---- cache-hinted accessors --------------------------------------------------------------------
@@ -133,6 +140,11 @@ __device__ __forceinline__ double mrc_cand(const RelaxArgs &p, int k, double du,
 __device__ __forceinline__ ll mrc_cand(const RelaxArgs &p, int k, ll du, ll c, ll t) {
     return du + (p.b[k] * c - p.a[k] * t);
 }
+// scenario batching: candidate k re-solves the graph with ONE edge perturbed (sensitivity_analysis, solver.py:1716-1721)
+__device__ __forceinline__ void mrc_scenario_patch(const RelaxArgs &p, int k, int e, double &c, double &t) {
+    if (p.scen && e == p.pe[k]) { c = __dadd_rn(c, p.pdc[k]); t = __dadd_rn(t, p.pdt[k]); }
+}
+__device__ __forceinline__ void mrc_scenario_patch(const RelaxArgs &, int, int, ll &, ll &) {}
 __device__ __forceinline__ bool mrc_improves(const RelaxArgs &p, double cand, double dv) {
     return cand < __dsub_rn(dv, p.slack);
 }
@@ -192,7 +204,9 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
         T cand = 0;
         bool imp = false;
         if (valid) {
-            cand = mrc_cand(p, k, du[k], c, t);
+            T ck = c, tk = t;
+            mrc_scenario_patch(p, k, e, ck, tk);
+            cand = mrc_cand(p, k, du[k], ck, tk);
             imp = mrc_improves(p, cand, dv[k]);
         }
         const unsigned im = __ballot_sync(0xffffffffu, imp);
@@ -663,7 +677,9 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                         if (i < p.cap) p.cyc_edges[(ll)k * p.cap + i] = e;
                         if (p.exact) { isc += __ldg(p.icost + e); ist += __ldg(p.itime + e); }
                         else {
-                            sc += __ldg(p.cost + e); stt += __ldg(p.time + e);
+                            double ce = __ldg(p.cost + e), te = __ldg(p.time + e);
+                            if (p.scen && e == p.pe[k]) { ce = __dadd_rn(ce, p.pdc[k]); te = __dadd_rn(te, p.pdt[k]); }
+                            sc += ce; stt += te;
                             mabs = fmax(mabs, fabs(__ldcg(static_cast<const double *>(p.dist) + (ll)cur * K + k)));
                         }
                         cur = (int)(pe >> 32);
@@ -714,9 +730,11 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
 __global__ void gather_cycle_kernel(const int *edges, ll len, const int *src, const double *cost,
                                     const double *time, const ll *icost, const ll *itime, int exact,
                                     int *o_src, double *o_c, double *o_t, ll *o_ic, ll *o_it) {
+    // o_src[0..len) = source vertices, o_src[len..2len) = edge indices
     for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (ll)gridDim.x * blockDim.x) {
         const int e = edges[i];
         o_src[i] = src[e];
+        o_src[len + i] = e;
         if (exact) { o_ic[i] = icost[e]; o_it[i] = itime[e]; }
         else { o_c[i] = cost[e]; o_t[i] = time[e]; }
     }

@@ -661,7 +661,6 @@ class MinRatioCycleSolver:
         applied to the device-resident arrays (mrc_graph_patch_edges) instead of rebuilding Edge objects and
         arrays per scenario; reported sums use the perturbed weights.
         """
-        results: list[SolverResult] = []
         self._preprocess_graph()
         self._build_arrays_if_needed()
         # warm start: the unperturbed optimum is still a cycle of every perturbed graph, so its (re-costed)
@@ -674,6 +673,7 @@ class MinRatioCycleSolver:
         m = self._num_edges()
         inv = np.empty(m, dtype=np.int64)
         inv[self._order] = np.arange(m)
+        scen_arrays = []
         for scenario in edge_perturbations:
             for idx in scenario:
                 if idx < 0 or idx >= m:
@@ -683,7 +683,41 @@ class MinRatioCycleSolver:
             dt = np.array([float(d[1]) for d in scenario.values()], dtype=np.float64)
             if np.any(self._T[pos] + dt <= 0):
                 raise ValueError("Edge transit time must be strictly positive")
-            saved = (self._C[pos].copy(), self._T[pos].copy(), self._all_int)
+            scen_arrays.append((pos, dc, dt))
+        results: list[SolverResult | None] = [None] * len(scen_arrays)
+        tol, slack = self.config.numeric_tolerance, self.config.numeric_cycle_slack
+
+        def recost(pos, dc, dt, cyc):
+            keep = (self._C[pos].copy(), self._T[pos].copy())   # restore bit-exactly, not by subtracting
+            self._C[pos] += dc; self._T[pos] += dt
+            try:
+                return self._compute_cycle_weights_float(cyc)
+            finally:
+                self._C[pos], self._T[pos] = keep
+
+        # Fast path: K single-edge scenarios share every edge read (mrc_probe_numeric_scenarios).  Each one probes
+        # its own certifier, (ratio of the unperturbed optimum under that scenario's weights) - 0.75 tol; no
+        # negative cycle there means that cycle is still optimal to within tol -- the answer the sequential path
+        # below would give.  Scenarios whose optimum moves (or that touch several edges) fall through to it.
+        if warm is not None:
+            K = max(1, min(int(self.config.gpu_candidates), N.KMAX))
+            singles = [i for i, sa in enumerate(scen_arrays) if len(sa[0]) == 1]
+            for b0 in range(0, len(singles), K):
+                grp = singles[b0: b0 + K]
+                sums = [recost(*scen_arrays[i], warm[:-1]) for i in grp]
+                lams = [sc / st - 0.75 * tol for sc, st in sums]
+                out = self._dev.probe_numeric_scenarios(lams, [int(scen_arrays[i][0][0]) for i in grp],
+                                                        [float(scen_arrays[i][1][0]) for i in grp],
+                                                        [float(scen_arrays[i][2][0]) for i in grp], slack)
+                for i, (sc, st), o in zip(grp, sums, out):
+                    if o["verdict"] == N.V_NONNEG and st > 0:
+                        results[i] = SolverResult(cycle=list(warm), sum_cost=sc, sum_time=st, ratio=sc / st, success=True,
+                                                  metrics=SolverMetrics(iterations=1, mode_used="numeric"),
+                                                  config_used=self.config)
+        for i, (pos, dc, dt) in enumerate(scen_arrays):
+            if results[i] is not None:
+                continue
+            saved = (self._C[pos].copy(), self._T[pos].copy())
             self._dev.patch_edges(pos, dc, dt)
             self._C[pos] += dc
             self._T[pos] += dt
@@ -694,7 +728,7 @@ class MinRatioCycleSolver:
                 res.config_used = self.config
                 if self._metrics:
                     res.metrics = SolverMetrics(iterations=self._metrics.iterations, mode_used="numeric")
-                results.append(res)
+                results[i] = res
             finally:
                 self._dev.restore()
                 self._C[pos], self._T[pos] = saved[0], saved[1]
