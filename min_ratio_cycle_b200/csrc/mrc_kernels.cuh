@@ -258,14 +258,30 @@ template <> struct WeightT<true> { typedef ll type; };
 #ifndef MRC_TUNE_ROWS8
 #define MRC_TUNE_ROWS8 4
 #endif
+#ifndef MRC_TUNE_STAGE
+#define MRC_TUNE_STAGE false   /* measured slower than plain loads at every K (profiles/r01_relax_variants.txt) */
+#endif
+#ifndef MRC_TUNE_DEPTH
+#define MRC_TUNE_DEPTH 3
+#endif
 template <int K> struct RelaxTune {
     static constexpr int rows = MRC_TUNE_ROWS, minblocks = MRC_TUNE_MB;
     static constexpr bool prefetch = MRC_TUNE_PF;
+    static constexpr bool stage = MRC_TUNE_STAGE;   // edge stream through a per-warp cp.async ring in shared memory
 };
 template <> struct RelaxTune<8> {
     static constexpr int rows = MRC_TUNE_ROWS8, minblocks = 1;
     static constexpr bool prefetch = false;
+    static constexpr bool stage = false;
 };
+__device__ __forceinline__ void mrc_cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void mrc_cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void mrc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void mrc_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <int K, bool EXACT>
 __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) relax_kernel(const __grid_constant__ RelaxArgs p) {
     typedef typename WeightT<EXACT>::type W;
@@ -284,7 +300,62 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
     // cost more occupancy than the overlap wins.  Hoisting all gathers of a chunk ahead of the first use
     // was also measured and is slower at every K.)
     constexpr bool PREFETCH = RelaxTune<K>::prefetch;
-    if constexpr (!PREFETCH) {
+    if constexpr (RelaxTune<K>::stage) {
+        // EXPERIMENT, off by default.  Stall sampling put 2/3 of the memory stalls on the first use of the edge
+        // stream, not on the gathers, so here every warp keeps its own DEPTH-deep ring of chunks in shared
+        // memory, filled with cp.async (LDGSTS: no registers, no block barrier).  Measured: 88 us (K=4) and
+        // 71 us (K=1) per launch against 74 / 58 us for plain loads on the same box -- the LDGSTS issue cost and
+        // the extra shared-memory round trip outweigh the overlap.
+        constexpr int D = MRC_TUNE_DEPTH;
+        constexpr int WARPS = MRC_RELAX_THREADS / 32;
+        __shared__ int s_src[WARPS][D][MRC_ROWS][32], s_dst[WARPS][D][MRC_ROWS][32];
+        __shared__ W s_cost[WARPS][D][MRC_ROWS][32], s_time[WARPS][D][MRC_ROWS][32];
+        const int w = threadIdx.x >> 5;
+        auto issue = [&](ll c, int slot) {
+            if (c < nchunks) {
+                const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
+#pragma unroll
+                for (int j = 0; j < MRC_ROWS; j++) {
+                    const ll e = e0 + 32 * j;
+                    if (e < p.m) {
+                        mrc_cp_async4(&s_src[w][slot][j][lane], p.src + e);
+                        mrc_cp_async4(&s_dst[w][slot][j][lane], p.dst + e);
+                        mrc_cp_async8(&s_cost[w][slot][j][lane], cost + e);
+                        mrc_cp_async8(&s_time[w][slot][j][lane], time + e);
+                    }
+                }
+            }
+            mrc_cp_async_commit();
+        };
+#pragma unroll
+        for (int d = 0; d < D - 1; d++) issue(warp + (ll)d * nwarps, d);
+        int slot = 0;
+        for (ll c = warp; c < nchunks; c += nwarps) {
+            int nslot = slot + D - 1;
+            if (nslot >= D) nslot -= D;
+            issue(c + (ll)(D - 1) * nwarps, nslot);
+            mrc_cp_async_wait<D - 1>();
+            __syncwarp();
+            const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
+            if (e0 - lane + CH <= p.m) {
+#pragma unroll
+                for (int j = 0; j < MRC_ROWS; j++)
+                    relax_row<K, W>(p, true, lane, (int)(e0 + 32 * j), s_src[w][slot][j][lane], s_dst[w][slot][j][lane],
+                                    s_cost[w][slot][j][lane], s_time[w][slot][j][lane], chg);
+            } else {
+#pragma unroll
+                for (int j = 0; j < MRC_ROWS; j++) {
+                    const ll e = e0 + 32 * j;
+                    const bool ok = e < p.m;
+                    relax_row<K, W>(p, ok, lane, (int)e, ok ? s_src[w][slot][j][lane] : 0,
+                                    ok ? s_dst[w][slot][j][lane] : -1 - lane, ok ? s_cost[w][slot][j][lane] : W(0),
+                                    ok ? s_time[w][slot][j][lane] : W(0), chg);
+                }
+            }
+            __syncwarp();
+            slot = slot + 1 == D ? 0 : slot + 1;
+        }
+    } else if constexpr (!PREFETCH) {
         for (ll c = warp; c < nchunks; c += nwarps) {
             const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
             if (e0 - lane + CH <= p.m) {

@@ -455,3 +455,25 @@ def test_device_sort_matches_numpy(mrc):
     assert np.array_equal(s._U, U[ref]) and np.array_equal(s._V, V[ref]) and np.array_equal(s._C, C[ref])
     assert np.array_equal(s._order, ref) and s._U.dtype == np.int64
     assert np.array_equal(s._counts, np.bincount(V, minlength=n))
+
+
+def test_c1_three_way_statistics(mrc, oracle_mod):
+    """BASELINE config 1 on 16 seeds (reference: ~100 s per seed, tests/golden/c1_seeds.json): three-way verdict
+    of SURVEY 8c with the oracle certificate; every GPU answer must certify, none may MISMATCH."""
+    from min_ratio_cycle_b200 import synthetic
+    C1 = load_golden("c1_seeds.json")
+    counts = {MATCH: 0, REF_SUBOPTIMAL: 0, MISMATCH: 0}
+    for seed in sorted(C1, key=int):
+        n, U, V, C, T = synthetic.random_float(1000, 5000, seed=int(seed))
+        s = mrc.MinRatioCycleSolver(n, mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+        s.add_edges_arrays(U, V, C, T)
+        r = s.solve(mode="numeric")
+        o = oracle_mod.Oracle(n, U, V, C, T, all_int=False, threads=4)
+        o.set_quirks(False)
+        ok, why = o.certify(r.cycle, r.ratio)
+        assert ok, (seed, why)
+        v, why = three_way(o, {"cycle": r.cycle, "ratio": r.ratio}, C1[seed])
+        counts[v] += 1
+        assert v != MISMATCH, (seed, why)
+    print("C1 three-way verdicts over 16 seeds:", counts)
+    assert counts[MATCH] >= 12
