@@ -1138,8 +1138,11 @@ extern "C" int mrc_batch_solve_numeric(int64_t B, const int32_t *nverts, const i
     CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     BatchArgs a;
     memset(&a, 0, sizeof a);
-    ll *d_off; int *d_nv, *d_src, *d_dst, *d_len, *d_buf, *d_it, *d_status; double *d_c, *d_t, *d_r, *d_sc, *d_st; ull *d_cnt;
-    cudaEvent_t e0, e1;
+    ll *d_off = nullptr;
+    int *d_nv = nullptr, *d_src = nullptr, *d_dst = nullptr, *d_len = nullptr, *d_buf = nullptr, *d_it = nullptr, *d_status = nullptr;
+    double *d_c = nullptr, *d_t = nullptr, *d_r = nullptr, *d_sc = nullptr, *d_st = nullptr;
+    ull *d_cnt = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     int rc = [&]() -> int {
         CUDA_TRY(cudaMallocAsync((void **)&d_off, (B + 1) * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_nv, B * 4, st));
         CUDA_TRY(cudaMallocAsync((void **)&d_src, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_dst, M * 4, st));
@@ -1183,12 +1186,13 @@ extern "C" int mrc_batch_solve_numeric(int64_t B, const int32_t *nverts, const i
             stats_out->relax_launches = 1; stats_out->relax_edge_visits = (int64_t)cnt; stats_out->relax_ms = ms;
             stats_out->probes = B * K; stats_out->h2d_bytes = M * 24 + B * 12; stats_out->d2h_bytes = B * (36 + cycle_cap * 4);
         }
-        void *ptrs[] = {d_off, d_nv, d_src, d_dst, d_c, d_t, d_r, d_sc, d_st, d_len, d_buf, d_it, d_status, d_cnt};
-        for (void *q : ptrs) cudaFreeAsync(q, st);
-        cudaStreamSynchronize(st);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
         return MRC_OK;
     }();
+    void *ptrs[] = {d_off, d_nv, d_src, d_dst, d_c, d_t, d_r, d_sc, d_st, d_len, d_buf, d_it, d_status, d_cnt};
+    for (void *q : ptrs) if (q) cudaFreeAsync(q, st);
+    cudaStreamSynchronize(st);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
     cudaStreamDestroy(st);
     return rc;
 }
