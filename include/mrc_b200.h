@@ -149,7 +149,9 @@ int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_cycle, int m
 int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *ms_per_pass);
 /* Tuning knobs: "alternate" (sweep direction flips every pass, 0/1), "burst_init", "burst_max" (passes per
  * host round trip), "tma" (bit mask over K in {1,2,4,8}: TMA-staged edge stream), "frontier" (0/1: launches
- * from "frontier_from" on skip edges whose source vertex was not lowered by the previous launch). */
+ * from "frontier_from" on skip edges whose source vertex was not lowered by the previous launch), "stop_on_neg"
+ * (minimum K from which mrc_solve_numeric passes MRC_F_STOP_ON_NEG to its probes; 0 = never, the default).
+ * A graph handle is not thread-safe: one probe / solve at a time per mrc_graph. */
 int mrc_set_option(mrc_graph *g, const char *name, int value);
 
 /* Pure host helpers shared by mrc_solve_numeric and the multi-GPU driver (one process per GPU, the

@@ -70,6 +70,7 @@ struct mrc_graph {
     bool scen_on = false; int scen_pe[MRC_KMAX]; double scen_dc[MRC_KMAX], scen_dt[MRC_KMAX];   // scenario batching of the current probe
     int relax_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     int tma_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int stop_on_neg = 0;         // option "stop_on_neg": minimum K from which mrc_solve_numeric ends rounds early (0 = never)
     int frontier = 0;            // option "frontier": passes >= frontier_from use relax_kernel_frontier
     int frontier_from = 5;
     unsigned *d_act[2] = {nullptr, nullptr};   // active-vertex bitmaps (previous / current launch)
@@ -534,16 +535,9 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         // passes later than the far ones and are the ones worth waiting for (measured: stopping at pass 2
         // needs 10 rounds instead of 4).
         if ((flags & MRC_F_STOP_ON_NEG) && active && do_check && passes >= 6) {
-            // A cycle found below the largest lambda of the batch (usually the certifier, whose cycle barely
-            // moves the bracket) is worth stopping for at once; the certifier's own cycle only after the
-            // interior candidates had until pass 14 to close theirs.
-            int top = 0;
-            for (int k = 1; k < K; k++)
-                if (exact ? ((i128)a[k] * b[top] > (i128)a[top] * b[k]) : (lam[k] > lam[top])) top = k;
-            bool any_neg = false, interior_neg = false;
-            for (int k = 0; k < K; k++)
-                if (res[k].verdict == MRC_V_NEG) { any_neg = true; interior_neg |= (k != top); }
-            if (interior_neg || (any_neg && passes >= 14) || (any_neg && K == 1)) {
+            bool any_neg = false;
+            for (int k = 0; k < K; k++) any_neg |= res[k].verdict == MRC_V_NEG;
+            if (any_neg) {
                 for (int k = 0; k < K; k++)
                     if ((active >> k) & 1u) { res[k].verdict = MRC_V_ABANDONED; res[k].passes = passes; }
                 active = 0;
@@ -738,6 +732,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
             return set_err(MRC_ERR_ARG, "frontier mode keeps n/8 bytes of shared memory per SM: n too large");
         g->frontier = value != 0;
     }
+    else if (s == "stop_on_neg") g->stop_on_neg = std::max(0, value);
     else if (s == "frontier_from") g->frontier_from = std::max(1, value);
     else if (s == "burst_init") g->burst_init = std::max(1, std::min(value, MRC_MAX_BURST));
     else if (s == "burst_max") g->burst_max = std::max(1, std::min(value, MRC_MAX_BURST));
@@ -783,10 +778,11 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
         iters++;
         g->stats.rounds++;
         MRC_TRY(mrc_plan_candidates(lo, hi, have_cycle, tol, K, lam));
-        // (MRC_F_STOP_ON_NEG -- ending intermediate rounds at the first verified cycle -- was measured at C3:
-        // fewer passes per round but 5-10 rounds instead of 3-4 and no net gain, so every round runs until the
-        // bracket ends next to lambda* are decided.)
-        MRC_TRY(run_probe(g, false, K, lam, nullptr, nullptr, slack, MRC_F_MONOTONE_PRUNE, res));
+        // Option "stop_on_neg": intermediate rounds only need a better cycle, so a round may end at the first
+        // check (from pass 6 on) that verified one, leaving the slow non-negative candidates undecided; the round in
+        // which nothing is negative still runs to convergence and proves the lower end.
+        MRC_TRY(run_probe(g, false, K, lam, nullptr, nullptr, slack,
+                          MRC_F_MONOTONE_PRUNE | ((g->stop_on_neg && K >= g->stop_on_neg) ? MRC_F_STOP_ON_NEG : 0u), res));
         for (int k = 0; k < K; k++) {
             vd[k] = res[k].verdict;
             cr[k] = (vd[k] == MRC_V_NEG || vd[k] == MRC_V_TIE) ? res[k].sumc / res[k].sumt : NAN;

@@ -12,7 +12,7 @@ def main():
     if os.path.exists(cache) and n == 1_000_000:
         z = np.load(cache); U, V, C, T = z["U"], z["V"], z["C"], z["T"]
     else:
-        n, U, V, C, T = synthetic.random_float(n, m, seed=0)
+        n, U, V, C, T = synthetic.random_float(n, m, seed=int(os.environ.get('MRC_SEED', '0')))
         order = np.argsort(V, kind="stable")
         U, V, C, T = U[order], V[order], C[order], T[order]
         if n == 1_000_000: np.savez(cache, U=U, V=V, C=C, T=T)
@@ -23,6 +23,7 @@ def main():
     lo, hi = g.bounds()
     if os.environ.get("MRC_FRONTIER"): g.set_option("frontier", int(os.environ["MRC_FRONTIER"]))
     if os.environ.get("MRC_FFROM"): g.set_option("frontier_from", int(os.environ["MRC_FFROM"]))
+    if os.environ.get("MRC_STOP"): g.set_option("stop_on_neg", int(os.environ["MRC_STOP"]))
     if os.environ.get("MRC_BURST"): g.set_option("burst_init", int(os.environ["MRC_BURST"]))
     print("bounds", lo, hi)
     for K in (1, 2, 4, 4, 4):
