@@ -477,3 +477,12 @@ def test_c1_three_way_statistics(mrc, oracle_mod):
         assert v != MISMATCH, (seed, why)
     print("C1 three-way verdicts over 16 seeds:", counts)
     assert counts[MATCH] >= 12
+
+
+def test_every_kernel_variant_on_odd_sizes(mrc):
+    """Dense / TMA-staged / frontier relaxation at K=1,2,4,8, scenario probes, device patches, exact strategies,
+    batch kernel and device sort on sizes that exercise every tail path; all relaxation variants must agree."""
+    import os
+    import runpy
+    from conftest import ROOT
+    runpy.run_path(os.path.join(ROOT, "tools", "sanitize_case.py"), run_name="__main__")
