@@ -760,6 +760,13 @@ class MinRatioCycleSolver:
             lines.append(f"  Cycle length: {len(self._last_result.cycle) - 1}")
         return "\n".join(lines)
 
+    def visualize_solution(self, *args, **kwargs):
+        """Plotting (:1761-1812) is outside the hot path and not provided here; the result objects are the
+        reference's, so the reference's own plotting helpers can be fed with them."""
+        raise NotImplementedError("visualisation is out of scope of the GPU hot path (SURVEY.md section 2)")
+
+    create_interactive_plot = visualize_solution
+
     def health_check(self) -> dict[str, Any]:
         checks = []
         ndev = N.device_count()
