@@ -266,26 +266,6 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         DALLOC(g->d_act[0], g->act_bytes); DALLOC(g->d_act[1], g->act_bytes);
         if (const char *env = getenv("MRC_B200_FRONTIER"))   // A/B switch for experiments and the parity suite
             g->frontier = atoi(env) != 0 && g->act_bytes + 2048 <= 227 * 1024;
-        // dist is the only randomly gathered array: ask L2 to keep it resident while 240 MB of edges stream past
-        // (persisting access-policy window on the library stream; the edge loads carry evict-first hints anyway)
-        if (!getenv("MRC_B200_NO_L2_PERSIST")) {
-            int max_persist = 0, max_window = 0;
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
-            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-            const size_t want = (size_t)n * MRC_KMAX * 8;
-            const size_t win = std::min<size_t>(want, (size_t)std::max(max_window, 0));
-            if (max_persist > 0 && win > 0) {
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)max_persist, want));
-                cudaStreamAttrValue av;
-                memset(&av, 0, sizeof av);
-                av.accessPolicyWindow.base_ptr = g->d_dist;
-                av.accessPolicyWindow.num_bytes = win;
-                av.accessPolicyWindow.hitRatio = 1.0f;
-                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                if (cudaStreamSetAttribute(g->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
-            }
-        }
         // input validation on the device (the host never touches the 24 B/edge again)
         DALLOC(g->d_verr, 4);
         CUDA_TRY(cudaMemsetAsync(g->d_verr, 0, 4, g->stream));
