@@ -192,22 +192,28 @@ __device__ __forceinline__ bool mrc_resolve_crowded(bool imp, T cand, int v, int
 template <int K, typename T>
 __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int lane, int e, int u, int v, T c, T t,
                                           unsigned &chg) {
-    T du[K], dv[K];
+    // K = 8 is processed as two halves of 4 candidates (two 256-bit gathers from the same 64-B group, one after
+    // the other), so its register footprint stays that of K = 4 and 4 CTAs remain resident per SM.
+    constexpr int H = K > 4 ? 4 : K;
     T *dist = static_cast<T *>(p.dist);
+#pragma unroll
+    for (int h = 0; h < K; h += H) {
+    if (!((p.active >> h) & ((1u << H) - 1u))) continue;   // warp-uniform: nothing active in this half
+    T du[H], dv[H];
     if (valid) {
-        DistVec<K>::load(du, dist + (size_t)u * K);
-        DistVec<K>::load(dv, dist + (size_t)v * K);
+        DistVec<H>::load(du, dist + (size_t)u * K + h);
+        DistVec<H>::load(dv, dist + (size_t)v * K + h);
     }
 #pragma unroll
-    for (int k = 0; k < K; k++) {
+    for (int k = h; k < h + H; k++) {
         if (!((p.active >> k) & 1u)) continue;   // warp-uniform
         T cand = 0;
         bool imp = false;
         if (valid) {
             T ck = c, tk = t;
             mrc_scenario_patch(p, k, e, ck, tk);
-            cand = mrc_cand(p, k, du[k], ck, tk);
-            imp = mrc_improves(p, cand, dv[k]);
+            cand = mrc_cand(p, k, du[k - h], ck, tk);
+            imp = mrc_improves(p, cand, dv[k - h]);
         }
         const unsigned im = __ballot_sync(0xffffffffu, imp);
         if (im == 0) continue;                   // warp-uniform
@@ -231,6 +237,7 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
             if (p.act_out) atomicOr(p.act_out + (v >> 5), 1u << (v & 31));
             chg |= 1u << k;
         }
+    }
     }
 }
 
@@ -256,7 +263,10 @@ template <> struct WeightT<true> { typedef ll type; };
 #define MRC_TUNE_PF (K <= 2)
 #endif
 #ifndef MRC_TUNE_ROWS8
-#define MRC_TUNE_ROWS8 4
+#define MRC_TUNE_ROWS8 2
+#endif
+#ifndef MRC_TUNE_MB8
+#define MRC_TUNE_MB8 4
 #endif
 #ifndef MRC_TUNE_STAGE
 #define MRC_TUNE_STAGE false   /* measured slower than plain loads at every K (profiles/r01_relax_variants.txt) */
@@ -270,7 +280,7 @@ template <int K> struct RelaxTune {
     static constexpr bool stage = MRC_TUNE_STAGE;   // edge stream through a per-warp cp.async ring in shared memory
 };
 template <> struct RelaxTune<8> {
-    static constexpr int rows = MRC_TUNE_ROWS8, minblocks = 1;
+    static constexpr int rows = MRC_TUNE_ROWS8, minblocks = MRC_TUNE_MB8;
     static constexpr bool prefetch = false;
     static constexpr bool stage = false;
 };
