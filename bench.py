@@ -282,6 +282,11 @@ def main():
         if args.frontier:
             # a frontier launch does not read 24 B for every edge: no HBM roofline is claimed for this mode
             achieved = 0.0
+        # for information: the same kernel in steady state (30 launches from dist = 0 at K non-negative lambdas, each
+        # timed with its own CUDA-event pair; mean of launches 21-30, i.e. without the atomics-heavy first passes)
+        ms30 = g.bench_relax([out["ratio"] - 0.5 - 0.1 * k for k in range(K)], 30)
+        steady_us = float(ms30[20:].mean()) * 1e3
+        steady = bytes_per_launch / (steady_us * 1e-6) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -303,7 +308,9 @@ def main():
                     "path": "mrc_graph_create(pinned host arrays) + mrc_solve_numeric + mrc_graph_destroy"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_kind": peak_kind, "kernel": f"relax_kernel<K={K if K in (1,2,4,8) else 8},f64>",
-                         "bytes_per_launch": bytes_per_launch, "frac_of_8TBs_nominal": achieved / 8000.0},
+                         "bytes_per_launch": bytes_per_launch, "frac_of_8TBs_nominal": achieved / 8000.0,
+                         "steady_state": {"us_per_launch": steady_us, "achieved": steady, "frac": steady / peak,
+                                          "note": "outside the timed region; launches 21-30 of a 30-launch sweep"}},
         }
         if not args.no_cpu_baseline:
             lam = (lo0 + hi0) / 2.0
