@@ -31,7 +31,8 @@ struct PatchRec {
 struct ProbeOut {
     int verdict = -1;
     int len = 0;
-    int minv = -1;
+    int minv = -1;               // smallest vertex of the cycle
+    int start = -1;              // vertex the device walk (and its edge list) starts from
     double sumc = 0, sumt = 0;   // predecessor-walk order (device)
     ll isumc = 0, isumt = 0;
     ll passes = 0;
@@ -511,7 +512,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
                 // found == 1 verified negative, 2 rounding tie; cycles that are neither were cut there
                 const CycleOut &c = hs.out[k];
                 o.verdict = (c.found == 1) ? MRC_V_NEG : MRC_V_TIE;
-                o.len = c.len; o.minv = c.minv; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
+                o.len = c.len; o.minv = c.minv; o.start = c.pad; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
             }
             if (o.verdict >= 0) { o.passes = passes; active &= ~(1u << k); }
         }
@@ -587,19 +588,24 @@ static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::
     CUDA_TRY(cudaStreamSynchronize(g->stream));
     g->stats.other_launches++;
     g->stats.d2h_bytes += L * 20;
-    // backward walk e_0..e_{L-1} from minv; forward cycle uses e_{L-1}, ..., e_0
+    // The device recorded the BACKWARD walk from `start`: b_0 = start, b_{j+1} = src(e_j), b_L = start, edge e_j
+    // runs b_{j+1} -> b_j.  Forward cycle: f_i = b_{L-i}, forward edge i = e_{L-1-i}.  Rotate it so that it starts
+    // at the smallest vertex, and accumulate the sums in that order.
+    auto fvert = [&](ll i) { return i == 0 ? o.start : hsrc[(size_t)(L - 1 - i)]; };   // f_i for 0 <= i < L
+    ll r = 0;
+    for (ll i = 0; i < L; i++) if (fvert(i) == o.minv) { r = i; break; }
     verts.reserve((size_t)L + 1);
-    verts.push_back(o.minv);
-    for (ll j = L - 2; j >= 0; j--) verts.push_back(hsrc[j]);
+    for (ll i = 0; i < L; i++) verts.push_back(fvert((r + i) % L));
     verts.push_back(o.minv);
     if (exact) {
         ll c = 0, t = 0;
-        for (ll j = L - 1; j >= 0; j--) { c += hic[j]; t += hit[j]; }
+        for (ll i = 0; i < L; i++) { const ll j = L - 1 - (r + i) % L; c += hic[j]; t += hit[j]; }
         if (isc) *isc = c;
         if (ist) *ist = t;
     } else {
         double c = 0.0, t = 0.0;
-        for (ll j = L - 1; j >= 0; j--) {
+        for (ll i = 0; i < L; i++) {
+            const ll j = L - 1 - (r + i) % L;
             double ce = hc[j], te = ht[j];
             if (g->scen_on && hsrc[L + j] == g->scen_pe[k]) { ce += g->scen_dc[k]; te += g->scen_dt[k]; }
             c += ce; t += te;

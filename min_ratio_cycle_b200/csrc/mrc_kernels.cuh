@@ -731,27 +731,25 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
             const int rep = __ldcg(&st->rep[it * MRC_KMAX + k]);
             bool settled = true;   // nothing left to examine for k unless a false cycle is cut below
             if (rep != 0x7fffffff) {
-                // rep leads into a cycle; enter it with a tortoise/hare walk over pred (tails are short)
+                // rep leads into a cycle.  Brent's cycle finding over pred (one pointer step per iteration, ~half the
+                // dependent loads of tortoise/hare) lands `x` on the cycle; ONE further lap from x then records the
+                // edge list, the sums and the smallest vertex (the host rotates the list to start there).
                 auto step = [&](int y) { return y < 0 ? -1 : (int)(__ldcg(p.pred + (ll)y * K + k) >> 32); };
-                int x = rep, hare = rep;
-                for (ll g = 0; g <= p.n; g++) {
-                    x = step(x);
-                    hare = step(step(hare));
-                    if (x == hare) break;
+                int x = step(rep), tort = rep;
+                {
+                    ll power = 1, lam_ = 1;
+                    for (ll g = 0; x >= 0 && x != tort && g <= 3 * p.n; g++) {
+                        if (power == lam_) { tort = x; power <<= 1; lam_ = 0; }
+                        x = step(x);
+                        lam_++;
+                    }
                 }
-                int cur = x, minv = x;
-                ll len = 0;
-                bool ok = x >= 0;
-                if (ok) do {
-                    cur = step(cur);
-                    if (cur < 0) { ok = false; break; }
-                    len++;
-                    if (cur < minv) minv = cur;
-                } while (cur != x && len <= p.n);
-                if (ok && cur == x) {
+                bool ok = x >= 0 && x == tort;
+                int minv = x;
+                if (ok) {
                     double sc = 0.0, stt = 0.0, mabs = 0.0;
                     ll isc = 0, ist = 0, i = 0;
-                    cur = minv;
+                    int cur = x;
                     do {
                         const ull pe = __ldcg(p.pred + (ll)cur * K + k);
                         const int e = (int)(unsigned)pe;
@@ -764,8 +762,11 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                             mabs = fmax(mabs, fabs(__ldcg(static_cast<const double *>(p.dist) + (ll)cur * K + k)));
                         }
                         cur = (int)(pe >> 32);
+                        if (cur >= 0 && cur < minv) minv = cur;
                         i++;
-                    } while (cur != minv && i <= p.n);
+                    } while (cur != x && cur >= 0 && i <= p.n);
+                    ok = (cur == x);
+                    if (!ok) { sc = 0.0; stt = 0.0; isc = 0; ist = 0; }
                     int kind = 0;
                     if (p.exact) {
                         if ((__int128)p.b[k] * isc - (__int128)p.a[k] * ist < 0) kind = MRC_CYC_NEG;
@@ -778,7 +779,7 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                     }
                     if (kind) {
                         CycleOut o;
-                        o.found = kind; o.len = (int)i; o.minv = minv; o.pad = 0;
+                        o.found = kind; o.len = (int)i; o.minv = minv; o.pad = x;   // pad = vertex the recorded walk starts from
                         o.sumc = sc; o.sumt = stt; o.maxabs = mabs; o.isumc = isc; o.isumt = ist;
                         st->out[k] = o;
                     } else {

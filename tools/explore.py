@@ -37,7 +37,7 @@ def main():
               f"wall={dt*1e3:.1f}ms relax_launches={st['relax_launches']} relax_ms={st['relax_ms']:.2f} "
               f"check_launches={st['check_launches']} check_ms={st['check_ms']:.2f} "
               f"us/pass={st['relax_ms']*1e3/max(1,st['relax_launches']):.1f} edge GB/s={gbps:.0f} "
-              f"GTEPS={st['relax_edge_visits']/(st['relax_ms']*1e-3)/1e9:.1f}", flush=True)
+              f"GTEPS={st['relax_edge_visits']/(st['relax_ms']*1e-3)/1e9:.1f} cuts={st['false_cycles_cut']}", flush=True)
     # single probes for pass counts
     r = out["ratio"]
     for lam in (r + 1.0, r + 1e-3, r - 1e-3, r - 1.0):
