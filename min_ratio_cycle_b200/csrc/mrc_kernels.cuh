@@ -518,8 +518,15 @@ __global__ void __launch_bounds__(MRC_FRONTIER_THREADS, 1) relax_kernel_frontier
 // an mbarrier (complete_tx::bytes).  The copy engine runs 2 tiles (48 KB per CTA, 3 CTAs per SM) ahead of
 // the warps, so HBM latency is fully decoupled from the dist gathers, and the threads keep all their
 // registers for the K-wide gather/compare/atomic part.
+#ifndef MRC_TMA_TILE
 #define MRC_TMA_TILE 1024
+#endif
+#ifndef MRC_TMA_STAGES
 #define MRC_TMA_STAGES 3
+#endif
+#ifndef MRC_TMA_MB
+#define MRC_TMA_MB 3
+#endif
 #define MRC_TMA_THREADS 256
 #define MRC_TMA_STAGE_BYTES (MRC_TMA_TILE * 24)
 #define MRC_TMA_SMEM (MRC_TMA_STAGES * MRC_TMA_STAGE_BYTES + 64)
@@ -545,7 +552,7 @@ __device__ __forceinline__ void mrc_bulk_g2s(unsigned dst, const void *src, unsi
 }
 
 template <int K, bool EXACT>
-__global__ void __launch_bounds__(MRC_TMA_THREADS, 3) relax_kernel_tma(const __grid_constant__ RelaxArgs p) {
+__global__ void __launch_bounds__(MRC_TMA_THREADS, MRC_TMA_MB) relax_kernel_tma(const __grid_constant__ RelaxArgs p) {
     typedef typename WeightT<EXACT>::type W;
     extern __shared__ __align__(128) unsigned char smem[];
     const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
