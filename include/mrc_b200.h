@@ -50,13 +50,16 @@ extern "C" {
 #define MRC_V_TIE 3            /* extracted cycle has ratio >= lambda within rounding: lambda ~ ratio of that cycle */
 #define MRC_V_SKIPPED_NEG 4    /* not evaluated to the end: a smaller lambda of the batch was already negative */
 #define MRC_V_SKIPPED_NONNEG 5 /* not evaluated to the end: a larger lambda of the batch already had no negative cycle */
-#define MRC_V_ABANDONED 6      /* not evaluated to the end and nothing implied (MRC_F_STOP_ON_NEG) */
+#define MRC_V_ABANDONED 6      /* not evaluated to the end and nothing implied (MRC_F_STOP_ON_NEG / MRC_F_PATIENCE) */
 
 /* probe flags */
 #define MRC_F_MONOTONE_PRUNE 1u /* stop candidates whose verdict is implied by monotonicity in lambda */
 #define MRC_F_STOP_ON_NEG 2u     /* end the probe at the first cycle check that verifies a negative cycle: the search only
                                    needs that cycle's ratio to tighten the bracket; the candidates still relaxing are
                                    reported MRC_V_ABANDONED */
+#define MRC_F_PATIENCE 4u        /* once a negative cycle is verified, end the probe at the first cycle check whose whole
+                                   interval (as long as everything before it) brought no further verdict; the open
+                                   candidates -- slow ones next to lambda* -- are reported MRC_V_ABANDONED */
 
 typedef struct mrc_graph mrc_graph;
 
@@ -150,7 +153,12 @@ int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *m
 /* Tuning knobs: "alternate" (sweep direction flips every pass, 0/1), "burst_init", "burst_max" (passes per
  * host round trip), "tma" (bit mask over K in {1,2,4,8}: TMA-staged edge stream), "frontier" (0/1: launches
  * from "frontier_from" on skip edges whose source vertex was not lowered by the previous launch), "stop_on_neg"
- * (minimum K from which mrc_solve_numeric passes MRC_F_STOP_ON_NEG to its probes; 0 = never, the default).
+ * (minimum K from which mrc_solve_numeric passes MRC_F_STOP_ON_NEG to its probes; 0 = never, the default),
+ * "narrow" (0/1, default 1: once some of the K candidates of a probe are decided, the remaining passes run the
+ * narrowest kernel -- 1, 2 or 4 candidates wide -- that covers the undecided slots of the dist/pred layout),
+ * "gate" (0/1, default 1: a relaxation launch returns at once when the previous launch of its burst moved none of
+ * its candidates, so bursts can be long without wasting passes after convergence), "patience" (0/1:
+ * mrc_solve_numeric passes MRC_F_PATIENCE to its probes).
  * A graph handle is not thread-safe: one probe / solve at a time per mrc_graph. */
 int mrc_set_option(mrc_graph *g, const char *name, int value);
 

@@ -78,7 +78,10 @@ struct mrc_graph {
     size_t act_bytes = 0;
     int use_tma[4] = {0, 0, 0, 0};   // per KT index: stream the edges through the TMA-staged kernel (option "tma")
     int check_blocks[4] = {0, 0, 0, 0};
-    int burst_init = 2, burst_max = MRC_MAX_BURST;
+    int burst_init = 2, burst_max = 16;
+    int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
+    int patience = 0;            // option "patience": mrc_solve_numeric passes MRC_F_PATIENCE to its probes
+    int narrow = 1;              // option "narrow": late passes run the narrowest kernel covering the undecided candidates
     bool alternate = true;
     mrc_stats stats;
 };
@@ -370,7 +373,38 @@ extern "C" int mrc_graph_restore(mrc_graph *g) {
 }
 
 // ------------------------------------------------------------------------------------------- probe engine
-static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra, bool frontier_pass = false) {
+// Narrowest kernel that still covers every undecided candidate slot: an aligned sub-range of width 1, 2 or 4 of
+// the KT slots (alignment keeps the 128/256-bit dist loads legal).  Most rounds spend their late passes on a
+// single slow candidate; serving it with the K=1 kernel on the strided layout saves the arithmetic and the
+// registers of the decided ones.
+static void narrow_candidates(int KT, unsigned active, int *kc, int *k0) {
+    *kc = KT; *k0 = 0;
+    for (int w = 1; w < KT; w *= 2)
+        for (int o = 0; o < KT; o += w)
+            if (active && !(active & ~(((1u << w) - 1u) << o))) { *kc = w; *k0 = o; return; }
+}
+static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_full, bool frontier_pass = false) {
+    RelaxArgs ra = ra_full;
+    ra.ks = KT; ra.k0 = 0;
+    if (g->narrow && !frontier_pass && !g->use_tma[kt_index(KT)]) {
+        int kc, k0;
+        narrow_candidates(KT, ra.active, &kc, &k0);
+        if (kc < KT) {
+            const size_t esz = 8;   // double and int64 slots alike
+            ra.dist = (char *)ra.dist + (size_t)k0 * esz;
+            ra.pred += k0;
+            ra.active >>= k0;
+            ra.k0 = k0;
+            for (int j = 0; j < kc; j++) {
+                ra.lam[j] = ra_full.lam[k0 + j]; ra.a[j] = ra_full.a[k0 + j]; ra.b[j] = ra_full.b[k0 + j];
+                ra.pe[j] = ra_full.pe[k0 + j]; ra.pdc[j] = ra_full.pdc[k0 + j]; ra.pdt[j] = ra_full.pdt[k0 + j];
+            }
+            void *nargs[] = {(void *)&ra};
+            const int blocks = g->relax_blocks[kt_index(kc)][exact ? 1 : 0];
+            CUDA_TRY(cudaLaunchKernel(relax_fn_of(kc, exact), dim3(blocks), dim3(MRC_RELAX_THREADS), nargs, 0, g->stream));
+            return MRC_OK;
+        }
+    }
     void *args[] = {(void *)&ra};
     if (frontier_pass) {
         const size_t smem = g->act_bytes;
@@ -455,6 +489,8 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     int burst = g->burst_init;
     ll next_check = g->burst_init;   // cycle checks after 2, 6, 14, 30, ... passes; convergence flags every burst
     g->stats.probes += K;
+    bool any_neg = false;            // MRC_F_PATIENCE bookkeeping
+    int new_verdicts = 0;
     while (active) {
         const int nb = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
         if (nb <= 0) {
@@ -479,12 +515,15 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
                 fpass = pidx + 1 >= g->frontier_from;
             }
             if (!fpass) dense_launches++;
+            // launch i > 0 returns at once if launch i-1 moved none of the candidates still open
+            ra.gate = (i > 0 && !g->frontier && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
             MRC_TRY(launch_relax(g, KT, exact, ra, fpass));
         }
         CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
         const bool do_check = passes + nb >= next_check || passes + nb >= max_passes;
         if (do_check) {
             ca.active = active;
+            ca.gate = g->gate ? &g->d_status->changed[nb - 1] : nullptr;
             MRC_TRY(launch_check(g, KT, ca));
             next_check = 2 * next_check + 2;
         }
@@ -494,28 +533,36 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->stats.relax_ms += ms;
         CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
-        passes += nb;
-        g->stats.relax_launches += nb;
+        const DevStatus &hs = *g->h_status;
+        // launches that did work: the first of the burst, and each one whose predecessor still moved something
+        int ran = nb;
+        if (!g->frontier && g->gate)
+            for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
+        if (!g->frontier) dense_launches = ran;
+        g->stats.relax_launches += ran;
+        g->stats.other_launches += nb - ran;
         g->stats.relax_edge_visits += ((int64_t)dense_launches * m + (int64_t)g->h_status->examined) * __builtin_popcount(active);
-        g->stats.relax_edge_slots += (int64_t)nb * m * __builtin_popcount(active);
+        g->stats.relax_edge_slots += (int64_t)ran * m * __builtin_popcount(active);
         if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += g->h_status->cuts; }
         g->stats.d2h_bytes += sizeof(DevStatus);
-        const DevStatus &hs = *g->h_status;
         for (int k = 0; k < K; k++) {
             if (!((active >> k) & 1u)) continue;
-            bool conv = false;
-            for (int i = 0; i < nb; i++) conv |= !((hs.changed[i] >> k) & 1u);
+            int conv_at = -1;
+            for (int i = 0; i < nb && conv_at < 0; i++) if (!((hs.changed[i] >> k) & 1u)) conv_at = i;
             ProbeOut &o = res[k];
-            if (conv) { o.verdict = MRC_V_NONNEG; }
+            if (conv_at >= 0) { o.verdict = MRC_V_NONNEG; o.passes = passes + conv_at + 1; }
             else if (do_check && ((hs.cyc_mask >> k) & 1u) && hs.out[k].found) {
                 // the check kernel extracted a cycle and tested it against lambda on the device:
                 // found == 1 verified negative, 2 rounding tie; cycles that are neither were cut there
                 const CycleOut &c = hs.out[k];
                 o.verdict = (c.found == 1) ? MRC_V_NEG : MRC_V_TIE;
                 o.len = c.len; o.minv = c.minv; o.start = c.pad; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
+                o.passes = passes + nb;
+                any_neg |= c.found == 1;
             }
-            if (o.verdict >= 0) { o.passes = passes; active &= ~(1u << k); }
+            if (o.verdict >= 0) { active &= ~(1u << k); new_verdicts++; }
         }
+        passes += nb;
         if (flags & MRC_F_MONOTONE_PRUNE) {
             // verdicts are monotone in lambda: NEG at x implies NEG above x, NONNEG at x implies NONNEG below x
             for (int k = 0; k < K; k++) {
@@ -536,13 +583,23 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         // passes later than the far ones and are the ones worth waiting for (measured: stopping at pass 2
         // needs 10 rounds instead of 4).
         if ((flags & MRC_F_STOP_ON_NEG) && active && do_check && passes >= 6) {
-            bool any_neg = false;
-            for (int k = 0; k < K; k++) any_neg |= res[k].verdict == MRC_V_NEG;
-            if (any_neg) {
+            bool neg_now = false;
+            for (int k = 0; k < K; k++) neg_now |= res[k].verdict == MRC_V_NEG;
+            if (neg_now) {
                 for (int k = 0; k < K; k++)
                     if ((active >> k) & 1u) { res[k].verdict = MRC_V_ABANDONED; res[k].passes = passes; }
                 active = 0;
             }
+        }
+        // MRC_F_PATIENCE: a negative cycle is in hand and a whole check interval (as long as everything before it)
+        // brought no further verdict -- what is still open is a slow candidate next to lambda*; leave it undecided.
+        if ((flags & MRC_F_PATIENCE) && active && do_check) {
+            if (any_neg && new_verdicts == 0) {
+                for (int k = 0; k < K; k++)
+                    if ((active >> k) & 1u) { res[k].verdict = MRC_V_ABANDONED; res[k].passes = passes; }
+                active = 0;
+            }
+            new_verdicts = 0;
         }
         burst = std::min(burst * 2, g->burst_max);
     }
@@ -740,6 +797,9 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     }
     else if (s == "stop_on_neg") g->stop_on_neg = std::max(0, value);
     else if (s == "frontier_from") g->frontier_from = std::max(1, value);
+    else if (s == "narrow") g->narrow = value != 0;
+    else if (s == "gate") g->gate = value != 0;
+    else if (s == "patience") g->patience = value != 0;
     else if (s == "burst_init") g->burst_init = std::max(1, std::min(value, MRC_MAX_BURST));
     else if (s == "burst_max") g->burst_max = std::max(1, std::min(value, MRC_MAX_BURST));
     else return set_err(MRC_ERR_ARG, "unknown option %s", name);
@@ -788,7 +848,8 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
         // check (from pass 6 on) that verified one, leaving the slow non-negative candidates undecided; the round in
         // which nothing is negative still runs to convergence and proves the lower end.
         MRC_TRY(run_probe(g, false, K, lam, nullptr, nullptr, slack,
-                          MRC_F_MONOTONE_PRUNE | ((g->stop_on_neg && K >= g->stop_on_neg) ? MRC_F_STOP_ON_NEG : 0u), res));
+                          MRC_F_MONOTONE_PRUNE | ((g->stop_on_neg && K >= g->stop_on_neg) ? MRC_F_STOP_ON_NEG : 0u) |
+                              (g->patience ? MRC_F_PATIENCE : 0u), res));
         for (int k = 0; k < K; k++) {
             vd[k] = res[k].verdict;
             cr[k] = (vd[k] == MRC_V_NEG || vd[k] == MRC_V_TIE) ? res[k].sumc / res[k].sumt : NAN;

@@ -26,7 +26,7 @@ namespace cg = cooperative_groups;
 typedef long long ll;
 typedef unsigned long long ull;
 
-#define MRC_MAX_BURST 8
+#define MRC_MAX_BURST 32
 #ifndef MRC_CROWD_MIN
 #define MRC_CROWD_MIN 6   /* improving lanes per row above which the segmented scan replaces the pairwise loop */
 #endif
@@ -47,6 +47,15 @@ struct RelaxArgs {
     ll a[MRC_KMAX], b[MRC_KMAX];
     double slack;
     unsigned active;     // bit k: candidate k still undecided
+    // A launch may serve a SUB-RANGE of the KT candidate slots of the dist/pred layout (the slots still undecided):
+    // the kernel template then is the sub-range width, `ks` stays the slot count of the layout (row stride of
+    // dist and pred), the host pre-offsets dist/pred/lam/a/b/active/pe.. by the first slot `k0`, and `k0` only
+    // shifts the bits of the changed word back.
+    int ks, k0;
+    // Convergence gate: the changed word of the PREVIOUS launch of the same burst (NULL for the first).  If that
+    // launch lowered nothing for any candidate this launch serves, every one of them sits at its fixed point and
+    // the launch returns at once -- the host enqueues whole bursts without looking, the device stops on the pass.
+    const unsigned *gate;
     int reverse;         // sweep the edge stream back to front (L2 reuse between consecutive passes)
     // frontier mode (optional): one bit per vertex, "dist[v] was lowered for some candidate"
     unsigned *act_out;         // set by this launch (NULL = not tracked)
@@ -87,6 +96,8 @@ struct CheckArgs {
     ll n, cap;
     int rounds;          // ceil(log2(n+1)) + 1
     unsigned active;
+    const unsigned *gate;   // changed word of the last relaxation launch: candidates it did not move are at their
+                            // fixed point (no cycle to look for); all of them there -> the launch returns at once
     int exact;
     double lam[MRC_KMAX];
     ll a[MRC_KMAX], b[MRC_KMAX];
@@ -201,8 +212,8 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
     if (!((p.active >> h) & ((1u << H) - 1u))) continue;   // warp-uniform: nothing active in this half
     T du[H], dv[H];
     if (valid) {
-        DistVec<H>::load(du, dist + (size_t)u * K + h);
-        DistVec<H>::load(dv, dist + (size_t)v * K + h);
+        DistVec<H>::load(du, dist + (size_t)u * p.ks + h);
+        DistVec<H>::load(dv, dist + (size_t)v * p.ks + h);
     }
 #pragma unroll
     for (int k = h; k < h + H; k++) {
@@ -232,8 +243,8 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int la
             }
             imp = imp && !lose;
         }
-        if (imp && mrc_atomic_lower(dist + (size_t)v * K + k, cand)) {
-            __stcg(p.pred + (size_t)v * K + k, ((ull)(unsigned)u << 32) | (unsigned)e);
+        if (imp && mrc_atomic_lower(dist + (size_t)v * p.ks + k, cand)) {
+            __stcg(p.pred + (size_t)v * p.ks + k, ((ull)(unsigned)u << 32) | (unsigned)e);
             if (p.act_out) atomicOr(p.act_out + (v >> 5), 1u << (v & 31));
             chg |= 1u << k;
         }
@@ -297,6 +308,7 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
     typedef typename WeightT<EXACT>::type W;
     const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
     const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
+    if (p.gate && !((__ldcg(p.gate) >> p.k0) & p.active)) return;
     unsigned chg = 0;
     const int lane = threadIdx.x & 31;
     const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -450,7 +462,7 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
     }
     // changed flag: warp vote, one atomic per warp at most
     chg = __reduce_or_sync(0xffffffffu, chg);
-    if (lane == 0 && chg) atomicOr(p.changed, chg);
+    if (lane == 0 && chg) atomicOr(p.changed, chg << p.k0);
 }
 
 // ---- frontier relaxation ------------------------------------------------------------------------------
@@ -506,7 +518,7 @@ __global__ void __launch_bounds__(MRC_FRONTIER_THREADS, 1) relax_kernel_frontier
     }
     chg = __reduce_or_sync(0xffffffffu, chg);
     if (lane == 0) {
-        if (chg) atomicOr(p.changed, chg);
+        if (chg) atomicOr(p.changed, chg << p.k0);
         if (seen) atomicAdd(p.examined, (ull)seen);
     }
 }
@@ -615,7 +627,7 @@ __global__ void __launch_bounds__(MRC_TMA_THREADS, MRC_TMA_MB) relax_kernel_tma(
         }
     }
     chg = __reduce_or_sync(0xffffffffu, chg);
-    if (lane == 0 && chg) atomicOr(p.changed, chg);
+    if (lane == 0 && chg) atomicOr(p.changed, chg << p.k0);
 }
 
 // ---- predecessor-graph cycle check -----------------------------------------------------------------
@@ -649,12 +661,14 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         st->out[threadIdx.x].len = 0;
     }
     if (tid0 == 0) { st->cyc_mask = 0; st->pend = 0; st->cuts = 0; }
+    const unsigned active = p.gate ? (p.active & __ldcg(p.gate)) : p.active;
+    if (!active) return;   // grid-uniform
     // jump = grandparent (two predecessor steps straight from pred, which nobody writes during this
     // phase): saves the separate init sweep, its grid sync and the src[] gather of an edge-only pred
     for (ll i = tid0; i < total; i += stride) {
         const int k = (int)(i % K);
         int j = -1;
-        if ((p.active >> k) & 1u) {
+        if ((active >> k) & 1u) {
             const int u = (int)(__ldcg(p.pred + i) >> 32);
             if (u >= 0) j = (int)(__ldcg(p.pred + (ll)u * K + k) >> 32);
         }
@@ -665,8 +679,8 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     // In a forest at least one live vertex reaches a root in every doubling round (the shallowest live
     // vertex of each chain), so a candidate whose live count did not drop in a round has only vertices
     // that lead into cycles left: stop doubling for it right there instead of running all log2(n) rounds.
-    unsigned alive_mask = p.active;   // candidates with live vertices
-    unsigned moving = p.active;       // ... whose live count is still dropping
+    unsigned alive_mask = active;   // candidates with live vertices
+    unsigned moving = active;       // ... whose live count is still dropping
     int r = 0;
     for (; r < p.rounds && moving; r++) {
         unsigned cnt[K];
