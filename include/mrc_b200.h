@@ -157,7 +157,9 @@ int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *m
  * "narrow" (0/1, default 1: once some of the K candidates of a probe are decided, the remaining passes run the
  * narrowest kernel -- 1, 2 or 4 candidates wide -- that covers the undecided slots of the dist/pred layout),
  * "gate" (0/1, default 1: a relaxation launch returns at once when the previous launch of its burst moved none of
- * its candidates, so bursts can be long without wasting passes after convergence), "patience" (0/1:
+ * its candidates, so bursts can be long without wasting passes after convergence), "prune_above" (0/1, default 1:
+ * with MRC_F_MONOTONE_PRUNE and candidates in increasing order a cycle check stops working on the candidates
+ * above the lowest one whose predecessor graph holds a cycle), "patience" (0/1:
  * mrc_solve_numeric passes MRC_F_PATIENCE to its probes).
  * A graph handle is not thread-safe: one probe / solve at a time per mrc_graph. */
 int mrc_set_option(mrc_graph *g, const char *name, int value);

@@ -79,6 +79,7 @@ struct mrc_graph {
     int use_tma[4] = {0, 0, 0, 0};   // per KT index: stream the edges through the TMA-staged kernel (option "tma")
     int check_blocks[4] = {0, 0, 0, 0};
     int burst_init = 2, burst_max = 16;
+    int prune_above = 1;         // option "prune_above": cycle checks stop examining candidates above the lowest one with a cycle
     int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
     int patience = 0;            // option "patience": mrc_solve_numeric passes MRC_F_PATIENCE to its probes
     int narrow = 1;              // option "narrow": late passes run the narrowest kernel covering the undecided candidates
@@ -479,6 +480,12 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     ca.src = g->d_src; ca.cost = g->d_cost; ca.time = g->d_time; ca.icost = g->d_icost; ca.itime = g->d_itime;
     ca.pred = g->d_pred; ca.dist = g->d_dist; ca.jump = g->d_jump; ca.cyc_edges = g->d_cyc_edges; ca.st = g->d_status;
     ca.n = n; ca.cap = g->cyc_cap; ca.exact = exact;
+    if ((flags & MRC_F_MONOTONE_PRUNE) && g->prune_above) {
+        bool asc = true;
+        for (int k = 1; k < K; k++)
+            asc &= exact ? ((i128)a[k - 1] * b[k] < (i128)a[k] * b[k - 1]) : (lam[k - 1] < lam[k]);
+        ca.prune_above = asc ? 1 : 0;
+    }
     { int r = 1; while (((ll)1 << r) < n + 1) r++; ca.rounds = std::min(r + 1, MRC_MAX_ROUNDS); }
 
     CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)n * KT * 8, g->stream));      // dist = 0 (:1148 / :829)
@@ -799,6 +806,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "frontier_from") g->frontier_from = std::max(1, value);
     else if (s == "narrow") g->narrow = value != 0;
     else if (s == "gate") g->gate = value != 0;
+    else if (s == "prune_above") g->prune_above = value != 0;
     else if (s == "patience") g->patience = value != 0;
     else if (s == "burst_init") g->burst_init = std::max(1, std::min(value, MRC_MAX_BURST));
     else if (s == "burst_max") g->burst_max = std::max(1, std::min(value, MRC_MAX_BURST));

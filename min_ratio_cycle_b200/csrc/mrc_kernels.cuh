@@ -99,6 +99,8 @@ struct CheckArgs {
     const unsigned *gate;   // changed word of the last relaxation launch: candidates it did not move are at their
                             // fixed point (no cycle to look for); all of them there -> the launch returns at once
     int exact;
+    int prune_above;        // candidates are in increasing lambda order and the caller prunes by monotonicity: once the
+                            // lowest candidate with a cycle is known, the ones above it are not examined further
     double lam[MRC_KMAX];
     ll a[MRC_KMAX], b[MRC_KMAX];
     int scen;
@@ -718,6 +720,13 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
             if (c) na |= 1u << k;
             if (c && c < cp && ((moving >> k) & 1u)) nm |= 1u << k;
         }
+        if (p.prune_above) {
+            // a candidate that is alive but no longer moving holds a cycle; a cycle negative at lambda_k is negative
+            // at every larger lambda, so the (deeper, junk-cycle) predecessor graphs above it need no more rounds
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (((na >> k) & 1u) && !((nm >> k) & 1u)) { na &= (2u << k) - 1u; nm &= (2u << k) - 1u; break; }
+        }
         alive_mask = na;
         moving = nm;
     }
@@ -747,47 +756,102 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
             if ((threadIdx.x & 31) == 0 && b != 0x7fffffff) atomicMin(&st->rep[it * MRC_KMAX + k], b);
         }
         grid.sync();
-        if (threadIdx.x == 0 && blockIdx.x < K && ((pending >> blockIdx.x) & 1u)) {
+        if (blockIdx.x < K && ((pending >> blockIdx.x) & 1u)) {   // block-uniform: block k serves candidate k
             const int k = blockIdx.x;
-            const int rep = __ldcg(&st->rep[it * MRC_KMAX + k]);
-            bool settled = true;   // nothing left to examine for k unless a false cycle is cut below
-            if (rep != 0x7fffffff) {
-                // rep leads into a cycle.  Brent's cycle finding over pred (one pointer step per iteration, ~half the
-                // dependent loads of tortoise/hare) lands `x` on the cycle; ONE further lap from x then records the
-                // edge list, the sums and the smallest vertex (the host rotates the list to start there).
-                auto step = [&](int y) { return y < 0 ? -1 : (int)(__ldcg(p.pred + (ll)y * K + k) >> 32); };
-                int x = step(rep), tort = rep;
-                {
-                    ll power = 1, lam_ = 1;
-                    for (ll g = 0; x >= 0 && x != tort && g <= 3 * p.n; g++) {
-                        if (power == lam_) { tort = x; power <<= 1; lam_ = 0; }
-                        x = step(x);
-                        lam_++;
+            __shared__ int s_x, s_len;
+            __shared__ double s_d[3][8];
+            __shared__ ll s_l[2][8];
+            __shared__ int s_m[8];
+            auto step = [&](int y) { return y < 0 ? -1 : (int)(__ldcg(p.pred + (ll)y * K + k) >> 32); };
+            // one lap over pred from y, recording the edge list; returns the vertex it stopped at
+            auto lap = [&](int y, ll cap, ll &len) {
+                int cur = y;
+                ll i = 0;
+                do {
+                    const ull pe = __ldcg(p.pred + (ll)cur * K + k);
+                    if (i < p.cap) p.cyc_edges[(ll)k * p.cap + i] = (int)(unsigned)pe;
+                    cur = (int)(pe >> 32);
+                    i++;
+                } while (cur != y && cur >= 0 && i < cap);
+                len = i;
+                return cur;
+            };
+            if (threadIdx.x == 0) {
+                const int rep = __ldcg(&st->rep[it * MRC_KMAX + k]);
+                int x = -1;
+                ll len = 0;
+                if (rep != 0x7fffffff) {
+                    // rep leads into a cycle.  The doubled pointers land ON it in a few dozen hops (each hop is
+                    // >= 2^(rounds+1) predecessor steps; doubling may have stalled after 2-3 rounds while the tail
+                    // into the cycle is hundreds of steps long); a lap that returns to its start proves it.  If the
+                    // tail is longer still, the point where the capped lap stopped is itself past the tail; only
+                    // if even that fails Brent's cycle finding (one pointer step per iteration) runs from there.
+                    int y = rep;
+                    for (int t = 0; t < 96; t++) {
+                        const int j = __ldcg(p.jump + (ll)y * K + k);
+                        if (j < 0) break;
+                        y = j;
+                    }
+                    int cur = lap(y, 2048, len);
+                    if (cur == y) x = y;
+                    else if (cur >= 0) {
+                        y = cur;
+                        cur = lap(y, 4096, len);
+                        if (cur == y) x = y;
+                        else if (cur >= 0) {
+                            int hare = step(cur), tort = cur;
+                            ll power = 1, lam_ = 1;
+                            for (ll g = 0; hare >= 0 && hare != tort && g <= 3 * p.n; g++) {
+                                if (power == lam_) { tort = hare; power <<= 1; lam_ = 0; }
+                                hare = step(hare);
+                                lam_++;
+                            }
+                            if (hare >= 0 && hare == tort && lap(hare, p.n + 1, len) == hare) x = hare;
+                        }
                     }
                 }
-                bool ok = x >= 0 && x == tort;
-                int minv = x;
-                if (ok) {
-                    double sc = 0.0, stt = 0.0, mabs = 0.0;
-                    ll isc = 0, ist = 0, i = 0;
-                    int cur = x;
-                    do {
-                        const ull pe = __ldcg(p.pred + (ll)cur * K + k);
-                        const int e = (int)(unsigned)pe;
-                        if (i < p.cap) p.cyc_edges[(ll)k * p.cap + i] = e;
-                        if (p.exact) { isc += __ldg(p.icost + e); ist += __ldg(p.itime + e); }
-                        else {
-                            double ce = __ldg(p.cost + e), te = __ldg(p.time + e);
-                            if (p.scen && e == p.pe[k]) { ce = __dadd_rn(ce, p.pdc[k]); te = __dadd_rn(te, p.pdt[k]); }
-                            sc += ce; stt += te;
-                            mabs = fmax(mabs, fabs(__ldcg(static_cast<const double *>(p.dist) + (ll)cur * K + k)));
-                        }
-                        cur = (int)(pe >> 32);
-                        if (cur >= 0 && cur < minv) minv = cur;
-                        i++;
-                    } while (cur != x && cur >= 0 && i <= p.n);
-                    ok = (cur == x);
-                    if (!ok) { sc = 0.0; stt = 0.0; isc = 0; ist = 0; }
+                s_x = x;
+                s_len = x >= 0 ? (int)len : 0;
+            }
+            __syncthreads();
+            const int x = s_x, len = s_len;
+            if (x >= 0) {   // block-uniform
+                // sums, smallest vertex and max |dist| of the recorded lap, by the whole block
+                double sc = 0.0, stt = 0.0, mabs = 0.0;
+                ll isc = 0, ist = 0;
+                int minv = 0x7fffffff;
+                __threadfence_block();
+                for (int i = threadIdx.x; i < len; i += blockDim.x) {
+                    const int e = __ldcg(p.cyc_edges + (ll)k * p.cap + i);
+                    const int u = __ldg(p.src + e);
+                    minv = u < minv ? u : minv;
+                    if (p.exact) { isc += __ldg(p.icost + e); ist += __ldg(p.itime + e); }
+                    else {
+                        double ce = __ldg(p.cost + e), te = __ldg(p.time + e);
+                        if (p.scen && e == p.pe[k]) { ce = __dadd_rn(ce, p.pdc[k]); te = __dadd_rn(te, p.pdt[k]); }
+                        sc += ce; stt += te;
+                        mabs = fmax(mabs, fabs(__ldcg(static_cast<const double *>(p.dist) + (ll)u * K + k)));
+                    }
+                }
+                for (int o = 16; o; o >>= 1) {
+                    sc += __shfl_down_sync(0xffffffffu, sc, o); stt += __shfl_down_sync(0xffffffffu, stt, o);
+                    mabs = fmax(mabs, __shfl_down_sync(0xffffffffu, mabs, o));
+                    isc += __shfl_down_sync(0xffffffffu, isc, o); ist += __shfl_down_sync(0xffffffffu, ist, o);
+                    const int mo = __shfl_down_sync(0xffffffffu, minv, o);
+                    minv = mo < minv ? mo : minv;
+                }
+                const int w = threadIdx.x >> 5;
+                if ((threadIdx.x & 31) == 0) { s_d[0][w] = sc; s_d[1][w] = stt; s_d[2][w] = mabs; s_l[0][w] = isc; s_l[1][w] = ist; s_m[w] = minv; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    sc = 0.0; stt = 0.0; mabs = 0.0; isc = 0; ist = 0; minv = 0x7fffffff;
+                    for (int j = 0; j < 8; j++) {
+                        sc += s_d[0][j]; stt += s_d[1][j]; mabs = fmax(mabs, s_d[2][j]);
+                        isc += s_l[0][j]; ist += s_l[1][j]; minv = s_m[j] < minv ? s_m[j] : minv;
+                    }
+                }
+                if (threadIdx.x == 0) {
+                    bool settled = true;   // nothing left to examine for k unless a false cycle is cut below
                     int kind = 0;
                     if (p.exact) {
                         if ((__int128)p.b[k] * isc - (__int128)p.a[k] * ist < 0) kind = MRC_CYC_NEG;
@@ -796,16 +860,16 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                         // walk (len * eps * max|dist|, x8): a rounding artefact that would relax forever -> TIE.
                         const double rr = sc / stt;
                         if (rr < p.lam[k]) kind = MRC_CYC_NEG;
-                        else if ((rr - p.lam[k]) * stt <= 8.0 * (double)i * 2.220446049250313e-16 * mabs) kind = MRC_CYC_TIE;
+                        else if ((rr - p.lam[k]) * stt <= 8.0 * (double)len * 2.220446049250313e-16 * mabs) kind = MRC_CYC_TIE;
                     }
                     if (kind) {
                         CycleOut o;
-                        o.found = kind; o.len = (int)i; o.minv = minv; o.pad = x;   // pad = vertex the recorded walk starts from
+                        o.found = kind; o.len = len; o.minv = minv; o.pad = x;   // pad = vertex the recorded walk starts from
                         o.sumc = sc; o.sumt = stt; o.maxabs = mabs; o.isumc = isc; o.isumt = ist;
                         st->out[k] = o;
                     } else {
                         // false cycle: mark its vertices dead for this launch and cut it for good
-                        cur = minv;
+                        int cur = minv;
                         ll g = 0;
                         do {
                             const int nxt = step(cur);
@@ -817,11 +881,12 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                         atomicAdd(&st->cuts, 1u);
                         settled = false;
                     }
-                } else {
-                    // the chain left the cycle while we walked (cannot happen between launches); give up on k
+                    if (settled) atomicAnd(&st->pend, ~(1u << k));
                 }
+            } else if (threadIdx.x == 0) {
+                // no representative left, or the chain broke while we walked (cannot happen between launches)
+                atomicAnd(&st->pend, ~(1u << k));
             }
-            if (settled) atomicAnd(&st->pend, ~(1u << k));
         }
         grid.sync();
         pending = __ldcg(&st->pend);
