@@ -170,8 +170,8 @@ __device__ __forceinline__ bool mrc_atomic_lower(double *addr, double cand) {
 }
 __device__ __forceinline__ bool mrc_atomic_lower(ll *addr, ll cand) { return cand < atomicMin(addr, cand); }
 
-// Crowded row (first passes: many lanes improve): segmented min over the runs of equal destination in
-// 2 x 5 shuffle steps; the lowest lane holding the run minimum keeps `imp`.
+// Crowded row (first passes: many lanes improve): segmented min over the runs of equal destination (prefix-min
+// inside the run, read back from the run's last lane); the lowest lane holding the run minimum keeps `imp`.
 template <typename T>
 __device__ __forceinline__ bool mrc_resolve_crowded(bool imp, T cand, int v, int lane) {
     const int vprev = __shfl_up_sync(0xffffffffu, v, 1);
@@ -179,16 +179,14 @@ __device__ __forceinline__ bool mrc_resolve_crowded(bool imp, T cand, int v, int
     const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
     const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
     const int end = above ? (__ffs(above) - 2) : 31;
-    const T ident = mrc_identity(T(0));
-    T lo_ = imp ? cand : ident, hi_ = lo_;
+    // inclusive prefix-min inside the run (5 shuffle steps); the run's last lane then holds the run minimum
+    T x = imp ? cand : mrc_identity(T(0));
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        const T a = __shfl_up_sync(0xffffffffu, lo_, off);
-        const T b = __shfl_down_sync(0xffffffffu, hi_, off);
-        if (lane - off >= start && a < lo_) lo_ = a;
-        if (lane + off <= end && b < hi_) hi_ = b;
+        const T a = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane - off >= start && a < x) x = a;
     }
-    const T runmin = lo_ < hi_ ? lo_ : hi_;
+    const T runmin = __shfl_sync(0xffffffffu, x, end);
     const unsigned eq = __ballot_sync(0xffffffffu, imp && cand == runmin);
     const unsigned runmask = ((end == 31) ? 0xffffffffu : ((2u << end) - 1u)) & ~((1u << start) - 1u);
     return imp && (__ffs(eq & runmask) - 1 == lane);
