@@ -83,7 +83,7 @@ struct mrc_graph {
     int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
     int patience = 0;            // option "patience": mrc_solve_numeric passes MRC_F_PATIENCE to its probes
     int narrow = 1;              // option "narrow": late passes run the narrowest kernel covering the undecided candidates
-    bool alternate = true;
+    bool alternate = false;      // option "alternate": flip the sweep direction every pass (measured: more passes, same time per pass)
     mrc_stats stats;
 };
 
