@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MRC_ABI_VERSION 1
+#define MRC_ABI_VERSION 2   /* 2: mrc_stats grew (sparse_passes, sparse_ms) */
 #define MRC_KMAX 8 /* candidate lambdas evaluated by one relaxation launch */
 
 /* status codes */
@@ -64,7 +64,7 @@ extern "C" {
 typedef struct mrc_graph mrc_graph;
 
 typedef struct mrc_stats {
-    int64_t relax_launches;       /* relaxation kernel launches */
+    int64_t relax_launches;       /* dense relaxation launches that did work */
     int64_t relax_edge_visits;    /* edge relaxations actually evaluated (dense launch: m per candidate; frontier launch: edges with an active source) */
     int64_t check_launches;       /* predecessor-graph cycle checks */
     int64_t probes;               /* candidate lambdas evaluated */
@@ -76,6 +76,8 @@ typedef struct mrc_stats {
     int64_t d2h_bytes;
     int64_t false_cycles_cut;     /* predecessor-graph cycles that did not verify negative and were cut */
     int64_t relax_edge_slots;     /* sum over launches of m * (active candidates), whether or not an edge was skipped */
+    int64_t sparse_passes;        /* worklist passes (relax_sparse_kernel: only out-edges of the vertices the previous pass lowered) */
+    double sparse_ms;             /* CUDA-event time spent in them (not part of relax_ms) */
 } mrc_stats;
 
 int mrc_abi_version(void);
@@ -157,7 +159,10 @@ int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *m
  * "narrow" (0/1, default 1: once some of the K candidates of a probe are decided, the remaining passes run the
  * narrowest kernel -- 1, 2 or 4 candidates wide -- that covers the undecided slots of the dist/pred layout),
  * "gate" (0/1, default 1: a relaxation launch returns at once when the previous launch of its burst moved none of
- * its candidates, so bursts can be long without wasting passes after convergence), "prune_above" (0/1, default 1:
+ * its candidates, so bursts can be long without wasting passes after convergence), "sparse" (0/1, default 1:
+ * once fewer than n / "sparse_div" (default 32) vertices were lowered by the last pass of a burst, the next bursts
+ * run as worklist passes over the out-edges of just those vertices -- same fixed point, same verdicts),
+ * "prune_above" (0/1, default 1:
  * with MRC_F_MONOTONE_PRUNE and candidates in increasing order a cycle check stops working on the candidates
  * above the lowest one whose predecessor graph holds a cycle), "patience" (0/1:
  * mrc_solve_numeric passes MRC_F_PATIENCE to its probes).

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "mrc_kernels.cuh"
+#define MRC_SPARSE_MIN_EDGES 65536   /* below this a dense sweep is launch-bound anyway */
 #include "mrc_search.h"
 #include "mrc_batch.cuh"
 #include "mrc_host.h"
@@ -79,6 +80,14 @@ struct mrc_graph {
     int use_tma[4] = {0, 0, 0, 0};   // per KT index: stream the edges through the TMA-staged kernel (option "tma")
     int check_blocks[4] = {0, 0, 0, 0};
     int burst_init = 2, burst_max = 16;
+    // sparse (worklist) passes: out-edge index by source, worklists + membership bitmaps, built on first use
+    int sparse = 1;              // option "sparse": bursts run as worklist passes once few vertices are still lowered
+    int sparse_div = 32;         // option "sparse_div": ... i.e. fewer than n / sparse_div
+    bool sparse_ready = false;
+    int *d_out_off = nullptr, *d_out_edge = nullptr, *d_wl[2] = {nullptr, nullptr};
+    unsigned *d_bm[2] = {nullptr, nullptr};
+    size_t bm_bytes = 0;
+    int sparse_blocks[2] = {0, 0};
     int prune_above = 1;         // option "prune_above": cycle checks stop examining candidates above the lowest one with a cycle
     int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
     int patience = 0;            // option "patience": mrc_solve_numeric passes MRC_F_PATIENCE to its probes
@@ -166,7 +175,8 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
     if (g->stream) {
         void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
                         g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
-                        g->d_keys, g->d_verr, g->d_act[0], g->d_act[1]};
+                        g->d_keys, g->d_verr, g->d_act[0], g->d_act[1], g->d_out_off, g->d_out_edge,
+                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1]};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
         cudaStreamSynchronize(g->stream);
     }
@@ -384,22 +394,31 @@ static void narrow_candidates(int KT, unsigned active, int *kc, int *k0) {
         for (int o = 0; o < KT; o += w)
             if (active && !(active & ~(((1u << w) - 1u) << o))) { *kc = w; *k0 = o; return; }
 }
+// `ra` := ra_full restricted to the narrowest aligned candidate sub-range; returns its width
+static int narrow_args(const mrc_graph *g, int KT, const RelaxArgs &ra_full, RelaxArgs &ra) {
+    ra = ra_full;
+    ra.ks = KT; ra.k0 = 0;
+    int kc = KT, k0 = 0;
+    if (g->narrow) narrow_candidates(KT, ra.active, &kc, &k0);
+    if (kc < KT) {
+        const size_t esz = 8;   // double and int64 slots alike
+        ra.dist = (char *)ra.dist + (size_t)k0 * esz;
+        ra.pred += k0;
+        ra.active >>= k0;
+        ra.k0 = k0;
+        for (int j = 0; j < kc; j++) {
+            ra.lam[j] = ra_full.lam[k0 + j]; ra.a[j] = ra_full.a[k0 + j]; ra.b[j] = ra_full.b[k0 + j];
+            ra.pe[j] = ra_full.pe[k0 + j]; ra.pdc[j] = ra_full.pdc[k0 + j]; ra.pdt[j] = ra_full.pdt[k0 + j];
+        }
+    }
+    return kc;
+}
 static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_full, bool frontier_pass = false) {
     RelaxArgs ra = ra_full;
     ra.ks = KT; ra.k0 = 0;
-    if (g->narrow && !frontier_pass && !g->use_tma[kt_index(KT)]) {
-        int kc, k0;
-        narrow_candidates(KT, ra.active, &kc, &k0);
+    if (!frontier_pass && !g->use_tma[kt_index(KT)]) {
+        const int kc = narrow_args(g, KT, ra_full, ra);
         if (kc < KT) {
-            const size_t esz = 8;   // double and int64 slots alike
-            ra.dist = (char *)ra.dist + (size_t)k0 * esz;
-            ra.pred += k0;
-            ra.active >>= k0;
-            ra.k0 = k0;
-            for (int j = 0; j < kc; j++) {
-                ra.lam[j] = ra_full.lam[k0 + j]; ra.a[j] = ra_full.a[k0 + j]; ra.b[j] = ra_full.b[k0 + j];
-                ra.pe[j] = ra_full.pe[k0 + j]; ra.pdc[j] = ra_full.pdc[k0 + j]; ra.pdt[j] = ra_full.pdt[k0 + j];
-            }
             void *nargs[] = {(void *)&ra};
             const int blocks = g->relax_blocks[kt_index(kc)][exact ? 1 : 0];
             CUDA_TRY(cudaLaunchKernel(relax_fn_of(kc, exact), dim3(blocks), dim3(MRC_RELAX_THREADS), nargs, 0, g->stream));
@@ -430,6 +449,40 @@ static int launch_check(mrc_graph *g, int KT, const CheckArgs &ca) {
     const int blocks = g->check_blocks[kt_index(KT)];
     void *args[] = {(void *)&ca};
     CUDA_TRY(cudaLaunchCooperativeKernel(check_fn_of(KT), dim3(blocks), dim3(256), args, 0, g->stream));
+    return MRC_OK;
+}
+
+// Out-edge index, worklists and bitmaps of the sparse passes (built once per graph, on first use).
+static int ensure_sparse(mrc_graph *g) {
+    if (g->sparse_ready) return MRC_OK;
+    MRC_TRY(mrc_build_out_csr(g->stream, g->n, g->m, g->d_src, &g->d_out_off, &g->d_out_edge));
+    g->bm_bytes = (size_t)((g->n + 31) / 32) * 4;
+    for (int i = 0; i < 2; i++) {
+        DALLOC(g->d_bm[i], g->bm_bytes);
+        DALLOC(g->d_wl[i], (size_t)g->n * 4);
+        CUDA_TRY(cudaMemsetAsync(g->d_bm[i], 0, g->bm_bytes, g->stream));
+    }
+    for (int ex = 0; ex < 2; ex++) {
+        int occ = 0;
+        const void *fn = ex ? (const void *)relax_sparse_kernel<true> : (const void *)relax_sparse_kernel<false>;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, 0));
+        if (occ < 1) return set_err(MRC_ERR_CUDA, "sparse relaxation kernel does not fit on an SM");
+        g->sparse_blocks[ex] = std::min(occ, 2) * g->sms;
+    }
+    g->stats.other_launches += 3;
+    g->sparse_ready = true;
+    return MRC_OK;
+}
+static int launch_sparse(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_full, int first, int cidx, int npasses) {
+    SparseArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.kc = narrow_args(g, KT, ra_full, sa.r);
+    sa.out_off = g->d_out_off; sa.out_edge = g->d_out_edge;
+    sa.bm[0] = g->d_bm[0]; sa.bm[1] = g->d_bm[1]; sa.wl[0] = g->d_wl[0]; sa.wl[1] = g->d_wl[1];
+    sa.st = g->d_status; sa.first = first; sa.cidx = cidx; sa.npasses = npasses;
+    void *args[] = {(void *)&sa};
+    const void *fn = exact ? (const void *)relax_sparse_kernel<true> : (const void *)relax_sparse_kernel<false>;
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(g->sparse_blocks[exact ? 1 : 0]), dim3(256), args, 0, g->stream));
     return MRC_OK;
 }
 
@@ -498,6 +551,11 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     g->stats.probes += K;
     bool any_neg = false;            // MRC_F_PATIENCE bookkeeping
     int new_verdicts = 0;
+    // sparse passes (see relax_sparse_kernel): decided burst by burst from the number of vertices the last pass lowered
+    const bool use_sparse = g->sparse && !g->frontier && m >= MRC_SPARSE_MIN_EDGES && !g->use_tma[kt_index(KT)];
+    if (use_sparse) MRC_TRY(ensure_sparse(g));
+    bool sparse_mode = false, bm1_dirty = false;
+    int sp_in = 0, sp_ci = 0;
     while (active) {
         const int nb = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
         if (nb <= 0) {
@@ -509,10 +567,18 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
         ra.active = active;
         int dense_launches = 0;
-        for (int i = 0; i < nb; i++) {
+        const bool sparse_burst = sparse_mode;
+        if (sparse_burst) {
+            // one cooperative launch runs the nb worklist passes of this burst
+            ra.changed = &g->d_status->changed[0];
+            ra.act_out = nullptr; ra.gate = nullptr; ra.reverse = 0;
+            MRC_TRY(launch_sparse(g, KT, exact, ra, sp_in, sp_ci, nb));
+        }
+        for (int i = 0; i < nb && !sparse_burst; i++) {
             ra.changed = &g->d_status->changed[i];
             ra.reverse = g->alternate ? (int)((passes + i) & 1) : 0;
             bool fpass = false;
+            ra.act_out = nullptr;
             if (g->frontier) {
                 // bitmap written by launch p is read by launch p+1; launches before frontier_from sweep densely
                 const ll pidx = passes + i;
@@ -520,11 +586,23 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
                 ra.act_in = g->d_act[(pidx + 1) & 1];
                 CUDA_TRY(cudaMemsetAsync(ra.act_out, 0, g->act_bytes, g->stream));
                 fpass = pidx + 1 >= g->frontier_from;
+            } else if (use_sparse && i == nb - 1) {
+                // the last dense launch of a burst records which vertices it lowered: the seed of a worklist
+                CUDA_TRY(cudaMemsetAsync(g->d_bm[0], 0, g->bm_bytes, g->stream));
+                ra.act_out = g->d_bm[0];
             }
             if (!fpass) dense_launches++;
             // launch i > 0 returns at once if launch i-1 moved none of the candidates still open
             ra.gate = (i > 0 && !g->frontier && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
             MRC_TRY(launch_relax(g, KT, exact, ra, fpass));
+        }
+        if (use_sparse && !sparse_burst) {
+            if (bm1_dirty) { CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0, g->bm_bytes, g->stream)); bm1_dirty = false; }
+            CUDA_TRY(cudaMemsetAsync(&g->d_status->act_count, 0, 4 * sizeof(unsigned), g->stream));   // act_count + act_cnt[3]
+            compact_active_kernel<<<std::min<int>((int)((g->bm_bytes / 4 + 255) / 256), 4 * g->sms), 256, 0, g->stream>>>(
+                g->d_bm[0], (int)(g->bm_bytes / 4), g->d_wl[0], g->d_status, 0);
+            publish_active_count_kernel<<<1, 1, 0, g->stream>>>(g->d_status, 0);
+            CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
         const bool do_check = passes + nb >= next_check || passes + nb >= max_passes;
@@ -538,16 +616,26 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         CUDA_TRY(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, g->stream));
         CUDA_TRY(cudaStreamSynchronize(g->stream));
         float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->stats.relax_ms += ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]));
+        if (sparse_burst) g->stats.sparse_ms += ms; else g->stats.relax_ms += ms;
         CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
         const DevStatus &hs = *g->h_status;
-        // launches that did work: the first of the burst, and each one whose predecessor still moved something
+        // launches / passes that did work: the first of the burst, and each one whose predecessor still moved something
         int ran = nb;
-        if (!g->frontier && g->gate)
+        if (!g->frontier && (g->gate || sparse_burst))
             for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
-        if (!g->frontier) dense_launches = ran;
-        g->stats.relax_launches += ran;
-        g->stats.other_launches += nb - ran;
+        if (sparse_burst) {
+            dense_launches = 0;
+            g->stats.sparse_passes += ran;
+            g->stats.other_launches += 1;
+            sp_in ^= nb & 1; sp_ci = (sp_ci + nb) % 3;
+            if ((ll)hs.act_count * g->sparse_div > 2 * n) { sparse_mode = false; bm1_dirty = true; }   // the frontier grew back: sweep densely again
+        } else {
+            if (!g->frontier) dense_launches = ran;
+            g->stats.relax_launches += ran;
+            g->stats.other_launches += nb - ran + (use_sparse ? 2 : 0);
+            if (use_sparse && (ll)hs.act_count * g->sparse_div < n) { sparse_mode = true; sp_in = 0; sp_ci = 0; }
+        }
         g->stats.relax_edge_visits += ((int64_t)dense_launches * m + (int64_t)g->h_status->examined) * __builtin_popcount(active);
         g->stats.relax_edge_slots += (int64_t)ran * m * __builtin_popcount(active);
         if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += g->h_status->cuts; }
@@ -806,6 +894,8 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "frontier_from") g->frontier_from = std::max(1, value);
     else if (s == "narrow") g->narrow = value != 0;
     else if (s == "gate") g->gate = value != 0;
+    else if (s == "sparse") g->sparse = value != 0;
+    else if (s == "sparse_div") g->sparse_div = std::max(1, value);
     else if (s == "prune_above") g->prune_above = value != 0;
     else if (s == "patience") g->patience = value != 0;
     else if (s == "burst_init") g->burst_init = std::max(1, std::min(value, MRC_MAX_BURST));

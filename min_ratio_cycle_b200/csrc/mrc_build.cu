@@ -78,3 +78,35 @@ extern "C" int mrc_sort_edges_by_dst(int64_t n, int64_t m, const int32_t *src, c
     cudaStreamDestroy(st);
     return rc;
 }
+
+/*
+ * Out-edge index of a device-resident graph (for the sparse relaxation passes): out_edge[out_off[u] .. out_off[u+1])
+ * are the indices (into the destination-sorted arrays) of the edges leaving u, in increasing edge index.  One stable
+ * radix sort of (src, edge index) pairs + n+1 binary searches.  The two result arrays are allocated here
+ * (stream-ordered) and owned by the caller.
+ */
+int mrc_build_out_csr(cudaStream_t st, int64_t n, int64_t m, const int32_t *d_src, int32_t **d_off_out, int32_t **d_edge_out) {
+    int *d_idx = nullptr, *d_keys = nullptr, *d_off = nullptr, *d_edge = nullptr;
+    void *d_tmp = nullptr;
+    int rc = [&]() -> int {
+        const size_t M = (size_t)m;
+        CUDA_TRY(cudaMallocAsync((void **)&d_idx, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_keys, M * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_edge, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_off, ((size_t)n + 1) * 4, st));
+        const int blocks = (int)std::min<ll>((m + 255) / 256, 148 * 16);
+        build_iota_kernel<<<blocks, 256, 0, st>>>(d_idx, m);
+        int bits = 1;
+        while (((ll)1 << bits) < n) bits++;
+        size_t tmp_bytes = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_src, d_keys, d_idx, d_edge, (int)m, 0, bits, st));
+        CUDA_TRY(cudaMallocAsync(&d_tmp, tmp_bytes, st));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_src, d_keys, d_idx, d_edge, (int)m, 0, bits, st));
+        build_out_offsets_kernel<<<(int)std::min<ll>((n + 256) / 256, 148 * 16), 256, 0, st>>>(d_keys, m, n, d_off);
+        CUDA_TRY(cudaGetLastError());
+        return MRC_OK;
+    }();
+    void *ptrs[] = {d_idx, d_keys, d_tmp};
+    for (void *q : ptrs) if (q) cudaFreeAsync(q, st);
+    if (rc) { if (d_off) cudaFreeAsync(d_off, st); if (d_edge) cudaFreeAsync(d_edge, st); return rc; }
+    *d_off_out = d_off; *d_edge_out = d_edge;
+    return MRC_OK;
+}

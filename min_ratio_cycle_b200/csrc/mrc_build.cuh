@@ -31,3 +31,15 @@ __global__ void build_count_dups_kernel(const ull *keys, ll m, ull *count) {
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (ull)c);
 }
+
+// out_off[v] = first position in the src-sorted edge list whose source is >= v (lower bound), v in [0, n]
+__global__ void build_out_offsets_kernel(const int *sorted_src, ll m, ll n, int *out_off) {
+    for (ll v = (ll)blockIdx.x * blockDim.x + threadIdx.x; v <= n; v += (ll)gridDim.x * blockDim.x) {
+        ll lo = 0, hi = m;
+        while (lo < hi) {
+            const ll mid = (lo + hi) >> 1;
+            if (sorted_src[mid] < (int)v) lo = mid + 1; else hi = mid;
+        }
+        out_off[v] = (int)lo;
+    }
+}

@@ -33,3 +33,6 @@ static inline int set_err(int code, const char *fmt, ...) {
         int rc_ = (x);        \
         if (rc_) return rc_;  \
     } while (0)
+
+// mrc_build.cu: out-edge (by source) index of a device-resident destination-sorted graph
+int mrc_build_out_csr(cudaStream_t st, int64_t n, int64_t m, const int32_t *d_src, int32_t **d_off_out, int32_t **d_edge_out);

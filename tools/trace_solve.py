@@ -40,7 +40,7 @@ def trace(g, K, tol=1e-12, flags=1):
         desc = " ".join(f"[{l:.6g} {VN[v]} p{r['passes']}{' len%d r=%.9g' % (r['cycle_len'] - 1, c) if v in (1, 3) else ''}]"
                         for l, v, r, c in zip(lam, vd, res, cr))
         if not QUIET: print(f"  round {rnd}: wall {dt*1e3:.2f} ms relax {st['relax_launches']}L {st['relax_ms']:.2f} ms  "
-              f"check {st['check_launches']}L {st['check_ms']:.2f} ms | {desc} -> lo={lo:.9g} hi={hi:.12g}", flush=True)
+              f"sparse {st['sparse_passes']}P {st['sparse_ms']:.2f} ms  check {st['check_launches']}L {st['check_ms']:.2f} ms | {desc} -> lo={lo:.9g} hi={hi:.12g}", flush=True)
         if hi - lo <= tol:
             break
     print(f"  total wall {tot*1e3:.2f} ms, rounds {rnd+1}, ratio {hi!r}", flush=True)
@@ -51,7 +51,7 @@ def main():
     for seed in [int(s) for s in os.environ.get("MRC_SEEDS", "0").split(",")]:
         n, U, V, C, T = load(n, m, seed)
         g = N.DeviceGraph(n, U, V, C, T)
-        for opt in ("burst_init", "frontier", "frontier_from", "stop_on_neg", "narrow", "gate", "patience", "burst_max", "prune_above", "alternate"):
+        for opt in ("burst_init", "frontier", "frontier_from", "stop_on_neg", "narrow", "gate", "patience", "burst_max", "prune_above", "alternate", "sparse", "sparse_div"):
             if os.environ.get("MRC_" + opt.upper()): g.set_option(opt, int(os.environ["MRC_" + opt.upper()]))
         for K in [int(k) for k in os.environ.get("MRC_KS", "4,1").split(",")]:
             for rep in range(2):
@@ -64,7 +64,7 @@ def main():
             dt = time.perf_counter() - t0
             st = g.stats()
             print(f"seed {seed} K={K} mrc_solve_numeric: {dt*1e3:.2f} ms rounds={out['iterations']} relax {st['relax_launches']}L "
-                  f"{st['relax_ms']:.2f} ms check {st['check_launches']}L {st['check_ms']:.2f} ms ratio={out['ratio']!r}", flush=True)
+                  f"{st['relax_ms']:.2f} ms sparse {st['sparse_passes']}P {st['sparse_ms']:.2f} ms check {st['check_launches']}L {st['check_ms']:.2f} ms ratio={out['ratio']!r}", flush=True)
 
 
 main()
