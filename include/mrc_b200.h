@@ -159,8 +159,8 @@ int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *m
  * "narrow" (0/1, default 1: once some of the K candidates of a probe are decided, the remaining passes run the
  * narrowest kernel -- 1, 2 or 4 candidates wide -- that covers the undecided slots of the dist/pred layout),
  * "gate" (0/1, default 1: a relaxation launch returns at once when the previous launch of its burst moved none of
- * its candidates, so bursts can be long without wasting passes after convergence), "sparse" (0/1, default 1:
- * once fewer than n / "sparse_div" (default 32) vertices were lowered by the last pass of a burst, the next bursts
+ * its candidates, so bursts can be long without wasting passes after convergence), "sparse" (0/1, default 0 or
+ * the environment variable MRC_B200_SPARSE; the Python facade switches it on: once fewer than n / "sparse_div" (default 32) vertices were lowered by the last pass of a burst, the next bursts
  * run as worklist passes over the out-edges of just those vertices -- same fixed point, same verdicts),
  * "prune_above" (0/1, default 1:
  * with MRC_F_MONOTONE_PRUNE and candidates in increasing order a cycle check stops working on the candidates

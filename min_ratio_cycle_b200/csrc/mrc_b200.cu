@@ -81,7 +81,7 @@ struct mrc_graph {
     int check_blocks[4] = {0, 0, 0, 0};
     int burst_init = 2, burst_max = 16;
     // sparse (worklist) passes: out-edge index by source, worklists + membership bitmaps, built on first use
-    int sparse = 1;              // option "sparse": bursts run as worklist passes once few vertices are still lowered
+    int sparse = 0;              // option "sparse" (env MRC_B200_SPARSE): bursts run as worklist passes once few vertices are still lowered
     int sparse_div = 32;         // option "sparse_div": ... i.e. fewer than n / sparse_div
     bool sparse_ready = false;
     int *d_out_off = nullptr, *d_out_edge = nullptr, *d_wl[2] = {nullptr, nullptr};
@@ -279,6 +279,7 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         }
         g->act_bytes = (((size_t)n + 31) / 32 * 4 + 15) & ~(size_t)15;
         DALLOC(g->d_act[0], g->act_bytes); DALLOC(g->d_act[1], g->act_bytes);
+        if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
         if (const char *env = getenv("MRC_B200_FRONTIER"))   // A/B switch for experiments and the parity suite
             g->frontier = atoi(env) != 0 && g->act_bytes + 2048 <= 227 * 1024;
         // input validation on the device (the host never touches the 24 B/edge again)

@@ -75,6 +75,8 @@ class SolverConfig:
     gpu_candidates: int = 4            # lambdas evaluated per relaxation launch (1..8)
     gpu_exact_strategy: int = 1        # 0: every Stern-Brocot step probes the GPU; 1: Newton + replay
     gpu_frontier: bool = False         # skip edges whose source was not lowered by the previous pass (same results)
+    gpu_sparse: bool = True            # late passes walk only the out-edges of the vertices still being lowered
+                                       # (worklist + out-edge index; same fixed point and verdicts, shorter solves)
     honor_mode: bool = False           # True: solve(mode="exact") really runs _solve_exact (reference ignores mode)
 
 
@@ -359,6 +361,7 @@ class MinRatioCycleSolver:
                                   device=self.config.gpu_device)
         if self.config.gpu_frontier and self.n <= 1_700_000:
             self._dev.set_option("frontier", 1)
+        self._dev.set_option("sparse", 1 if self.config.gpu_sparse else 0)
         self._arrays_built = True
         if self._metrics:
             self._metrics.preprocessing_time = _time.time() - t0
