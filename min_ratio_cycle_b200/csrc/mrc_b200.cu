@@ -88,6 +88,7 @@ struct mrc_graph {
     unsigned *d_bm[2] = {nullptr, nullptr};
     size_t bm_bytes = 0;
     int sparse_blocks[2] = {0, 0};
+    int sparse_bps = 2;          // CTAs per SM of the cooperative sparse kernel (env MRC_B200_SPARSE_BPS, experiments)
     int prune_above = 1;         // option "prune_above": cycle checks stop examining candidates above the lowest one with a cycle
     int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
     int patience = 0;            // option "patience": mrc_solve_numeric passes MRC_F_PATIENCE to its probes
@@ -280,6 +281,8 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         g->act_bytes = (((size_t)n + 31) / 32 * 4 + 15) & ~(size_t)15;
         DALLOC(g->d_act[0], g->act_bytes); DALLOC(g->d_act[1], g->act_bytes);
         if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
+        if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
+        if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_FRONTIER"))   // A/B switch for experiments and the parity suite
             g->frontier = atoi(env) != 0 && g->act_bytes + 2048 <= 227 * 1024;
         // input validation on the device (the host never touches the 24 B/edge again)
@@ -468,7 +471,7 @@ static int ensure_sparse(mrc_graph *g) {
         const void *fn = ex ? (const void *)relax_sparse_kernel<true> : (const void *)relax_sparse_kernel<false>;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, 0));
         if (occ < 1) return set_err(MRC_ERR_CUDA, "sparse relaxation kernel does not fit on an SM");
-        g->sparse_blocks[ex] = std::min(occ, 2) * g->sms;
+        g->sparse_blocks[ex] = std::min(occ, g->sparse_bps) * g->sms;
     }
     g->stats.other_launches += 3;
     g->sparse_ready = true;
