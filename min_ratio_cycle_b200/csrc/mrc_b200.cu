@@ -88,6 +88,7 @@ struct mrc_graph {
     unsigned *d_bm[2] = {nullptr, nullptr};
     size_t bm_bytes = 0;
     int sparse_blocks[2] = {0, 0};
+    int sparse_look = 2;         // option "sparse_look": dense bursts are at most this long while the sparse passes wait to take over
     int sparse_bps = 2;          // CTAs per SM of the cooperative sparse kernel (env MRC_B200_SPARSE_BPS, experiments)
     int prune_above = 1;         // option "prune_above": cycle checks stop examining candidates above the lowest one with a cycle
     int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
@@ -558,10 +559,13 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     // sparse passes (see relax_sparse_kernel): decided burst by burst from the number of vertices the last pass lowered
     const bool use_sparse = g->sparse && !g->frontier && m >= MRC_SPARSE_MIN_EDGES && !g->use_tma[kt_index(KT)];
     if (use_sparse) MRC_TRY(ensure_sparse(g));
-    bool sparse_mode = false, bm1_dirty = false;
+    bool sparse_mode = false;
     int sp_in = 0, sp_ci = 0;
     while (active) {
-        const int nb = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
+        int nb = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
+        // while sweeping densely with the sparse passes available, look at the active count every few sweeps:
+        // a worklist pass is 5-10x cheaper than a sweep as soon as it applies
+        if (use_sparse && !sparse_mode && nb > g->sparse_look) nb = g->sparse_look;
         if (nb <= 0) {
             for (int k = 0; k < K; k++)
                 if ((active >> k) & 1u) { res[k].verdict = MRC_V_NEG_NOCYCLE; res[k].passes = passes; }
@@ -601,7 +605,9 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
             MRC_TRY(launch_relax(g, KT, exact, ra, fpass));
         }
         if (use_sparse && !sparse_burst) {
-            if (bm1_dirty) { CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0, g->bm_bytes, g->stream)); bm1_dirty = false; }
+            // bm[1] may hold the membership bits of a worklist nobody consumed (a probe that ended on a verified cycle,
+            // or a switch back to dense sweeps): the next worklist pass deduplicates through it, so it must be clean
+            CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0, g->bm_bytes, g->stream));
             CUDA_TRY(cudaMemsetAsync(&g->d_status->act_count, 0, 4 * sizeof(unsigned), g->stream));   // act_count + act_cnt[3]
             compact_active_kernel<<<std::min<int>((int)((g->bm_bytes / 4 + 255) / 256), 4 * g->sms), 256, 0, g->stream>>>(
                 g->d_bm[0], (int)(g->bm_bytes / 4), g->d_wl[0], g->d_status, 0);
@@ -633,7 +639,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
             g->stats.sparse_passes += ran;
             g->stats.other_launches += 1;
             sp_in ^= nb & 1; sp_ci = (sp_ci + nb) % 3;
-            if ((ll)hs.act_count * g->sparse_div > 2 * n) { sparse_mode = false; bm1_dirty = true; }   // the frontier grew back: sweep densely again
+            if ((ll)hs.act_count * g->sparse_div > 2 * n) sparse_mode = false;   // the frontier grew back: sweep densely again
         } else {
             if (!g->frontier) dense_launches = ran;
             g->stats.relax_launches += ran;
@@ -900,6 +906,13 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "gate") g->gate = value != 0;
     else if (s == "sparse") g->sparse = value != 0;
     else if (s == "sparse_div") g->sparse_div = std::max(1, value);
+    else if (s == "sparse_look") g->sparse_look = std::max(1, value);
+    else if (s == "sparse_poison") {   // test hook: garbage in both membership bitmaps, as an interrupted probe may leave it
+        CUDA_TRY(cudaSetDevice(g->device));
+        MRC_TRY(ensure_sparse(g));
+        CUDA_TRY(cudaMemsetAsync(g->d_bm[0], 0xff, g->bm_bytes, g->stream));
+        CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0xff, g->bm_bytes, g->stream));
+    }
     else if (s == "prune_above") g->prune_above = value != 0;
     else if (s == "patience") g->patience = value != 0;
     else if (s == "burst_init") g->burst_init = std::max(1, std::min(value, MRC_MAX_BURST));

@@ -124,3 +124,55 @@ def test_long_tail_and_ring_through_sparse_passes():
         assert r[sparse]["rc"] == 0
         g.close()
     assert abs(r[0]["ratio"] - r[1]["ratio"]) <= 1e-9 * max(1.0, abs(r[0]["ratio"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_back_to_back_probes_leave_no_stale_worklist_state(seed, oracle_mod):
+    """
+    A probe that ends on a verified negative cycle leaves a non-empty worklist (and its membership bits) behind; the
+    next probe must not inherit them.  Newton iteration (K=1) with the earliest possible switch to worklist passes
+    runs 6-12 such probes in a row; the last, certifying one must still reach the true fixed point.
+    """
+    from min_ratio_cycle_b200 import _native as N, synthetic
+    args = _sorted(*synthetic.random_float(50_000, 500_000, seed=seed))
+    g = _graph(N, args, 0)
+    lo, hi = g.bounds()
+    want = g.solve_numeric(lo, hi, K=1)["ratio"]
+    g.close()
+    for look in (1, 2):
+        g = _graph(N, args, 1, sparse_look=look, sparse_div=4)
+        for K in (1, 4, 1):
+            out = g.solve_numeric(lo, hi, K=K)
+            assert out["rc"] == 0
+            assert abs(out["ratio"] - want) <= 1e-9 * max(1.0, abs(want)), (look, K, out["ratio"], want)
+        # verdicts around the optimum, straight after a negative probe
+        for _ in range(3):
+            assert g.probe_numeric([want + 1e-3])[0]["verdict"] == N.V_NEG
+            assert g.probe_numeric([want - 1e-6])[0]["verdict"] == N.V_NONNEG
+        g.close()
+    o = oracle_mod.Oracle(*args, all_int=False)
+    o.set_quirks(False)
+    pr = o.detect_negative_cycle_numeric(want - 1e-7 * max(1.0, abs(want)), 1e-15, True)
+    assert pr.has_neg == 0
+
+
+@pytest.mark.parametrize("K", [1, 4])
+def test_membership_bitmaps_are_reset_before_use(K):
+    """Garbage in the worklist membership bitmaps (test hook "sparse_poison") must not survive into a probe."""
+    from min_ratio_cycle_b200 import _native as N, synthetic
+    args = _sorted(*synthetic.random_float(50_000, 500_000, seed=9))
+    g = _graph(N, args, 0)
+    lo, hi = g.bounds()
+    want = g.solve_numeric(lo, hi, K=4)["ratio"]
+    g.close()
+    g = _graph(N, args, 1, sparse_look=1, sparse_div=2)
+    for lam, verdict in ((want - 1e-6, N.V_NONNEG), (want + 1e-4, N.V_NEG), (want - 1e-6, N.V_NONNEG)):
+        g.set_option("sparse_poison", 1)
+        g.reset_stats()
+        p = g.probe_numeric([lam] if K == 1 else [lam - 3.0, lam - 2.0, lam - 1.0, lam])[-1]
+        assert g.stats()["sparse_passes"] > 0
+        assert p["verdict"] == verdict, (lam, p["verdict"])
+    g.set_option("sparse_poison", 1)
+    out = g.solve_numeric(lo, hi, K=K)
+    assert out["rc"] == 0 and abs(out["ratio"] - want) <= 1e-9 * max(1.0, abs(want))
+    g.close()

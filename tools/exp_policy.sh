@@ -1,5 +1,4 @@
-for bps in 1 2 4 8; do
-  echo "== sparse blocks/SM $bps"
-  MRC_B200_SPARSE_BPS=$bps MRC_SPARSE=1 MRC_SEEDS=0,1 MRC_KS=4,1 MRC_QUIET=1 python tools/trace_solve.py 2>&1 | grep "mrc_solve" | cut -c1-220
-  MRC_B200_SPARSE_BPS=$bps python tools/explore_c5.py 2>&1 | grep scenarios | cut -c1-200
+MRC_B200_SPARSE=1 timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+for rep in 1 2 3 4; do
+  MRC_SPARSE_LOOK=1 MRC_SPARSE=1 MRC_SEEDS=1,0 MRC_KS=1,4 MRC_QUIET=1 python tools/trace_solve.py 2>&1 | grep "mrc_solve\|total wall" | cut -c1-220
 done
