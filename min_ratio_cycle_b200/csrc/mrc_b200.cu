@@ -88,6 +88,7 @@ struct mrc_graph {
     unsigned *d_bm[2] = {nullptr, nullptr};
     size_t bm_bytes = 0;
     int sparse_blocks[2] = {0, 0};
+    ll sparse_min_edges = MRC_SPARSE_MIN_EDGES;   // option "sparse_min_edges": smaller graphs sweep densely (launch-bound anyway)
     int sparse_look = 2;         // option "sparse_look": dense bursts are at most this long while the sparse passes wait to take over
     int sparse_bps = 2;          // CTAs per SM of the cooperative sparse kernel (env MRC_B200_SPARSE_BPS, experiments)
     int prune_above = 1;         // option "prune_above": cycle checks stop examining candidates above the lowest one with a cycle
@@ -284,6 +285,7 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
         if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
+        if (const char *env = getenv("MRC_B200_SPARSE_MIN_EDGES")) g->sparse_min_edges = atoll(env);   // parity suite: 0
         if (const char *env = getenv("MRC_B200_FRONTIER"))   // A/B switch for experiments and the parity suite
             g->frontier = atoi(env) != 0 && g->act_bytes + 2048 <= 227 * 1024;
         // input validation on the device (the host never touches the 24 B/edge again)
@@ -557,7 +559,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     bool any_neg = false;            // MRC_F_PATIENCE bookkeeping
     int new_verdicts = 0;
     // sparse passes (see relax_sparse_kernel): decided burst by burst from the number of vertices the last pass lowered
-    const bool use_sparse = g->sparse && !g->frontier && m >= MRC_SPARSE_MIN_EDGES && !g->use_tma[kt_index(KT)];
+    const bool use_sparse = g->sparse && !g->frontier && m >= g->sparse_min_edges && !g->use_tma[kt_index(KT)];
     if (use_sparse) MRC_TRY(ensure_sparse(g));
     bool sparse_mode = false;
     int sp_in = 0, sp_ci = 0;
@@ -907,6 +909,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "sparse") g->sparse = value != 0;
     else if (s == "sparse_div") g->sparse_div = std::max(1, value);
     else if (s == "sparse_look") g->sparse_look = std::max(1, value);
+    else if (s == "sparse_min_edges") g->sparse_min_edges = std::max(0, value);
     else if (s == "sparse_poison") {   // test hook: garbage in both membership bitmaps, as an interrupted probe may leave it
         CUDA_TRY(cudaSetDevice(g->device));
         MRC_TRY(ensure_sparse(g));
