@@ -285,6 +285,7 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
         if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
+        if (const char *env = getenv("MRC_B200_SPARSE_LOOK")) g->sparse_look = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_MIN_EDGES")) g->sparse_min_edges = atoll(env);   // parity suite: 0
         if (const char *env = getenv("MRC_B200_FRONTIER"))   // A/B switch for experiments and the parity suite
             g->frontier = atoi(env) != 0 && g->act_bytes + 2048 <= 227 * 1024;

@@ -784,11 +784,10 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     // phase): saves the separate init sweep, its grid sync and the src[] gather of an edge-only pred
     for (ll i = tid0; i < total; i += stride) {
         const int k = (int)(i % K);
+        if (!((active >> k) & 1u)) continue;   // jump of a decided candidate is never read
         int j = -1;
-        if ((active >> k) & 1u) {
-            const int u = (int)(__ldcg(p.pred + i) >> 32);
-            if (u >= 0) j = (int)(__ldcg(p.pred + (ll)u * K + k) >> 32);
-        }
+        const int u = (int)(__ldcg(p.pred + i) >> 32);
+        if (u >= 0) j = (int)(__ldcg(p.pred + (ll)u * K + k) >> 32);
         __stcg(p.jump + i, j);
     }
     grid.sync();

@@ -1,4 +1,8 @@
-MRC_B200_SPARSE=1 timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-for rep in 1 2 3 4; do
-  MRC_SPARSE_LOOK=1 MRC_SPARSE=1 MRC_SEEDS=1,0 MRC_KS=1,4 MRC_QUIET=1 python tools/trace_solve.py 2>&1 | grep "mrc_solve\|total wall" | cut -c1-220
+for look in 2 32 4 2 32 4; do
+  for K in 4 1; do
+  MRC_B200_SPARSE_LOOK=$look python bench.py --sparse --no-cpu-baseline --klocal $K --steps 30 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('look $look K $K', round(d['ms_per_step'],3), 'ms rounds', d['rounds'], 'e2e ms', round(d['e2e']['ms_per_step'],2))"
+  done
 done
