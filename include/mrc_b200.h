@@ -96,6 +96,10 @@ int mrc_graph_destroy(mrc_graph *g);
 int mrc_graph_info(const mrc_graph *g, int64_t *n, int64_t *m, int *device, int *has_int);
 /* min/max of cost/time over edges -/+ 1.0: the default bracket of _solve_numeric (solver.py:1019-1023) */
 int mrc_numeric_bounds(mrc_graph *g, double *lo, double *hi);
+/* get_graph_properties (solver.py:339-387) on the resident arrays.  out[13] = isolated, source, sink vertices, max
+ * in-degree, max out-degree, cost min / max / mean / std, time min / max / mean / std (population std, as np.std).
+ * solve() stores this dictionary in result.metrics on every call; at m = 10^7 the NumPy version costs 160 ms. */
+int mrc_graph_properties(mrc_graph *g, double *out);
 int mrc_get_stats(const mrc_graph *g, mrc_stats *out);
 int mrc_reset_stats(mrc_graph *g);
 

@@ -26,7 +26,7 @@ F_STOP_ON_NEG = 2
 
 EXPORTS = [
     "mrc_abi_version", "mrc_last_error", "mrc_device_count", "mrc_graph_create", "mrc_graph_destroy",
-    "mrc_graph_info", "mrc_numeric_bounds", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
+    "mrc_graph_info", "mrc_numeric_bounds", "mrc_graph_properties", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
     "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
     "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
     "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle", "mrc_sort_edges_by_dst", "mrc_probe_numeric_scenarios",
@@ -75,6 +75,7 @@ def lib():
     L.mrc_graph_destroy.argtypes = [vp]
     L.mrc_graph_info.argtypes = [vp, p64, p64, pi, pi]
     L.mrc_numeric_bounds.argtypes = [vp, pd, pd]
+    L.mrc_graph_properties.argtypes = [vp, pd]
     L.mrc_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mrc_reset_stats.argtypes = [vp]
     L.mrc_graph_patch_edges.argtypes = [vp, C.c_int64, p64, pd, pd]
@@ -176,6 +177,14 @@ class DeviceGraph:
         lo, hi = C.c_double(), C.c_double()
         check(lib().mrc_numeric_bounds(self._h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+    def properties(self):
+        """Degree and weight statistics of get_graph_properties (solver.py:339-387), computed on the device."""
+        out = np.zeros(13)
+        check(lib().mrc_graph_properties(self._h, _ptr(out, C.c_double)))
+        keys = ("isolated_vertices", "source_vertices", "sink_vertices", "max_in_degree", "max_out_degree",
+                "cost_min", "cost_max", "cost_mean", "cost_std", "time_min", "time_max", "time_mean", "time_std")
+        return dict(zip(keys, out.tolist()))
 
     def patch_edges(self, idx, dcost, dtime):
         idx = np.ascontiguousarray(idx, dtype=np.int64)

@@ -1022,6 +1022,66 @@ __global__ void gather_cycle_kernel(const int *edges, ll len, const int *src, co
     }
 }
 
+// ---- get_graph_properties (solver.py:339-387) on the resident arrays ----------------------------------------------
+// acc layout (doubles): 0 cost sum, 1 time sum, 2 cost sum of squared deviations, 3 time ssd; keys (ull, order-preserving
+// f64 keys): 0 cost min, 1 cost max, 2 time min, 3 time max; cnt (unsigned): 0 isolated, 1 sources, 2 sinks, 3 max in, 4 max out
+__device__ __forceinline__ ull f64_key_of(double x) {
+    ull b = (ull)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void props_edges_kernel(const int *src, const int *dst, const double *cost, const double *time, ll m,
+                                   unsigned *indeg, unsigned *outdeg, double *acc, ull *keys) {
+    double sc = 0.0, st = 0.0;
+    ull cmin = ~0ull, cmax = 0ull, tmin = ~0ull, tmax = 0ull;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (ll)gridDim.x * blockDim.x) {
+        atomicAdd(indeg + dst[e], 1u);
+        atomicAdd(outdeg + src[e], 1u);
+        const double c = cost[e], t = time[e];
+        sc += c; st += t;
+        const ull kc = f64_key_of(c), kt = f64_key_of(t);
+        cmin = kc < cmin ? kc : cmin; cmax = kc > cmax ? kc : cmax;
+        tmin = kt < tmin ? kt : tmin; tmax = kt > tmax ? kt : tmax;
+    }
+    for (int o = 16; o; o >>= 1) {
+        sc += __shfl_xor_sync(0xffffffffu, sc, o); st += __shfl_xor_sync(0xffffffffu, st, o);
+        ull x;
+        x = __shfl_xor_sync(0xffffffffu, cmin, o); cmin = x < cmin ? x : cmin;
+        x = __shfl_xor_sync(0xffffffffu, cmax, o); cmax = x > cmax ? x : cmax;
+        x = __shfl_xor_sync(0xffffffffu, tmin, o); tmin = x < tmin ? x : tmin;
+        x = __shfl_xor_sync(0xffffffffu, tmax, o); tmax = x > tmax ? x : tmax;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc + 0, sc); atomicAdd(acc + 1, st);
+        atomicMin(keys + 0, cmin); atomicMax(keys + 1, cmax); atomicMin(keys + 2, tmin); atomicMax(keys + 3, tmax);
+    }
+}
+__global__ void props_deviation_kernel(const double *cost, const double *time, ll m, double *acc) {
+    const double mc = acc[0] / (double)m, mt = acc[1] / (double)m;
+    double dc = 0.0, dt = 0.0;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (ll)gridDim.x * blockDim.x) {
+        const double a = cost[e] - mc, b = time[e] - mt;
+        dc += a * a; dt += b * b;
+    }
+    for (int o = 16; o; o >>= 1) { dc += __shfl_xor_sync(0xffffffffu, dc, o); dt += __shfl_xor_sync(0xffffffffu, dt, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(acc + 2, dc); atomicAdd(acc + 3, dt); }
+}
+__global__ void props_vertices_kernel(const unsigned *indeg, const unsigned *outdeg, ll n, unsigned *cnt) {
+    unsigned iso = 0, so = 0, si = 0, mi = 0, mo = 0;
+    for (ll v = (ll)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (ll)gridDim.x * blockDim.x) {
+        const unsigned a = indeg[v], b = outdeg[v];
+        iso += (a == 0 && b == 0); so += (a == 0 && b > 0); si += (a > 0 && b == 0);
+        mi = a > mi ? a : mi; mo = b > mo ? b : mo;
+    }
+    iso = __reduce_add_sync(0xffffffffu, iso); so = __reduce_add_sync(0xffffffffu, so); si = __reduce_add_sync(0xffffffffu, si);
+    mi = __reduce_max_sync(0xffffffffu, mi); mo = __reduce_max_sync(0xffffffffu, mo);
+    if ((threadIdx.x & 31) == 0) {
+        if (iso) atomicAdd(cnt + 0, iso);
+        if (so) atomicAdd(cnt + 1, so);
+        if (si) atomicAdd(cnt + 2, si);
+        atomicMax(cnt + 3, mi); atomicMax(cnt + 4, mo);
+    }
+}
+
 // equal_mask = (dist[U] + W) == dist[V], solver.py:878-879 (dist layout [n][1])
 __global__ void tight_mask_kernel(const int *src, const int *dst, const ll *icost, const ll *itime,
                                   const ll *dist, ll a, ll b, ll m, uint8_t *mask) {

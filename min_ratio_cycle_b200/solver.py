@@ -267,24 +267,25 @@ class MinRatioCycleSolver:
             return {"error": "No edges in graph"}
         self._build_arrays_if_needed()
         n, m = self.n, len(self._U)
-        indeg = np.bincount(self._V, minlength=n)
-        outdeg = np.bincount(self._U, minlength=n)
         density = m / (n * n)
+        # the degree / weight statistics come from the device-resident arrays (mrc_graph_properties): solve() stores
+        # this dictionary in result.metrics on every call and the eight NumPy sweeps cost 160 ms at m = 10^7
+        p = self._device().properties()
         return {
             "vertices": n, "edges": m, "density": density, "is_sparse": density < self.config.sparse_threshold,
             "connectivity": {
-                "isolated_vertices": int(np.sum((indeg == 0) & (outdeg == 0))),
-                "source_vertices": int(np.sum((indeg == 0) & (outdeg > 0))),
-                "sink_vertices": int(np.sum((indeg > 0) & (outdeg == 0))),
-                "avg_in_degree": float(indeg.mean()), "avg_out_degree": float(outdeg.mean()),
-                "max_in_degree": int(indeg.max()), "max_out_degree": int(outdeg.max()),
+                "isolated_vertices": int(p["isolated_vertices"]),
+                "source_vertices": int(p["source_vertices"]),
+                "sink_vertices": int(p["sink_vertices"]),
+                "avg_in_degree": m / n, "avg_out_degree": m / n,
+                "max_in_degree": int(p["max_in_degree"]), "max_out_degree": int(p["max_out_degree"]),
             },
             "weights": {
                 "all_integer": self._all_int,
-                "cost_range": (float(self._C.min()), float(self._C.max())),
-                "time_range": (float(self._T.min()), float(self._T.max())),
-                "cost_mean": float(self._C.mean()), "time_mean": float(self._T.mean()),
-                "cost_std": float(self._C.std()), "time_std": float(self._T.std()),
+                "cost_range": (p["cost_min"], p["cost_max"]),
+                "time_range": (p["time_min"], p["time_max"]),
+                "cost_mean": p["cost_mean"], "time_mean": p["time_mean"],
+                "cost_std": p["cost_std"], "time_std": p["time_std"],
             },
         }
 

@@ -486,3 +486,30 @@ def test_every_kernel_variant_on_odd_sizes(mrc):
     import runpy
     from conftest import ROOT
     runpy.run_path(os.path.join(ROOT, "tools", "sanitize_case.py"), run_name="__main__")
+
+
+def test_graph_properties_on_device_match_numpy(mrc):
+    """get_graph_properties (solver.py:339-387): the device-side statistics equal the NumPy ones."""
+    from min_ratio_cycle_b200 import synthetic
+    rng = np.random.default_rng(4)
+    n = 5000
+    U = rng.integers(0, n // 2, 30_000); V = rng.integers(n // 4, n - 50, 30_000)   # sources, sinks and isolated vertices
+    C = rng.uniform(-10, 10, 30_000); T = rng.uniform(0.1, 5, 30_000)
+    s = mrc.MinRatioCycleSolver(n, mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+    s.add_edges_arrays(U, V, C, T)
+    p = s.get_graph_properties()
+    indeg = np.bincount(s._V, minlength=n); outdeg = np.bincount(s._U, minlength=n)
+    c = p["connectivity"]
+    assert c["isolated_vertices"] == int(np.sum((indeg == 0) & (outdeg == 0))) > 0
+    assert c["source_vertices"] == int(np.sum((indeg == 0) & (outdeg > 0))) > 0
+    assert c["sink_vertices"] == int(np.sum((indeg > 0) & (outdeg == 0))) > 0
+    assert c["max_in_degree"] == int(indeg.max()) and c["max_out_degree"] == int(outdeg.max())
+    assert c["avg_in_degree"] == pytest.approx(indeg.mean()) and c["avg_out_degree"] == pytest.approx(outdeg.mean())
+    w = p["weights"]
+    assert w["cost_range"] == (float(s._C.min()), float(s._C.max()))
+    assert w["time_range"] == (float(s._T.min()), float(s._T.max()))
+    for key, arr in (("cost", s._C), ("time", s._T)):
+        assert w[key + "_mean"] == pytest.approx(float(arr.mean()), rel=1e-12, abs=1e-12)
+        assert w[key + "_std"] == pytest.approx(float(arr.std()), rel=1e-12)
+    assert p["vertices"] == n and p["edges"] == len(s._U) and w["all_integer"] is False
+    assert {i["level"] for i in s.detect_issues()} >= {"WARNING"}
