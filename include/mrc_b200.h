@@ -165,7 +165,9 @@ int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *m
  * "gate" (0/1, default 1: a relaxation launch returns at once when the previous launch of its burst moved none of
  * its candidates, so bursts can be long without wasting passes after convergence), "sparse" (0/1, default 0 or
  * the environment variable MRC_B200_SPARSE; the Python facade switches it on: once fewer than n / "sparse_div" (default 32) vertices were lowered by the last pass of a burst, the next bursts
- * run as worklist passes over the out-edges of just those vertices -- same fixed point, same verdicts),
+ * run as worklist passes over the out-edges of just those vertices -- same fixed point, same verdicts; graphs
+ * below "sparse_min_edges" (default 1.5 M) keep sweeping; "sparse_look": dense bursts are at most this long while
+ * the worklist waits to take over, 0 = chosen by graph size),
  * "prune_above" (0/1, default 1:
  * with MRC_F_MONOTONE_PRUNE and candidates in increasing order a cycle check stops working on the candidates
  * above the lowest one whose predecessor graph holds a cycle), "patience" (0/1:

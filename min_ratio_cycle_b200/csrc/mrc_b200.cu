@@ -14,7 +14,7 @@
 #include <vector>
 
 #include "mrc_kernels.cuh"
-#define MRC_SPARSE_MIN_EDGES 65536   /* below this a dense sweep is launch-bound anyway */
+#define MRC_SPARSE_MIN_EDGES 1500000   /* below this a dense sweep is launch-bound (~10 us) and a worklist pass does not pay */
 #include "mrc_search.h"
 #include "mrc_batch.cuh"
 #include "mrc_host.h"
@@ -83,13 +83,13 @@ struct mrc_graph {
     // sparse (worklist) passes: out-edge index by source, worklists + membership bitmaps, built on first use
     int sparse = 0;              // option "sparse" (env MRC_B200_SPARSE): bursts run as worklist passes once few vertices are still lowered
     int sparse_div = 32;         // option "sparse_div": ... i.e. fewer than n / sparse_div
-    bool sparse_ready = false;
+    bool sparse_ready = false, bm1_dirty = false;
     int *d_out_off = nullptr, *d_out_edge = nullptr, *d_wl[2] = {nullptr, nullptr};
     unsigned *d_bm[2] = {nullptr, nullptr};
     size_t bm_bytes = 0;
     int sparse_blocks[2] = {0, 0};
     ll sparse_min_edges = MRC_SPARSE_MIN_EDGES;   // option "sparse_min_edges": smaller graphs sweep densely (launch-bound anyway)
-    int sparse_look = 2;         // option "sparse_look": dense bursts are at most this long while the sparse passes wait to take over
+    int sparse_look = 0;         // option "sparse_look": dense bursts are at most this long while the sparse passes wait to take over (0 = by graph size)
     int sparse_bps = 2;          // CTAs per SM of the cooperative sparse kernel (env MRC_B200_SPARSE_BPS, experiments)
     int prune_above = 1;         // option "prune_above": cycle checks stop examining candidates above the lowest one with a cycle
     int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
@@ -285,7 +285,7 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
         if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
-        if (const char *env = getenv("MRC_B200_SPARSE_LOOK")) g->sparse_look = std::max(1, atoi(env));
+        if (const char *env = getenv("MRC_B200_SPARSE_LOOK")) g->sparse_look = std::max(0, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_MIN_EDGES")) g->sparse_min_edges = atoll(env);   // parity suite: 0
         if (const char *env = getenv("MRC_B200_FRONTIER"))   // A/B switch for experiments and the parity suite
             g->frontier = atoi(env) != 0 && g->act_bytes + 2048 <= 227 * 1024;
@@ -603,11 +603,15 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     if (use_sparse) MRC_TRY(ensure_sparse(g));
     bool sparse_mode = false;
     int sp_in = 0, sp_ci = 0;
+    // dense sweeps until the active count is looked at again: every look is a host round trip (~30 us) plus a
+    // compaction, worth it when a sweep costs 60-100 us (m >= 5 M edges), not when it costs 10-25 us
+    const int look0 = g->sparse_look > 0 ? g->sparse_look : (m >= 5000000 ? 2 : MRC_MAX_BURST);
+    int look = look0;
     while (active) {
         int nb = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
         // while sweeping densely with the sparse passes available, look at the active count every few sweeps:
         // a worklist pass is 5-10x cheaper than a sweep as soon as it applies
-        if (use_sparse && !sparse_mode && nb > g->sparse_look) nb = g->sparse_look;
+        if (use_sparse && !sparse_mode && nb > look) nb = look;
         if (nb <= 0) {
             for (int k = 0; k < K; k++)
                 if ((active >> k) & 1u) { res[k].verdict = MRC_V_NEG_NOCYCLE; res[k].passes = passes; }
@@ -623,6 +627,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
             ra.changed = &g->d_status->changed[0];
             ra.act_out = nullptr; ra.gate = nullptr; ra.reverse = 0;
             MRC_TRY(launch_sparse(g, KT, exact, ra, sp_in, sp_ci, nb));
+            g->bm1_dirty = true;   // either bitmap may now hold bits of a worklist that is never consumed
         }
         for (int i = 0; i < nb && !sparse_burst; i++) {
             ra.changed = &g->d_status->changed[i];
@@ -649,11 +654,10 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         if (use_sparse && !sparse_burst) {
             // bm[1] may hold the membership bits of a worklist nobody consumed (a probe that ended on a verified cycle,
             // or a switch back to dense sweeps): the next worklist pass deduplicates through it, so it must be clean
-            CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0, g->bm_bytes, g->stream));
+            if (g->bm1_dirty) { CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0, g->bm_bytes, g->stream)); g->bm1_dirty = false; }
             CUDA_TRY(cudaMemsetAsync(&g->d_status->act_count, 0, 4 * sizeof(unsigned), g->stream));   // act_count + act_cnt[3]
             compact_active_kernel<<<std::min<int>((int)((g->bm_bytes / 4 + 255) / 256), 4 * g->sms), 256, 0, g->stream>>>(
                 g->d_bm[0], (int)(g->bm_bytes / 4), g->d_wl[0], g->d_status, 0);
-            publish_active_count_kernel<<<1, 1, 0, g->stream>>>(g->d_status, 0);
             CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
@@ -685,8 +689,13 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         } else {
             if (!g->frontier) dense_launches = ran;
             g->stats.relax_launches += ran;
-            g->stats.other_launches += nb - ran + (use_sparse ? 2 : 0);
-            if (use_sparse && (ll)hs.act_count * g->sparse_div < n) { sparse_mode = true; sp_in = 0; sp_ci = 0; }
+            g->stats.other_launches += nb - ran + (use_sparse ? 1 : 0);
+            if (use_sparse) {
+                const ll scaled = (ll)hs.act_cnt[0] * g->sparse_div;   // size of the worklist compacted from the last sweep
+                if (scaled < n) { sparse_mode = true; sp_in = 0; sp_ci = 0; }
+                // far from the threshold: look again later (every look costs a host round trip)
+                look = scaled > 8 * n ? 8 * look0 : scaled > 4 * n ? 4 * look0 : scaled > 2 * n ? 2 * look0 : look0;
+            }
         }
         g->stats.relax_edge_visits += ((int64_t)dense_launches * m + (int64_t)g->h_status->examined) * __builtin_popcount(active);
         g->stats.relax_edge_slots += (int64_t)ran * m * __builtin_popcount(active);
@@ -948,13 +957,14 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "gate") g->gate = value != 0;
     else if (s == "sparse") g->sparse = value != 0;
     else if (s == "sparse_div") g->sparse_div = std::max(1, value);
-    else if (s == "sparse_look") g->sparse_look = std::max(1, value);
+    else if (s == "sparse_look") g->sparse_look = std::max(0, value);
     else if (s == "sparse_min_edges") g->sparse_min_edges = std::max(0, value);
     else if (s == "sparse_poison") {   // test hook: garbage in both membership bitmaps, as an interrupted probe may leave it
         CUDA_TRY(cudaSetDevice(g->device));
         MRC_TRY(ensure_sparse(g));
         CUDA_TRY(cudaMemsetAsync(g->d_bm[0], 0xff, g->bm_bytes, g->stream));
         CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0xff, g->bm_bytes, g->stream));
+        g->bm1_dirty = true;   // ... and the library knows no more than that
     }
     else if (s == "prune_above") g->prune_above = value != 0;
     else if (s == "patience") g->patience = value != 0;

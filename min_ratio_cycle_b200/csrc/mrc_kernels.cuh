@@ -574,7 +574,6 @@ __global__ void compact_active_kernel(const unsigned *bm, int words, int *wl, De
         }
     }
 }
-__global__ void publish_active_count_kernel(DevStatus *st, int cidx) { st->act_count = st->act_cnt[cidx]; }
 
 template <bool EXACT>
 __global__ void __launch_bounds__(256) relax_sparse_kernel(const __grid_constant__ SparseArgs a) {
