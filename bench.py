@@ -292,6 +292,8 @@ def main():
             g3.close()
         torch.cuda.synchronize()
         te = (time.perf_counter() - t0) / 3
+        if abs(o3["ratio"] - out["ratio"]) > 1e-9 * max(1.0, abs(out["ratio"])):
+            raise RuntimeError(f"sparse passes changed the answer: {o3['ratio']!r} vs {out['ratio']!r}")
         sparse_info = {"solve_ms": 1e3 * ts / e2e_steps, "e2e_ms": 1e3 * te, "ratio": o3["ratio"],
                        "value_executed": st3["relax_edge_visits"] / ts / 1e9,
                        "dense_launches_per_solve": st3["relax_launches"] / e2e_steps,
