@@ -309,6 +309,8 @@ class MinRatioCycleSolver:
     # ------------------------------------------------------------------ arrays + preprocessing (:450-575)
     def _insertion_arrays(self):
         m1 = len(self._edges)
+        if m1 == 0 and len(self._bulk) == 1:      # one bulk block and nothing else: no copies
+            return self._bulk[0]
         U = np.fromiter((e.u for e in self._edges), dtype=np.int64, count=m1)
         V = np.fromiter((e.v for e in self._edges), dtype=np.int64, count=m1)
         Cw = np.fromiter((float(e.cost) for e in self._edges), dtype=np.float64, count=m1)
@@ -337,9 +339,11 @@ class MinRatioCycleSolver:
                                                            count_dups=False)
         else:
             so = None
+        u32 = v32 = None
         if so is not None:                                     # stable radix sort on the GPU (mrc_sort_edges_by_dst)
             self._U, self._V, self._C, self._T = so.astype(np.int64), do.astype(np.int64), co, to
             order = order.astype(np.int64)
+            u32, v32 = so, do                                  # the upload below takes the int32 arrays as they are
         else:
             U, V, Cw, Tw = self._insertion_arrays()
             order = np.argsort(V, kind="stable")
@@ -358,8 +362,8 @@ class MinRatioCycleSolver:
         self._is_sparse = len(self._U) / (self.n * self.n) < self.config.sparse_threshold
         if self._dev is not None:
             self._dev.close()
-        self._dev = N.DeviceGraph(self.n, self._U, self._V, self._C, self._T, self._Ci, self._Ti,
-                                  device=self.config.gpu_device)
+        self._dev = N.DeviceGraph(self.n, self._U if u32 is None else u32, self._V if v32 is None else v32,
+                                  self._C, self._T, self._Ci, self._Ti, device=self.config.gpu_device)
         if self.config.gpu_frontier and self.n <= 1_700_000:
             self._dev.set_option("frontier", 1)
         self._dev.set_option("sparse", 1 if self.config.gpu_sparse else 0)
