@@ -747,11 +747,11 @@ class MinRatioCycleSolver:
         self._build_arrays_if_needed()
         m = self._num_edges()
         U, V, Cw, Tw = self._insertion_arrays()
-        out: dict[int, bool] = {}
-        for idx in range(m):
-            res = self.sensitivity_analysis([{idx: (float(Cw[idx]) * epsilon, float(Tw[idx]) * epsilon)}])
-            out[idx] = res[0].cycle == base.cycle
-        return out
+        # the reference re-solves once per edge (:1750-1757); the scenarios are independent, so they go to
+        # sensitivity_analysis in one call and share edge sweeps K at a time (mrc_probe_numeric_scenarios)
+        scenarios = [{idx: (float(Cw[idx]) * epsilon, float(Tw[idx]) * epsilon)} for idx in range(m)]
+        res = self.sensitivity_analysis(scenarios)
+        return {idx: res[idx].cycle == base.cycle for idx in range(m)}
 
     # ------------------------------------------------------------------ misc (:1631-1693, :1814-1933)
     def get_debug_info(self) -> str:

@@ -513,3 +513,23 @@ def test_graph_properties_on_device_match_numpy(mrc):
         assert w[key + "_std"] == pytest.approx(float(arr.std()), rel=1e-12)
     assert p["vertices"] == n and p["edges"] == len(s._U) and w["all_integer"] is False
     assert {i["level"] for i in s.detect_issues()} >= {"WARNING"}
+
+
+def test_stability_region_equals_one_resolve_per_edge(mrc):
+    """stability_region (solver.py:1731-1759): the batched scenarios give what the reference's per-edge loop gives."""
+    from min_ratio_cycle_b200 import synthetic
+    n, U, V, C, T = synthetic.ring_plus_random(120, 500, seed=3)
+    s = mrc.MinRatioCycleSolver(n, mrc.SolverConfig(log_level=mrc.LogLevel.NONE))
+    s.add_edges_arrays(U, V, C, T)
+    base = s.solve()
+    stab = s.stability_region(0.05)
+    assert set(stab) == set(range(len(U)))
+    U0, V0, C0, T0 = s._insertion_arrays()
+    for idx in list(range(0, len(U), 7)) + [i for i, ok in stab.items() if not ok][:10]:
+        one = s.sensitivity_analysis([{idx: (float(C0[idx]) * 0.05, float(T0[idx]) * 0.05)}])[0]
+        assert (one.cycle == base.cycle) == stab[idx], idx
+    on_cycle = {(a, b) for a, b in zip(base.cycle[:-1], base.cycle[1:])}
+    # perturbing an edge off the optimal cycle upwards can never change the optimum
+    for idx in range(len(U)):
+        if (int(U0[idx]), int(V0[idx])) not in on_cycle and C0[idx] > 0:
+            assert stab[idx], idx
