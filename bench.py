@@ -197,7 +197,7 @@ def main():
         if world == 1:
             return graph.solve_numeric(lo0, hi0, max_iter, tol, slack, K=K)
         r = sharded.solve_numeric_sharded(lambda l, s, f: graph.probe_numeric(l, s, f), lo0, hi0, max_iter, tol,
-                                          slack, K_local=K)
+                                          slack, K_local=K, fetch=graph.fetch_cycle_sums)
         return dict(rc=r.rc, ratio=r.ratio, cycle=r.cycle, iterations=r.iterations)
 
     def barrier():

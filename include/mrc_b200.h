@@ -61,6 +61,10 @@ extern "C" {
                                    interval (as long as everything before it) brought no further verdict; the open
                                    candidates -- slow ones next to lambda* -- are reported MRC_V_ABANDONED */
 
+#define MRC_F_NO_CYCLES 8u       /* do not bring the cycles to the host: cyc_len is the length each would have, the sums are the
+                                   device's (accumulated along the predecessor walk); the one cycle the caller wants is
+                                   fetched afterwards with mrc_fetch_cycle_sums.  Ignored by mrc_probe_numeric_scenarios. */
+
 typedef struct mrc_graph mrc_graph;
 
 typedef struct mrc_stats {
@@ -136,6 +140,10 @@ int mrc_probe_numeric_scenarios(mrc_graph *g, const double *lam, int K, double s
 /* Full cycle of candidate k of the LAST probe (numeric or exact), for callers that probed with a small
  * cyc_cap: CLOSED vertex list; *cycle_len = 0 if that candidate extracted none. */
 int mrc_fetch_cycle(mrc_graph *g, int k, int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len);
+/* The same plus the cost / time sums accumulated in forward cycle order from the smallest vertex -- what a probe
+ * without MRC_F_NO_CYCLES reports (numeric probes; after an exact probe the integer sums converted to double). */
+int mrc_fetch_cycle_sums(mrc_graph *g, int k, int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len, double *sum_cost,
+                         double *sum_time);
 
 /* ---- numeric lambda search -----------------------------------------------------------------
  * Replaces the bisection of _solve_numeric (solver.py:1017-1117) by K-way multisection: every round

@@ -23,13 +23,15 @@ ERR_LOWER_NEG, ERR_UPPER_NONNEG, ERR_SB_STEPS, ERR_NOT_INTEGER, ERR_TIMEOUT, ERR
 V_NONNEG, V_NEG, V_NEG_NOCYCLE, V_TIE, V_SKIPPED_NEG, V_SKIPPED_NONNEG, V_ABANDONED = range(7)
 F_MONOTONE_PRUNE = 1
 F_STOP_ON_NEG = 2
+F_PATIENCE = 4
+F_NO_CYCLES = 8
 
 EXPORTS = [
     "mrc_abi_version", "mrc_last_error", "mrc_device_count", "mrc_graph_create", "mrc_graph_destroy",
     "mrc_graph_info", "mrc_numeric_bounds", "mrc_graph_properties", "mrc_get_stats", "mrc_reset_stats", "mrc_graph_patch_edges",
     "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
     "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
-    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle", "mrc_sort_edges_by_dst", "mrc_probe_numeric_scenarios",
+    "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle", "mrc_fetch_cycle_sums", "mrc_sort_edges_by_dst", "mrc_probe_numeric_scenarios",
 ]
 
 
@@ -95,6 +97,7 @@ def lib():
     L.mrc_probe_numeric_scenarios.argtypes = [vp, pd, C.c_int, C.c_double, C.c_uint32, p64, pd, pd, p32, p32, p32, C.c_int64,
                                               pd, pd, p64]
     L.mrc_fetch_cycle.argtypes = [vp, C.c_int, p32, C.c_int64, p64]
+    L.mrc_fetch_cycle_sums.argtypes = [vp, C.c_int, p32, C.c_int64, p64, pd, pd]
     L.mrc_bench_relax.argtypes = [vp, pd, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.mrc_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.mrc_batch_solve_numeric.argtypes = [C.c_int64, p32, p64, p32, p32, pd, pd, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -218,7 +221,7 @@ class DeviceGraph:
                                       _ptr(st, C.c_double), _ptr(ps, C.c_int64)))
         out = []
         for k in range(K):
-            cyc = self._cycle_of(k, buf, cap, int(cl[k]))
+            cyc = None if (int(flags) & F_NO_CYCLES) else self._cycle_of(k, buf, cap, int(cl[k]))
             out.append(dict(lam=float(lam[k]), verdict=int(vd[k]), cycle=cyc, cycle_len=int(cl[k]),
                             sum_cost=float(sc[k]), sum_time=float(st[k]), passes=int(ps[k])))
         return out
@@ -250,10 +253,18 @@ class DeviceGraph:
                                     _ptr(st, C.c_int64), _ptr(ps, C.c_int64)))
         out = []
         for k in range(K):
-            cyc = self._cycle_of(k, buf, cap, int(cl[k]))
+            cyc = None if (int(flags) & F_NO_CYCLES) else self._cycle_of(k, buf, cap, int(cl[k]))
             out.append(dict(a=int(a[k]), b=int(b[k]), verdict=int(vd[k]), cycle=cyc, cycle_len=int(cl[k]),
                             sum_cost=int(sc[k]), sum_time=int(st[k]), passes=int(ps[k])))
         return out
+
+    def fetch_cycle_sums(self, k: int, length: int | None = None):
+        """(closed cycle, sum_cost, sum_time) of candidate k of the last probe (probes run with F_NO_CYCLES)."""
+        cap = int(length) if length else self.n + 1
+        buf = np.empty(cap, np.int32)
+        n, sc, st = C.c_int64(), C.c_double(), C.c_double()
+        check(lib().mrc_fetch_cycle_sums(self._h, int(k), _ptr(buf, C.c_int32), cap, C.byref(n), C.byref(sc), C.byref(st)))
+        return buf[: n.value].tolist(), sc.value, st.value
 
     def _cycle_of(self, k: int, buf, cap: int, length: int):
         if not length:

@@ -842,7 +842,11 @@ static int probe_common(mrc_graph *g, bool exact, const double *lam, const ll *a
         if (cyc_len) cyc_len[k] = 0;
         if (sum_cost) sum_cost[k] = 0;
         if (sum_time) sum_time[k] = 0;
-        if (res[k].verdict == MRC_V_NEG || res[k].verdict == MRC_V_TIE) {
+        if ((res[k].verdict == MRC_V_NEG || res[k].verdict == MRC_V_TIE) && (flags & MRC_F_NO_CYCLES) && !g->scen_on) {
+            if (cyc_len) cyc_len[k] = (int32_t)res[k].len + 1;
+            if (sum_cost) sum_cost[k] = exact ? (S)res[k].isumc : (S)res[k].sumc;
+            if (sum_time) sum_time[k] = exact ? (S)res[k].isumt : (S)res[k].sumt;
+        } else if (res[k].verdict == MRC_V_NEG || res[k].verdict == MRC_V_TIE) {
             double sc = 0, st = 0; ll isc = 0, ist = 0;
             MRC_TRY(fetch_cycle(g, exact, k, res[k], verts, &sc, &st, &isc, &ist));
             if (cyc_len) cyc_len[k] = (int32_t)verts.size();
@@ -865,6 +869,23 @@ extern "C" int mrc_fetch_cycle(mrc_graph *g, int k, int32_t *cycle, int64_t cycl
     MRC_TRY(fetch_cycle(g, g->last_exact, k, o, verts, nullptr, nullptr, nullptr, nullptr));
     *cycle_len = (int64_t)verts.size();
     if (cycle) for (size_t i = 0; i < verts.size() && (int64_t)i < cycle_cap; i++) cycle[i] = verts[i];
+    return MRC_OK;
+}
+
+extern "C" int mrc_fetch_cycle_sums(mrc_graph *g, int k, int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len,
+                                    double *sum_cost, double *sum_time) {
+    if (!g || !cycle_len) return set_err(MRC_ERR_ARG, "NULL argument");
+    if (k < 0 || k >= g->last_K) return set_err(MRC_ERR_ARG, "candidate index out of range of the last probe");
+    const ProbeOut &o = g->last_res[k];
+    if (o.verdict != MRC_V_NEG && o.verdict != MRC_V_TIE) { *cycle_len = 0; return MRC_OK; }
+    CUDA_TRY(cudaSetDevice(g->device));
+    std::vector<int> verts;
+    double sc = 0, st = 0; ll isc = 0, ist = 0;
+    MRC_TRY(fetch_cycle(g, g->last_exact, k, o, verts, &sc, &st, &isc, &ist));
+    *cycle_len = (int64_t)verts.size();
+    if (cycle) for (size_t i = 0; i < verts.size() && (int64_t)i < cycle_cap; i++) cycle[i] = verts[i];
+    if (sum_cost) *sum_cost = g->last_exact ? (double)isc : sc;
+    if (sum_time) *sum_time = g->last_exact ? (double)ist : st;
     return MRC_OK;
 }
 

@@ -3,7 +3,7 @@ Multi-GPU lambda search: one process per GPU (torch.distributed), every rank hol
 device-resident edge arrays and owns K_local of the K_total = world * K_local candidate lambdas of a
 multisection round (sharding (1)).  The only communication is one all-gather of
 K_total (verdict, cycle ratio, cycle length) records per round -- tens of bytes over NCCL/NVLink --
-and one broadcast of the winning cycle at the end.  No graph data ever crosses the link.
+and one broadcast of the winning cycle at the end (vertex ids as f64: exact below 2^53).  No graph data ever crosses the link.
 
 Candidate planning and bracket folding are the SAME host functions the single-GPU driver uses
 (mrc_plan_candidates / mrc_reduce_round in libmrc_b200.so), so every rank derives the same bracket.
@@ -47,9 +47,12 @@ def _comm_device(group=None):
 
 
 def solve_numeric_sharded(probe, lo: float, hi: float, max_iter: int = 60, tol: float = 1e-12,
-                          slack: float = 1e-15, K_local: int = 4, group=None) -> ShardedResult:
+                          slack: float = 1e-15, K_local: int = 4, group=None, fetch=None) -> ShardedResult:
     """
     probe(lams, slack, flags) -> list of dicts like DeviceGraph.probe_numeric.
+    fetch(k) -> (closed cycle, sum_cost, sum_time) of candidate k of the LAST probe (DeviceGraph.fetch_cycle_sums);
+    when given, probes run with F_NO_CYCLES -- a round usually verifies several negative cycles per rank and only
+    the best one of all ranks is ever needed on a host.
     Collective: every rank of `group` must call this with the same lo/hi/max_iter/tol/K_local.
     """
     import torch
@@ -58,59 +61,72 @@ def solve_numeric_sharded(probe, lo: float, hi: float, max_iter: int = 60, tol: 
     K_total = K_local * world
     dev = _comm_device(group)
     have_cycle = False
-    best = None            # (owner rank, dict) -- only the owner keeps the cycle itself
-    best_owner = -1
+    best = None            # (cycle, sum_cost, sum_time) -- only the owner keeps the cycle itself
+    best_owner, best_len = -1, 0
     iterations = 0
     probes_local = 0
     it = -1
+    flags = N.F_MONOTONE_PRUNE | (N.F_NO_CYCLES if fetch is not None else 0)
+
+    def cycle_of(res, k):
+        r = res[k]
+        if r.get("cycle") is not None:
+            return list(r["cycle"]), r["sum_cost"], r["sum_time"]
+        return fetch(k)
+
     for it in range(max_iter):
         iterations += 1
         lam = N.plan_candidates(lo, hi, have_cycle, tol, K_total)
         mine = lam[rank * K_local:(rank + 1) * K_local]
-        res = probe(mine, slack, N.F_MONOTONE_PRUNE)
+        res = probe(mine, slack, flags)
         probes_local += len(mine)
-        rec = torch.zeros(K_local, 2, dtype=torch.float64)
+        rec = torch.zeros(K_local, 3, dtype=torch.float64)
         for k, r in enumerate(res):
             rec[k, 0] = float(r["verdict"])
-            rec[k, 1] = (r["sum_cost"] / r["sum_time"]) if r["verdict"] in (N.V_NEG, N.V_TIE) else float("nan")
+            neg = r["verdict"] in (N.V_NEG, N.V_TIE)
+            rec[k, 1] = (r["sum_cost"] / r["sum_time"]) if neg else float("nan")
+            rec[k, 2] = float(r.get("cycle_len") or len(r.get("cycle") or ())) if neg else 0.0
         rec = rec.to(dev)
-        allrec = torch.empty(world * K_local, 2, dtype=torch.float64, device=dev)
+        allrec = torch.empty(world * K_local, 3, dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allrec, rec, group=group)
         allrec = allrec.cpu().numpy()
         verdict = allrec[:, 0].astype(np.int32)
         ratios = allrec[:, 1].copy()
         lo, hi, have_cycle, best_idx = N.reduce_round(lam, verdict, ratios, lo, hi, have_cycle)
         if best_idx >= 0:
-            best_owner = best_idx // K_local
+            best_owner, best_len = best_idx // K_local, int(allrec[best_idx, 2])
             if best_owner == rank:
-                best = res[best_idx - rank * K_local]
+                best = cycle_of(res, best_idx - rank * K_local)   # before the next probe overwrites it
         if hi - lo <= tol:
             break
     if best_owner < 0:
         # one more try at the upper bound (solver.py:1079-1085); every rank probes, rank 0 owns it
-        r = probe(np.array([hi]), slack, 0)[0]
+        res = probe(np.array([hi]), slack, flags & ~N.F_MONOTONE_PRUNE)
         probes_local += 1
-        if r["verdict"] == N.V_NEG:
-            best_owner, best = 0, r
+        found = torch.zeros(1, dtype=torch.float64)
+        if rank == 0 and res[0]["verdict"] == N.V_NEG:
+            best = cycle_of(res, 0)
+            found[0] = float(len(best[0]))
+        found = found.to(dev)                    # ranks may extract different cycles: rank 0's is the one, and its
+        dist.broadcast(found, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)   # length
+        if int(found.cpu().item()) > 0:
+            best_owner, best_len = 0, int(found.cpu().item())
     if best_owner < 0:
         return ShardedResult([], 0.0, 0.0, float("inf"), iterations, lo, hi, N.ERR_NO_CYCLE, probes_local)
-    # broadcast the winning cycle from its owner
-    head = torch.zeros(3, dtype=torch.float64)
+    # one broadcast of the winning cycle from its owner: [sum_cost, sum_time, v_0 .. v_L-1]; every rank knows L from
+    # the records of the round that produced it
+    msg = torch.zeros(2 + best_len, dtype=torch.float64)
     if rank == best_owner:
-        head[0], head[1], head[2] = float(len(best["cycle"])), best["sum_cost"], best["sum_time"]
-    head = head.to(dev)
+        msg[0], msg[1] = best[1], best[2]
+        msg[2:] = torch.tensor(best[0], dtype=torch.float64)
+    msg = msg.to(dev)
     src = dist.get_global_rank(group, best_owner) if group is not None else best_owner
-    dist.broadcast(head, src=src, group=group)
-    head = head.cpu()
-    L = int(head[0].item())
-    cyc = torch.zeros(L, dtype=torch.int64)
-    if rank == best_owner:
-        cyc[:] = torch.tensor(best["cycle"], dtype=torch.int64)
-    cyc = cyc.to(dev)
-    dist.broadcast(cyc, src=src, group=group)
-    sc, st = float(head[1].item()), float(head[2].item())
+    dist.broadcast(msg, src=src, group=group)
+    msg = msg.cpu()
+    sc, st = float(msg[0].item()), float(msg[1].item())
+    cyc = [int(x) for x in msg[2:].tolist()]
     rc = N.ERR_CONVERGENCE if (it == max_iter - 1 and hi - lo > tol) else N.OK
-    return ShardedResult(cyc.cpu().tolist(), sc, st, sc / st, iterations, lo, hi, rc, probes_local)
+    return ShardedResult(cyc, sc, st, sc / st, iterations, lo, hi, rc, probes_local)
 
 
 def shard_units(n_units: int, rank: int, world: int) -> range:

@@ -533,3 +533,32 @@ def test_stability_region_equals_one_resolve_per_edge(mrc):
     for idx in range(len(U)):
         if (int(U0[idx]), int(V0[idx])) not in on_cycle and C0[idx] > 0:
             assert stab[idx], idx
+
+
+def test_probe_without_cycles_then_fetch_with_sums(mrc):
+    """MRC_F_NO_CYCLES + mrc_fetch_cycle_sums give what a plain probe reports (the multi-GPU driver's path)."""
+    from min_ratio_cycle_b200 import _native as N, synthetic
+    n, U, V, C, T = synthetic.random_float(3000, 20000, seed=2)
+    o = np.argsort(V, kind="stable")
+    g = N.DeviceGraph(n, U[o], V[o], C[o], T[o])
+    lo, hi = g.bounds()
+    star = g.solve_numeric(lo, hi, K=4)["ratio"]
+    lams = [star - 1.0, star + 1e-3, star + 0.5, star + 3.0]
+    full = g.probe_numeric(lams)
+    lean = g.probe_numeric(lams, flags=N.F_NO_CYCLES)
+    assert [p["verdict"] for p in lean] == [p["verdict"] for p in full] == [N.V_NONNEG, N.V_NEG, N.V_NEG, N.V_NEG]
+    for k, p in enumerate(lean):
+        assert p["cycle"] is None
+        if p["verdict"] != N.V_NEG:
+            assert g.fetch_cycle_sums(k)[0] == []
+            continue
+        cyc, sc, st = g.fetch_cycle_sums(k, p["cycle_len"])
+        assert len(cyc) == p["cycle_len"] and cyc[0] == cyc[-1] == min(cyc)
+        assert sc / st < lams[k] and abs(sc / st - p["sum_cost"] / p["sum_time"]) <= 1e-12 * max(1.0, abs(sc / st))
+        # the forward-order sums are the ones recomputed from the edges of the cycle
+        hop = {(int(a), int(b)): (c, t) for a, b, c, t in zip(U, V, C, T)}
+        rc = rt = 0.0
+        for a, b in zip(cyc[:-1], cyc[1:]):
+            rc += hop[(a, b)][0]; rt += hop[(a, b)][1]
+        assert (rc, rt) == (sc, st)
+    g.close()

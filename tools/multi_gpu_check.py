@@ -17,7 +17,7 @@ o = np.argsort(V, kind="stable")
 g = N.DeviceGraph(n, U[o], V[o], C[o], T[o], device=local)
 lo, hi = g.bounds()
 ref = g.solve_numeric(lo, hi, K=4)
-r = sharded.solve_numeric_sharded(lambda l, s, f: g.probe_numeric(l, s, f), lo, hi, K_local=4)
+r = sharded.solve_numeric_sharded(lambda l, s, f: g.probe_numeric(l, s, f), lo, hi, K_local=4, fetch=g.fetch_cycle_sums)
 assert r.rc == N.OK and abs(r.ratio - ref["ratio"]) <= 1e-12, (r.ratio, ref["ratio"])
 assert r.cycle == ref["cycle"], (r.cycle, ref["cycle"])
 graphs = [synthetic.currency_graph(64, 2000 + i) for i in range(64)]
