@@ -176,7 +176,9 @@ int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *m
  * run as worklist passes over the out-edges of just those vertices -- same fixed point, same verdicts; graphs
  * below "sparse_min_edges" (default 1.5 M) keep sweeping; "sparse_look": dense bursts are at most this long while
  * the worklist waits to take over, 0 = chosen by graph size),
- * "prune_above" (0/1, default 1:
+ * "async" (0/1, default 0 or the environment variable MRC_B200_ASYNC: mrc_solve_numeric with K >= 2 refills a
+ * candidate slot the moment its candidate is decided instead of waiting for the round's slowest one; fewer sweeps,
+ * costlier ones -- measured slower on large graphs, see profiles/r01e_policy.txt), "prune_above" (0/1, default 1:
  * with MRC_F_MONOTONE_PRUNE and candidates in increasing order a cycle check stops working on the candidates
  * above the lowest one whose predecessor graph holds a cycle), "patience" (0/1:
  * mrc_solve_numeric passes MRC_F_PATIENCE to its probes).

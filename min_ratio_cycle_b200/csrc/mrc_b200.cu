@@ -91,6 +91,7 @@ struct mrc_graph {
     ll sparse_min_edges = MRC_SPARSE_MIN_EDGES;   // option "sparse_min_edges": smaller graphs sweep densely (launch-bound anyway)
     int sparse_look = 0;         // option "sparse_look": dense bursts are at most this long while the sparse passes wait to take over (0 = by graph size)
     int sparse_bps = 2;          // CTAs per SM of the cooperative sparse kernel (env MRC_B200_SPARSE_BPS, experiments)
+    int async_slots = 0;         // option "async": mrc_solve_numeric refills candidate slots as they are decided (solve_numeric_async)
     int prune_above = 1;         // option "prune_above": cycle checks stop examining candidates above the lowest one with a cycle
     int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
     int patience = 0;            // option "patience": mrc_solve_numeric passes MRC_F_PATIENCE to its probes
@@ -282,6 +283,7 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         }
         g->act_bytes = (((size_t)n + 31) / 32 * 4 + 15) & ~(size_t)15;
         DALLOC(g->d_act[0], g->act_bytes); DALLOC(g->d_act[1], g->act_bytes);
+        if (const char *env = getenv("MRC_B200_ASYNC")) g->async_slots = atoi(env) != 0;   // default of option "async"
         if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
         if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
@@ -976,6 +978,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "frontier_from") g->frontier_from = std::max(1, value);
     else if (s == "narrow") g->narrow = value != 0;
     else if (s == "gate") g->gate = value != 0;
+    else if (s == "async") g->async_slots = value != 0;
     else if (s == "sparse") g->sparse = value != 0;
     else if (s == "sparse_div") g->sparse_div = std::max(1, value);
     else if (s == "sparse_look") g->sparse_look = std::max(0, value);
@@ -1010,6 +1013,220 @@ extern "C" int mrc_reduce_round(int K_total, const double *lam, const int32_t *v
     return MRC_OK;
 }
 
+/*
+ * Asynchronous multisection (option "async", numeric, K >= 2, dense sweeps).  The round-based driver below ends a
+ * round when its slowest candidate is decided, and the slowest is always a non-negative one just below lambda*
+ * (21+ sweeps) while negative candidates finish in 2-6; the K-wide kernel then runs with one or two live slots for
+ * most of its launches.  Here a slot is refilled the moment its candidate is decided or implied: with the certifier
+ * of the best cycle known so far if none is running for it, else with the midpoint of the widest open gap of the
+ * bracket.  Each slot keeps its own pass count and check schedule (2, 6, 14, ... sweeps after its reset); a burst runs
+ * until the first slot is due.  Same verdict logic, same certificate at the end (no negative cycle at ratio - 0.75 tol).
+ */
+static int solve_numeric_async(mrc_graph *g, double lo, double hi, int max_iter, double tol, double slack, int K,
+                               double max_seconds, std::vector<int> &best_cycle, double *best_sc, double *best_st,
+                               int *iterations, double *final_lo, double *final_hi, bool *have_best_out) {
+    CUDA_TRY(cudaSetDevice(g->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const int KT = kt_of(K);
+    const ll n = g->n, m = g->m;
+    g->pot_valid = false;
+    RelaxArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.src = g->d_src; ra.dst = g->d_dst; ra.cost = g->d_cost; ra.time = g->d_time;
+    ra.icost = g->d_icost; ra.itime = g->d_itime; ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = m;
+    ra.slack = slack; ra.n = n; ra.examined = &g->d_status->examined;
+    CheckArgs ca;
+    memset(&ca, 0, sizeof ca);
+    ca.src = g->d_src; ca.cost = g->d_cost; ca.time = g->d_time; ca.icost = g->d_icost; ca.itime = g->d_itime;
+    ca.pred = g->d_pred; ca.dist = g->d_dist; ca.jump = g->d_jump; ca.cyc_edges = g->d_cyc_edges; ca.st = g->d_status;
+    ca.n = n; ca.cap = g->cyc_cap; ca.exact = 0; ca.prune_above = 0;   // slots are in no particular lambda order
+    { int r = 1; while (((ll)1 << r) < n + 1) r++; ca.rounds = std::min(r + 1, MRC_MAX_ROUNDS); }
+    for (int k = 0; k < MRC_KMAX; k++) { ra.pe[k] = ca.pe[k] = -1; }
+
+    struct Slot { bool run = false; double lam = 0; ll passes = 0, due = 0, last_check = 0; bool is_cert = false; double cert_of = 0; };
+    Slot sl[MRC_KMAX];
+    bool have_cycle = false, have_best = false;
+    std::vector<double> probed;            // every lambda started so far (no duplicates)
+    std::vector<int> verts;
+    ll launched = 0;
+    int waves = 0;
+    const ll max_candidates = (ll)std::max(1, max_iter) * K;
+    const bool trace = getenv("MRC_B200_TRACE") != nullptr;
+
+    auto running_mask = [&]() { unsigned mk = 0; for (int k = 0; k < K; k++) if (sl[k].run) mk |= 1u << k; return mk; };
+    auto was_probed = [&](double x) { for (double y : probed) if (y == x) return true; return false; };
+    // next candidate for a free slot, or NAN.  With a cycle in hand (hi = its ratio): the certifier of hi if none is
+    // running, then ONE generation of K-1 speculative candidates per value of hi on a geometric ladder below it,
+    // hi - (hi - lo) / 2^j: the rung just above lambda* yields the biggest Newton step, the rungs below it are
+    // non-negative and cheap as long as they are far from lambda*.  Nothing else is started until hi moves again, so
+    // the certifying sweeps of the final hi run with few live slots and no freshly reset ones.
+    int ladder_left = 0;
+    double ladder_hi = NAN;
+    auto next_candidate = [&](bool *is_cert) -> double {
+        *is_cert = false;
+        const double gap = hi - lo;
+        if (have_cycle) {
+            bool cert_running = false;
+            for (int k = 0; k < K; k++) cert_running |= sl[k].run && sl[k].is_cert && sl[k].cert_of == hi;
+            if (!cert_running) {
+                const double a = tol * 0.75, b = gap / (2.0 * K);
+                const double c = hi - (a < b ? a : b);
+                if (c > lo && !was_probed(c)) { *is_cert = true; return c; }
+            }
+            if (ladder_hi != hi) { ladder_hi = hi; ladder_left = K - 1; }
+            while (ladder_left > 0) {
+                const int j = K - ladder_left;
+                ladder_left--;
+                const double x = hi - gap / (double)(1u << j);
+                if (x > lo && hi - x > tol && !was_probed(x)) return x;
+            }
+            return NAN;
+        }
+        // no cycle yet: midpoint of the widest gap between lo, the running candidates inside (lo, hi) and hi
+        double pts[MRC_KMAX + 2];
+        int np = 0;
+        pts[np++] = lo;
+        for (int k = 0; k < K; k++) if (sl[k].run && sl[k].lam > lo && sl[k].lam < hi) pts[np++] = sl[k].lam;
+        pts[np++] = hi;
+        std::sort(pts, pts + np);
+        double best_w = 0, mid = NAN;
+        for (int i = 0; i + 1 < np; i++)
+            if (pts[i + 1] - pts[i] > best_w) { best_w = pts[i + 1] - pts[i]; mid = pts[i] + 0.5 * (pts[i + 1] - pts[i]); }
+        if (!(best_w > tol) || !(mid > lo && mid < hi) || was_probed(mid)) return NAN;
+        return mid;
+    };
+
+    // the first wave is the reference-like uniform spread of mrc_plan (no cycle known yet)
+    double first[MRC_KMAX];
+    mrc_plan(lo, hi, 0, tol, K, first);
+    int first_left = K;
+    ll P = 0;   // sweeps launched so far
+    for (;;) {
+        if (max_seconds > 0) {
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (el > max_seconds) return set_err(MRC_ERR_TIMEOUT, "Numeric solve exceeded time limit");
+        }
+        // ---- refill
+        unsigned reset_mask = 0;
+        for (int k = 0; k < K; k++) {
+            if (sl[k].run) continue;
+            double x; bool cert = false;
+            if (first_left > 0) { x = first[K - first_left]; first_left--; }
+            else x = next_candidate(&cert);
+            if (!(x == x) || launched >= max_candidates) continue;
+            sl[k] = Slot(); sl[k].run = true; sl[k].lam = x; sl[k].due = 2; sl[k].is_cert = cert; sl[k].cert_of = hi;
+            probed.push_back(x);
+            if (trace) fprintf(stderr, "  [P=%lld] slot %d <- %.9g%s  (lo=%.9g hi=%.12g)\n", (long long)P, k, x, cert ? " cert" : "", lo, hi);
+            ra.lam[k] = ca.lam[k] = x;
+            reset_mask |= 1u << k;
+            launched++;
+        }
+        if (reset_mask) {
+            reset_slots_kernel<<<(int)std::min<ll>((n * KT + 255) / 256, (ll)g->sms * 8), 256, 0, g->stream>>>(
+                g->d_dist, g->d_pred, n, KT, reset_mask);
+            CUDA_TRY(cudaGetLastError());
+            g->stats.other_launches++; g->stats.probes += __builtin_popcount(reset_mask);
+            waves++; g->stats.rounds++;
+        }
+        const unsigned active = running_mask();
+        if (!active) break;   // nothing left to ask and nothing running
+        // ---- burst: until the first slot is due for a cycle check
+        ll nbl = g->burst_max;
+        for (int k = 0; k < K; k++) if (sl[k].run) nbl = std::min(nbl, std::max<ll>(1, sl[k].due - sl[k].passes));
+        const int nb = (int)nbl;
+        CUDA_TRY(cudaMemsetAsync(g->d_status, 0, offsetof(DevStatus, cnt), g->stream));
+        CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
+        ra.active = active;
+        for (int i = 0; i < nb; i++) {
+            ra.changed = &g->d_status->changed[i];
+            ra.reverse = 0; ra.act_out = nullptr;
+            ra.gate = (i > 0 && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
+            MRC_TRY(launch_relax(g, KT, false, ra, false));
+        }
+        CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
+        // slots that are due, and those at least half way to their next check (keeps the checks of out-of-phase slots together)
+        unsigned check_mask = 0;
+        for (int k = 0; k < K; k++) {
+            if (!sl[k].run) continue;
+            const ll p = sl[k].passes + nb;
+            if (p >= sl[k].due || 2 * (p - sl[k].last_check) >= (sl[k].due - sl[k].last_check) || p >= n) check_mask |= 1u << k;
+        }
+        if (check_mask) {
+            ca.active = check_mask;
+            ca.gate = g->gate ? &g->d_status->changed[nb - 1] : nullptr;
+            MRC_TRY(launch_check(g, KT, ca));
+        }
+        CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
+        CUDA_TRY(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->stats.relax_ms += ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
+        const DevStatus &hs = *g->h_status;
+        int ran = nb;
+        if (g->gate) for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
+        g->stats.relax_launches += ran;
+        g->stats.other_launches += nb - ran;
+        g->stats.relax_edge_visits += (int64_t)ran * m * __builtin_popcount(active);
+        g->stats.relax_edge_slots += (int64_t)ran * m * __builtin_popcount(active);
+        if (check_mask) { g->stats.check_launches++; g->stats.false_cycles_cut += hs.cuts; }
+        g->stats.d2h_bytes += sizeof(DevStatus);
+        P += nb;
+        // ---- verdicts
+        for (int k = 0; k < K; k++) {
+            if (!sl[k].run) continue;
+            Slot &s_ = sl[k];
+            int conv_at = -1;
+            for (int i = 0; i < nb && conv_at < 0; i++) if (!((hs.changed[i] >> k) & 1u)) conv_at = i;
+            s_.passes += nb;
+            if (conv_at >= 0) {                                   // fixed point: no negative cycle at lam
+                if (trace) fprintf(stderr, "  [P=%lld] slot %d %.9g NONNEG after %lld\n", (long long)P, k, s_.lam, (long long)(s_.passes - nb + conv_at + 1));
+                if (s_.lam > lo) lo = s_.lam;
+                s_.run = false;
+                continue;
+            }
+            if ((check_mask >> k) & 1u) {
+                s_.last_check = s_.passes;
+                s_.due = 2 * s_.passes + 2;
+                if (((hs.cyc_mask >> k) & 1u) && hs.out[k].found) {
+                    const CycleOut &c = hs.out[k];
+                    const double r = c.sumc / c.sumt;
+                    if (trace) fprintf(stderr, "  [P=%lld] slot %d %.9g %s after %lld len %d r=%.12g\n", (long long)P, k, s_.lam, c.found == 1 ? "NEG" : "TIE", (long long)s_.passes, c.len, r);
+                    if (c.found == 2 && s_.lam > lo) lo = s_.lam;          // tie: lam ~ ratio of that cycle (mrc_reduce)
+                    if (have_cycle ? (r < hi) : (r <= hi)) {               // a better cycle: Newton step of the upper end
+                        ProbeOut o;
+                        o.verdict = c.found == 1 ? MRC_V_NEG : MRC_V_TIE;
+                        o.len = c.len; o.minv = c.minv; o.start = c.pad; o.sumc = c.sumc; o.sumt = c.sumt;
+                        MRC_TRY(fetch_cycle(g, false, k, o, verts, best_sc, best_st, nullptr, nullptr));
+                        best_cycle = verts;
+                        have_best = true;
+                        hi = r; have_cycle = true;
+                    }
+                    s_.run = false;
+                    continue;
+                }
+            }
+            if (s_.passes >= n) {                                 // reference rule :1252-1257: still relaxing after n passes
+                if (s_.lam < hi) { hi = s_.lam; have_cycle = false; }
+                s_.run = false;
+            }
+        }
+        if (lo > hi) lo = hi;   // rounding noise near lambda*
+        // implied verdicts: above the best cycle's ratio -> negative, below a non-negative candidate -> non-negative
+        for (int k = 0; k < K; k++)
+            if (sl[k].run && (sl[k].lam > hi || sl[k].lam < lo)) {
+                if (trace) fprintf(stderr, "  [P=%lld] slot %d %.9g implied after %lld\n", (long long)P, k, sl[k].lam, (long long)sl[k].passes);
+                sl[k].run = false;
+            }
+        if (hi - lo <= tol) break;
+        if (launched >= max_candidates && !running_mask()) break;
+    }
+    *iterations = waves;
+    *final_lo = lo; *final_hi = hi;
+    *have_best_out = have_best;
+    return MRC_OK;
+}
+
 extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_cycle, int max_iter, double tol,
                                  double slack, int K, double max_seconds, double *ratio, double *sum_cost, double *sum_time,
                                  int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len, int32_t *iterations,
@@ -1024,7 +1241,14 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
     double lam[MRC_KMAX], cr[MRC_KMAX];
     int32_t vd[MRC_KMAX];
     ProbeOut res[MRC_KMAX];
-    for (int i = 0; i < max_iter; i++) {
+    const bool use_async = g->async_slots && K >= 2 && !hi_is_cycle && !g->frontier && !g->use_tma[kt_index(kt_of(K))] &&
+                           !(g->sparse && g->m >= g->sparse_min_edges);
+    if (use_async) {
+        MRC_TRY(solve_numeric_async(g, lo, hi, max_iter, tol, slack, K, max_seconds, best_cycle, &best_sc, &best_st, &iters,
+                                    &lo, &hi, &have_best));
+        it = (hi - lo > tol) ? max_iter - 1 : 0;   // for the convergence test of the common tail below
+    }
+    for (int i = 0; i < max_iter && !use_async; i++) {
         it = i;
         if (max_seconds > 0) {   // solver.py:1032-1041
             const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -539,6 +539,15 @@ __global__ void __launch_bounds__(MRC_FRONTIER_THREADS, 1) relax_kernel_frontier
     }
 }
 
+// dist = 0, pred = none for the candidate slots in `mask` only (asynchronous multisection refills one slot while the
+// others keep relaxing)
+__global__ void reset_slots_kernel(void *dist, ull *pred, ll n, int KT, unsigned mask) {
+    ull *d = static_cast<ull *>(dist);   // +0.0 and int64 0 are the same bits
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n * KT; i += (ll)gridDim.x * blockDim.x) {
+        if ((mask >> (int)(i % KT)) & 1u) { __stcg(d + i, 0ull); __stcg(pred + i, ~0ull); }
+    }
+}
+
 // ---- sparse relaxation ------------------------------------------------------------------------------------
 // After a handful of dense sweeps fewer than 1 % of the vertices are still being lowered (C3, certifying probe:
 // 239 k, 82 k, 34 k, 17 k, 9 k, 5.7 k, ... 8 vertices in passes 1..20), and an edge can only relax if its SOURCE was

@@ -51,7 +51,7 @@ def main():
     for seed in [int(s) for s in os.environ.get("MRC_SEEDS", "0").split(",")]:
         n, U, V, C, T = load(n, m, seed)
         g = N.DeviceGraph(n, U, V, C, T)
-        for opt in ("burst_init", "frontier", "frontier_from", "stop_on_neg", "narrow", "gate", "patience", "burst_max", "prune_above", "alternate", "sparse", "sparse_div", "sparse_look"):
+        for opt in ("burst_init", "frontier", "frontier_from", "stop_on_neg", "narrow", "gate", "patience", "burst_max", "prune_above", "alternate", "sparse", "sparse_div", "sparse_look", "async"):
             if os.environ.get("MRC_" + opt.upper()): g.set_option(opt, int(os.environ["MRC_" + opt.upper()]))
         for K in [int(k) for k in os.environ.get("MRC_KS", "4,1").split(",")]:
             for rep in range(2):
