@@ -1083,7 +1083,7 @@ static int solve_numeric_async(mrc_graph *g, double lo, double hi, int max_iter,
             return NAN;
         }
         // no cycle yet: midpoint of the widest gap between lo, the running candidates inside (lo, hi) and hi
-        double pts[MRC_KMAX + 2];
+        double pts[16];   // K + 2 <= 10 used (16: the size std::sort's insertion-sort path is analysed for)
         int np = 0;
         pts[np++] = lo;
         for (int k = 0; k < K; k++) if (sl[k].run && sl[k].lam > lo && sl[k].lam < hi) pts[np++] = sl[k].lam;
