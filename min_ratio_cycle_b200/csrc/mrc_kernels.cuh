@@ -553,7 +553,7 @@ __global__ void reset_slots_kernel(void *dist, ull *pred, ll n, int KT, unsigned
 // 239 k, 82 k, 34 k, 17 k, 9 k, 5.7 k, ... 8 vertices in passes 1..20), and an edge can only relax if its SOURCE was
 // lowered since it was last examined.  From then on a pass only touches the out-edges of the vertices the previous
 // pass lowered: a worklist of vertex ids (deduplicated through a bitmap), an out-edge index by source, 8 lanes per
-// vertex.  One COOPERATIVE launch runs a whole burst of passes (grid sync between passes, ~5 us each instead of a
+// vertex.  One COOPERATIVE launch runs a whole burst of passes (grid sync between passes, 9-12 us each instead of a
 // 60-90 us sweep of the 240 MB edge stream), keeps the per-pass changed words the host's verdict logic reads, and
 // stops on the pass whose worklist is empty -- a true fixed point (every edge was examined after its source's last
 // change), so verdicts, potentials and parity are unchanged.
