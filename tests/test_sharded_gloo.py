@@ -64,6 +64,23 @@ def _worker(rank, world, port, q):
             r = sharded.solve_numeric_sharded(_oracle_probe_factory(o, N), lo, hi, K_local=3)
             ok, why = o.certify(r.cycle, r.ratio)
             res[seed] = (r.rc, r.cycle, r.ratio, r.iterations, r.lo, r.hi, ok, why)
+            # the product path: probes keep their cycles (F_NO_CYCLES), the owner of the best one fetches it afterwards
+            full = _oracle_probe_factory(o, N)
+            stash = {}
+
+            def lean(lams, slack, flags, _full=full, _stash=stash):
+                assert flags & N.F_NO_CYCLES
+                out = _full(lams, slack, flags)
+                _stash.clear()
+                for k, d in enumerate(out):
+                    if d["cycle"] is not None:
+                        _stash[k] = (d["cycle"], d["sum_cost"], d["sum_time"])
+                        d["cycle_len"] = len(d["cycle"])
+                        d["cycle"] = None
+                return out
+
+            r2 = sharded.solve_numeric_sharded(lean, lo, hi, K_local=3, fetch=lambda k, _stash=stash: _stash[k])
+            res[("lean", seed)] = (r2.rc, r2.cycle, r2.ratio, r2.iterations) == (r.rc, r.cycle, r.ratio, r.iterations)
         # acyclic graph: every rank must agree on NO_CYCLE
         U = np.array([0, 1, 2]); V = np.array([1, 2, 3])
         o = oracle.Oracle(4, U, V, np.array([1.5, -2.0, 0.5]), np.array([1.0, 1.0, 2.0]), all_int=False)
@@ -101,5 +118,6 @@ def test_lambda_sharding_world2():
         assert rc == N.OK and ok, why
         assert hi - lo <= 1e-12 and cycle[0] == cycle[-1]
         assert iters <= 12
+        assert got[0][("lean", seed)] and got[1][("lean", seed)], "fetch-after-reduce path differs from the plain one"
     assert got[0]["acyclic"] == got[1]["acyclic"] == N.ERR_NO_CYCLE
     assert got[0]["units"] + got[1]["units"] == list(range(11))
