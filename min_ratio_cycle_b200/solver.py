@@ -72,7 +72,12 @@ class SolverConfig:
     max_memory_mb: int | None = None
     # additive GPU knobs
     gpu_device: int = 0
-    gpu_candidates: int = 4            # lambdas evaluated per relaxation launch (1..8)
+    gpu_candidates: int = 1            # lambdas evaluated per relaxation launch (1..8).  1 = Newton steps on the best cycle's
+                                       # ratio + one certifying probe: on ONE GPU that is 1.5-2.8x faster than 4-way
+                                       # multisection on most graphs (a negative probe costs 2-6 sweeps, a non-negative
+                                       # one next to lambda* 20-100, profiles/r01e_policy.txt section 11); K > 1 is the
+                                       # throughput / multi-GPU configuration (bench.py, sharded.py)
+    gpu_scenarios_per_sweep: int = 4   # sensitivity_analysis: single-edge scenarios that share one edge sweep (1..8)
     gpu_exact_strategy: int = 1        # 0: every Stern-Brocot step probes the GPU; 1: Newton + replay
     gpu_frontier: bool = False         # skip edges whose source was not lowered by the previous pass (same results)
     gpu_sparse: bool = True            # late passes walk only the out-edges of the vertices still being lowered
@@ -708,7 +713,7 @@ class MinRatioCycleSolver:
         # negative cycle there means that cycle is still optimal to within tol -- the answer the sequential path
         # below would give.  Scenarios whose optimum moves (or that touch several edges) fall through to it.
         if warm is not None:
-            K = max(1, min(int(self.config.gpu_candidates), N.KMAX))
+            K = max(1, min(int(self.config.gpu_scenarios_per_sweep), N.KMAX))
             singles = [i for i, sa in enumerate(scen_arrays) if len(sa[0]) == 1]
             for b0 in range(0, len(singles), K):
                 grp = singles[b0: b0 + K]

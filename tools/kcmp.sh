@@ -1,0 +1,3 @@
+for cfg in "100000 2000000 1,2,3,4" "300000 3000000 1,2,3" "30000 300000 1,2,3"; do set -- $cfg
+  MRC_SPARSE=1 MRC_N=$1 MRC_M=$2 MRC_SEEDS=$3 MRC_KS=4,1 MRC_QUIET=1 python tools/trace_solve.py 2>&1 | grep "mrc_solve" | cut -c1-60 | sed "s/^/n=$1 /"
+done
