@@ -302,6 +302,22 @@ def main():
                                "still being lowered a burst walks only their out-edges; same verdicts and ratio, fewer "
                                "relaxations executed, so it is reported beside the dense-sweep headline, not as it"}
         g.set_option("sparse", 0)
+        # ... and Newton-only (K = 1: certifier of the best cycle, nothing else), the Python facade's default on one GPU
+        k1 = {}
+        for name, sp in (("solve_ms", 0), ("solve_ms_sparse", 1)):
+            g.set_option("sparse", sp)
+            for _ in range(2):
+                g.solve_numeric(lo0, hi0, max_iter, tol, slack, K=1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                o4 = g.solve_numeric(lo0, hi0, max_iter, tol, slack, K=1)
+            torch.cuda.synchronize()
+            k1[name] = 1e3 * (time.perf_counter() - t0) / e2e_steps
+            if abs(o4["ratio"] - out["ratio"]) > 1e-9 * max(1.0, abs(out["ratio"])):
+                raise RuntimeError(f"K=1 changed the answer: {o4['ratio']!r} vs {out['ratio']!r}")
+        g.set_option("sparse", 0)
+        sparse_info["k1"] = k1
 
     if rank == 0:
         peak, peak_kind = measured_peak()
