@@ -52,6 +52,7 @@ struct mrc_graph {
     ull *d_pred = nullptr;       // [n][KT] (src vertex << 32 | edge index)
     int *d_jump = nullptr;       // [n][KT]
     int *d_cyc_edges = nullptr;  // [KMAX][cap]
+    int *d_best_edges = nullptr; // [cap] edge list of the best cycle of the running solve (stash_cycle)
     ll cyc_cap = 0;
     DevStatus *d_status = nullptr, *h_status = nullptr;
     int *d_g_src = nullptr; double *d_g_c = nullptr, *d_g_t = nullptr; ll *d_g_ic = nullptr, *d_g_it = nullptr;
@@ -180,7 +181,7 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
         void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
                         g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
                         g->d_keys, g->d_verr, g->d_act[0], g->d_act[1], g->d_out_off, g->d_out_edge,
-                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1]};
+                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
         cudaStreamSynchronize(g->stream);
     }
@@ -772,7 +773,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
  * smallest vertex, and cost/time sums accumulated in that order over the edges Bellman-Ford used.
  */
 static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::vector<int> &verts, double *sc,
-                       double *st, ll *isc, ll *ist) {
+                       double *st, ll *isc, ll *ist, const int *edges = nullptr) {
     const ll L = o.len;
     verts.clear();
     if (L <= 0) return MRC_OK;
@@ -783,7 +784,7 @@ static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::
         DALLOC(g->d_g_ic, (size_t)g->cyc_cap * 8); DALLOC(g->d_g_it, (size_t)g->cyc_cap * 8);
     }
     const int blocks = (int)std::min<ll>((L + 127) / 128, 1024);
-    gather_cycle_kernel<<<blocks, 128, 0, g->stream>>>(g->d_cyc_edges + (ll)k * g->cyc_cap, L, g->d_src, g->d_cost,
+    gather_cycle_kernel<<<blocks, 128, 0, g->stream>>>(edges ? edges : g->d_cyc_edges + (ll)k * g->cyc_cap, L, g->d_src, g->d_cost,
                                                        g->d_time, g->d_icost, g->d_itime, exact, g->d_g_src, g->d_g_c,
                                                        g->d_g_t, g->d_g_ic, g->d_g_it);
     CUDA_TRY(cudaGetLastError());
@@ -828,6 +829,15 @@ static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::
         if (sc) *sc = c;
         if (st) *st = t;
     }
+    return MRC_OK;
+}
+
+// The lambda search only needs the RATIO of a better cycle to go on (the device sums); its edge list is set aside on
+// the device (no host round trip) and brought to the host once, at the end of the solve.
+static int stash_cycle(mrc_graph *g, int k, const ProbeOut &o) {
+    if (o.len > g->cyc_cap) return set_err(MRC_ERR_ARG, "cycle longer than buffer");
+    if (!g->d_best_edges) DALLOC(g->d_best_edges, (size_t)g->cyc_cap * 4);
+    CUDA_TRY(cudaMemcpyAsync(g->d_best_edges, g->d_cyc_edges + (ll)k * g->cyc_cap, (size_t)o.len * 4, cudaMemcpyDeviceToDevice, g->stream));
     return MRC_OK;
 }
 
@@ -1045,7 +1055,8 @@ static int solve_numeric_async(mrc_graph *g, double lo, double hi, int max_iter,
 
     struct Slot { bool run = false; double lam = 0; ll passes = 0, due = 0, last_check = 0; bool is_cert = false; double cert_of = 0; };
     Slot sl[MRC_KMAX];
-    bool have_cycle = false, have_best = false;
+ bool have_cycle = false, have_best = false;
+    ProbeOut best_o;
     std::vector<double> probed;            // every lambda started so far (no duplicates)
     std::vector<int> verts;
     ll launched = 0;
@@ -1197,8 +1208,8 @@ static int solve_numeric_async(mrc_graph *g, double lo, double hi, int max_iter,
                         ProbeOut o;
                         o.verdict = c.found == 1 ? MRC_V_NEG : MRC_V_TIE;
                         o.len = c.len; o.minv = c.minv; o.start = c.pad; o.sumc = c.sumc; o.sumt = c.sumt;
-                        MRC_TRY(fetch_cycle(g, false, k, o, verts, best_sc, best_st, nullptr, nullptr));
-                        best_cycle = verts;
+                        MRC_TRY(stash_cycle(g, k, o));
+                        best_o = o;
                         have_best = true;
                         hi = r; have_cycle = true;
                     }
@@ -1221,6 +1232,10 @@ static int solve_numeric_async(mrc_graph *g, double lo, double hi, int max_iter,
         if (hi - lo <= tol) break;
         if (launched >= max_candidates && !running_mask()) break;
     }
+    if (have_best) {
+        MRC_TRY(fetch_cycle(g, false, 0, best_o, verts, best_sc, best_st, nullptr, nullptr, g->d_best_edges));
+        best_cycle = verts;
+    }
     *iterations = waves;
     *final_lo = lo; *final_hi = hi;
     *have_best_out = have_best;
@@ -1236,7 +1251,8 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<int> best_cycle, verts;
     double best_sc = 0, best_st = 0;
-    bool have_best = false;
+    bool have_best = false, best_pending = false;
+    ProbeOut best_o;
     int have_cycle = hi_is_cycle ? 1 : 0, iters = 0, it = -1;
     double lam[MRC_KMAX], cr[MRC_KMAX];
     int32_t vd[MRC_KMAX];
@@ -1270,11 +1286,15 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
         int best = -1;
         MRC_TRY(mrc_reduce_round(K, lam, vd, cr, &lo, &hi, &have_cycle, &best));
         if (best >= 0) {
-            MRC_TRY(fetch_cycle(g, false, best, res[best], verts, &best_sc, &best_st, nullptr, nullptr));
-            best_cycle = verts;
-            have_best = true;
+            MRC_TRY(stash_cycle(g, best, res[best]));
+            best_o = res[best];
+            have_best = best_pending = true;
         }
         if (hi - lo <= tol) break;   // solver.py:1075-1076
+    }
+    if (best_pending) {
+        MRC_TRY(fetch_cycle(g, false, 0, best_o, verts, &best_sc, &best_st, nullptr, nullptr, g->d_best_edges));
+        best_cycle = verts;
     }
     if (!have_best && hi_is_cycle) {   // the caller's cycle (ratio == the initial hi) was not beaten
         if (iterations) *iterations = iters;
