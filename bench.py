@@ -119,7 +119,13 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle
-    threads = oracle.lib().orc_max_threads()
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make
+    # omp_get_max_threads() report a single-threaded reference arm at N > 1
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    threads = max(threads, oracle.lib().orc_max_threads())
     n, U, V, C, T = make_workload()
     o = oracle.Oracle(n, U, V, C, T, all_int=False, preprocess=False, threads=threads)
     lo, hi = o.bounds()
