@@ -10,7 +10,8 @@ checked by the CPU oracle (which restates the reference and is pinned on the sma
                                 Both search strategies (probe-every-step / Newton+replay) agree on everything.
   C3  numeric, n=1M m=10M f64 : the returned cycle exists, its recomputed ratio equals the reported one, and the
                                 oracle's detector finds NO negative cycle at ratio - 1e-7*max(1,|ratio|)
-                                (certificate C(r) of SURVEY 8c); K = 1, 4, 8 agree to 1e-12.
+                                (certificate C(r) of SURVEY 8c); K = 1, 4, 8, with and without worklist passes,
+                                agree to 1e-12.
   C5  sensitivity, n=100k m=2M: 16 perturbation re-solves each certified the same way against the perturbed graph.
 """
 
@@ -62,15 +63,15 @@ def test_c3_numeric_full_size(S, oracle_mod):
     from min_ratio_cycle_b200 import synthetic
     n, U, V, C, T = synthetic.random_float(1_000_000, 10_000_000, seed=0)
     ratios = []
-    for K in (4, 1, 8):
-        s = S.MinRatioCycleSolver(n, S.SolverConfig(log_level=S.LogLevel.NONE, gpu_candidates=K,
+    for K, sparse in ((4, True), (1, True), (8, True), (4, False), (1, False)):   # worklist passes on (facade default) / off
+        s = S.MinRatioCycleSolver(n, S.SolverConfig(log_level=S.LogLevel.NONE, gpu_candidates=K, gpu_sparse=sparse,
                                                       enable_preprocessing=False))
         s.add_edges_arrays(U, V, C, T)
         r = s.solve(mode="numeric")
         ratios.append(r.ratio)
         assert r.cycle[0] == r.cycle[-1] and cycle_is_valid(r.cycle, U, V)
         assert abs(r.ratio - r.sum_cost / r.sum_time) < 1e-10 and r.sum_time > 0
-        if K == 4:
+        if K == 4 and sparse:
             keep = r
         s._dev.close()
     assert max(ratios) - min(ratios) <= 1e-12
