@@ -162,7 +162,6 @@ def main():
     ap.add_argument("--n", type=int, default=N_VERT)
     ap.add_argument("--m", type=int, default=N_EDGE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frontier", action="store_true", help="enable the active-source filter (not the headline config)")
     ap.add_argument("--sparse", action="store_true", help="run the headline legs with the sparse (worklist) passes on")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -189,8 +188,6 @@ def main():
     pin = [torch.from_numpy(a).pin_memory() for a in (U.astype(np.int32), V.astype(np.int32), C, T)]
     pU, pV, pC, pT = [p.numpy() for p in pin]
     g = N.DeviceGraph(n, pU, pV, pC, pT, device=local_rank)
-    if args.frontier:
-        g.set_option("frontier", 1)
     g.set_option("sparse", 1 if args.sparse else 0)   # headline: dense sweeps (every pass reads every edge, like the reference)
     lo0, hi0 = g.bounds()
     K = args.klocal
@@ -256,8 +253,6 @@ def main():
             barrier()
             t0 = time.perf_counter()
         g2 = N.DeviceGraph(n, pU, pV, pC, pT, device=local_rank)
-        if args.frontier:
-            g2.set_option("frontier", 1)
         g2.set_option("sparse", 1 if args.sparse else 0)
         o2 = one_solve(g2)
         if i >= 1:
@@ -278,7 +273,7 @@ def main():
 
     # ---------------- for information: the same solves with the sparse (worklist) passes the Python facade switches on
     sparse_info = None
-    if world == 1 and not args.sparse and not args.frontier:
+    if world == 1 and not args.sparse:
         g.set_option("sparse", 1)
         for _ in range(2):
             one_solve(g)
@@ -337,9 +332,6 @@ def main():
                 traffic = json.load(fh).get(f"K{K}")
         except Exception:
             pass
-        if args.frontier:
-            # a frontier launch does not read 24 B for every edge: no HBM roofline is claimed for this mode
-            achieved = 0.0
         # for information: the same kernel in steady state (30 launches from dist = 0 at K non-negative lambdas, each
         # timed with its own CUDA-event pair; mean of launches 21-30, i.e. without the atomics-heavy first passes)
         ms30 = g.bench_relax([out["ratio"] - 0.5 - 0.1 * k for k in range(K)], 30)
@@ -350,7 +342,7 @@ def main():
             "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3 random digraph n=1M m=10M f64, numeric multisection", "n": n, "m": m,
-                       "seed": SEED, "lambda_candidates_per_gpu": K, "tolerance": tol, "frontier_filter": bool(args.frontier), "sparse_passes": bool(args.sparse),
+                       "seed": SEED, "lambda_candidates_per_gpu": K, "tolerance": tol, "sparse_passes": bool(args.sparse),
                        "l2": "edge arrays 240 MB > 126 MB L2, streamed every pass (no flush needed)",
                        "parallelism": f"lambda-candidate sharding x{world}"},
             "solve_ms": 1e3 * t_max / args.steps, "ratio": out["ratio"], "rounds": out["iterations"],

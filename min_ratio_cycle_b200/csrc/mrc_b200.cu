@@ -10,10 +10,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "mrc_kernels.cuh"
+#define MRC_MAX_DEVICES 64
 #define MRC_SPARSE_MIN_EDGES 1500000   /* below this a dense sweep is launch-bound (~10 us) and a worklist pass does not pay */
 #include "mrc_search.h"
 #include "mrc_batch.cuh"
@@ -72,13 +74,7 @@ struct mrc_graph {
     bool last_exact = false; int last_K = 0;
     bool scen_on = false; int scen_pe[MRC_KMAX]; double scen_dc[MRC_KMAX], scen_dt[MRC_KMAX];   // scenario batching of the current probe
     int relax_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-    int tma_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     int stop_on_neg = 0;         // option "stop_on_neg": minimum K from which mrc_solve_numeric ends rounds early (0 = never)
-    int frontier = 0;            // option "frontier": passes >= frontier_from use relax_kernel_frontier
-    int frontier_from = 5;
-    unsigned *d_act[2] = {nullptr, nullptr};   // active-vertex bitmaps (previous / current launch)
-    size_t act_bytes = 0;
-    int use_tma[4] = {0, 0, 0, 0};   // per KT index: stream the edges through the TMA-staged kernel (option "tma")
     int check_blocks[4] = {0, 0, 0, 0};
     int burst_init = 2, burst_max = 16;
     // sparse (worklist) passes: out-edge index by source, worklists + membership bitmaps, built on first use
@@ -92,12 +88,14 @@ struct mrc_graph {
     ll sparse_min_edges = MRC_SPARSE_MIN_EDGES;   // option "sparse_min_edges": smaller graphs sweep densely (launch-bound anyway)
     int sparse_look = 0;         // option "sparse_look": dense bursts are at most this long while the sparse passes wait to take over (0 = by graph size)
     int sparse_bps = 2;          // CTAs per SM of the cooperative sparse kernel (env MRC_B200_SPARSE_BPS, experiments)
-    int async_slots = 0;         // option "async": mrc_solve_numeric refills candidate slots as they are decided (solve_numeric_async)
     int prune_above = 1;         // option "prune_above": cycle checks stop examining candidates above the lowest one with a cycle
     int gate = 1;                // option "gate": launches of a burst return at once after a launch that moved nothing
     int patience = 0;            // option "patience": mrc_solve_numeric passes MRC_F_PATIENCE to its probes
     int narrow = 1;              // option "narrow": late passes run the narrowest kernel covering the undecided candidates
-    bool alternate = false;      // option "alternate": flip the sweep direction every pass (measured: more passes, same time per pass)
+    int compact = 1;             // option "compact": a probe narrowed to ONE live slot continues on a compact [n][1] copy of its column
+    ll compact_min_edges = 2000000;   // ... on graphs where a sweep is bandwidth-bound (smaller ones are launch-bound)
+    int lookahead = 1;           // option "lookahead": the next burst is enqueued before the previous burst's status is read
+    void *d_cdist = nullptr; ull *d_cpred = nullptr; int *d_cjump = nullptr;   // compact column (compact survivor)
     mrc_stats stats;
 };
 
@@ -115,29 +113,16 @@ extern "C" int mrc_device_count(int *count) {
 static int kt_of(int K) { return K <= 1 ? 1 : K <= 2 ? 2 : K <= 4 ? 4 : 8; }
 static int kt_index(int KT) { return KT == 1 ? 0 : KT == 2 ? 1 : KT == 4 ? 2 : 3; }
 
-template <int K, bool EXACT> static const void *relax_fn() { return (const void *)relax_kernel<K, EXACT>; }
-static const void *relax_fn_of(int KT, bool exact) {
-    switch (KT) {
-        case 1: return exact ? relax_fn<1, true>() : relax_fn<1, false>();
-        case 2: return exact ? relax_fn<2, true>() : relax_fn<2, false>();
-        case 4: return exact ? relax_fn<4, true>() : relax_fn<4, false>();
-        default: return exact ? relax_fn<8, true>() : relax_fn<8, false>();
-    }
+template <int K> static const void *relax_fn(bool exact, bool scen) {
+    if (exact) return (const void *)relax_kernel<K, true, false>;
+    return scen ? (const void *)relax_kernel<K, false, true> : (const void *)relax_kernel<K, false, false>;
 }
-static const void *relax_tma_fn_of(int KT, bool exact) {
+static const void *relax_fn_of(int KT, bool exact, bool scen = false) {
     switch (KT) {
-        case 1: return exact ? (const void *)relax_kernel_tma<1, true> : (const void *)relax_kernel_tma<1, false>;
-        case 2: return exact ? (const void *)relax_kernel_tma<2, true> : (const void *)relax_kernel_tma<2, false>;
-        case 4: return exact ? (const void *)relax_kernel_tma<4, true> : (const void *)relax_kernel_tma<4, false>;
-        default: return exact ? (const void *)relax_kernel_tma<8, true> : (const void *)relax_kernel_tma<8, false>;
-    }
-}
-static const void *relax_frontier_fn_of(int KT, bool exact) {
-    switch (KT) {
-        case 1: return exact ? (const void *)relax_kernel_frontier<1, true> : (const void *)relax_kernel_frontier<1, false>;
-        case 2: return exact ? (const void *)relax_kernel_frontier<2, true> : (const void *)relax_kernel_frontier<2, false>;
-        case 4: return exact ? (const void *)relax_kernel_frontier<4, true> : (const void *)relax_kernel_frontier<4, false>;
-        default: return exact ? (const void *)relax_kernel_frontier<8, true> : (const void *)relax_kernel_frontier<8, false>;
+        case 1: return relax_fn<1>(exact, scen);
+        case 2: return relax_fn<2>(exact, scen);
+        case 4: return relax_fn<4>(exact, scen);
+        default: return relax_fn<8>(exact, scen);
     }
 }
 static const void *check_fn_of(int KT) {
@@ -149,26 +134,30 @@ static const void *check_fn_of(int KT) {
     }
 }
 
-// Device facts that do not depend on the graph are queried once per process and device.
+// Device facts that do not depend on the graph are queried once per process and device (several graphs, devices and
+// host threads may share the library: one record per device, filled under its own once-flag).
 struct DeviceInfo {
-    bool ready = false;
-    int sms = 0, occ_relax[4][2], occ_tma[4][2], occ_check[4];
+    std::once_flag once;
+    int rc = MRC_OK;
+    std::string err;
+    int sms = 0, occ_relax[4][2], occ_check[4];
 };
-static DeviceInfo g_devinfo[64];
+static DeviceInfo g_devinfo[MRC_MAX_DEVICES];
+static int device_info_fill(int device, DeviceInfo &d) {
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device));
+    for (int KT : {1, 2, 4, 8})
+        for (int ex = 0; ex < 2; ex++) {
+            const int i = kt_index(KT);
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_relax[i][ex], relax_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
+            if (ex == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_check[i], check_fn_of(KT), 256, 0));
+        }
+    return MRC_OK;
+}
 static int device_info(int device, const DeviceInfo **out) {
-    DeviceInfo &d = g_devinfo[device & 63];
-    if (!d.ready) {
-        CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device));
-        for (int KT : {1, 2, 4, 8})
-            for (int ex = 0; ex < 2; ex++) {
-                const int i = kt_index(KT);
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_relax[i][ex], relax_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
-                CUDA_TRY(cudaFuncSetAttribute(relax_tma_fn_of(KT, ex), cudaFuncAttributeMaxDynamicSharedMemorySize, MRC_TMA_SMEM));
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_tma[i][ex], relax_tma_fn_of(KT, ex), MRC_TMA_THREADS, MRC_TMA_SMEM));
-                if (ex == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_check[i], check_fn_of(KT), 256, 0));
-            }
-        d.ready = true;
-    }
+    if (device < 0 || device >= MRC_MAX_DEVICES) return set_err(MRC_ERR_ARG, "device %d out of range", device);
+    DeviceInfo &d = g_devinfo[device];
+    std::call_once(d.once, [&]() { d.rc = device_info_fill(device, d); if (d.rc) d.err = g_mrc_err; });
+    if (d.rc) { g_mrc_err = d.err; return d.rc; }
     *out = &d;
     return MRC_OK;
 }
@@ -180,8 +169,8 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
     if (g->stream) {
         void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
                         g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
-                        g->d_keys, g->d_verr, g->d_act[0], g->d_act[1], g->d_out_off, g->d_out_edge,
-                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges};
+                        g->d_keys, g->d_verr, g->d_out_off, g->d_out_edge,
+                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges, g->d_cdist, g->d_cpred, g->d_cjump};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
         cudaStreamSynchronize(g->stream);
     }
@@ -273,25 +262,16 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
                 const ll chunks = (m + 32 * rows - 1) / (32 * rows);   // one chunk per warp step
                 const ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
                 g->relax_blocks[i][ex] = (int)std::min<ll>(need, (ll)di->occ_relax[i][ex] * g->sms);
-                const ll tiles = (m + MRC_TMA_TILE - 1) / MRC_TMA_TILE;
-                g->tma_blocks[i][ex] = (int)std::max<ll>(1, std::min<ll>(tiles, (ll)std::max(di->occ_tma[i][ex], 1) * g->sms));
                 const ll needc = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
                 g->check_blocks[i] = (int)std::min<ll>(needc, (ll)di->occ_check[i] * g->sms);
             }
-        if (const char *env = getenv("MRC_B200_TMA")) {   // A/B switch for experiments: bit i = KT index i
-            const int mask = atoi(env);
-            for (int i = 0; i < 4; i++) g->use_tma[i] = (mask >> i) & 1;
-        }
-        g->act_bytes = (((size_t)n + 31) / 32 * 4 + 15) & ~(size_t)15;
-        DALLOC(g->d_act[0], g->act_bytes); DALLOC(g->d_act[1], g->act_bytes);
-        if (const char *env = getenv("MRC_B200_ASYNC")) g->async_slots = atoi(env) != 0;   // default of option "async"
         if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
         if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_LOOK")) g->sparse_look = std::max(0, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_MIN_EDGES")) g->sparse_min_edges = atoll(env);   // parity suite: 0
-        if (const char *env = getenv("MRC_B200_FRONTIER"))   // A/B switch for experiments and the parity suite
-            g->frontier = atoi(env) != 0 && g->act_bytes + 2048 <= 227 * 1024;
+        if (const char *env = getenv("MRC_B200_COMPACT_MIN_EDGES")) g->compact_min_edges = atoll(env);   // parity suite: 0
+        if (const char *env = getenv("MRC_B200_LOOKAHEAD")) g->lookahead = atoi(env) != 0;
         // input validation on the device (the host never touches the 24 B/edge again)
         DALLOC(g->d_verr, 4);
         CUDA_TRY(cudaMemsetAsync(g->d_verr, 0, 4, g->stream));
@@ -436,8 +416,7 @@ extern "C" int mrc_graph_restore(mrc_graph *g) {
 // ------------------------------------------------------------------------------------------- probe engine
 // Narrowest kernel that still covers every undecided candidate slot: an aligned sub-range of width 1, 2 or 4 of
 // the KT slots (alignment keeps the 128/256-bit dist loads legal).  Most rounds spend their late passes on a
-// single slow candidate; serving it with the K=1 kernel on the strided layout saves the arithmetic and the
-// registers of the decided ones.
+// single slow candidate; serving it with the K=1 kernel saves the arithmetic and the registers of the decided ones.
 static void narrow_candidates(int KT, unsigned active, int *kc, int *k0) {
     *kc = KT; *k0 = 0;
     for (int w = 1; w < KT; w *= 2)
@@ -463,37 +442,24 @@ static int narrow_args(const mrc_graph *g, int KT, const RelaxArgs &ra_full, Rel
     }
     return kc;
 }
-static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_full, bool frontier_pass = false) {
-    RelaxArgs ra = ra_full;
-    ra.ks = KT; ra.k0 = 0;
-    if (!frontier_pass && !g->use_tma[kt_index(KT)]) {
-        const int kc = narrow_args(g, KT, ra_full, ra);
-        if (kc < KT) {
-            void *nargs[] = {(void *)&ra};
-            const int blocks = g->relax_blocks[kt_index(kc)][exact ? 1 : 0];
-            CUDA_TRY(cudaLaunchKernel(relax_fn_of(kc, exact), dim3(blocks), dim3(MRC_RELAX_THREADS), nargs, 0, g->stream));
-            return MRC_OK;
-        }
-    }
+// Compact survivor: candidate slot `k` of the [n][KT] layout continues on the [n][1] copy of its column.
+static void compact_args(const mrc_graph *g, int k, const RelaxArgs &ra_full, RelaxArgs &ra) {
+    ra = ra_full;
+    ra.dist = g->d_cdist; ra.pred = g->d_cpred; ra.ks = 1; ra.k0 = k; ra.active = 1u;
+    ra.lam[0] = ra_full.lam[k]; ra.a[0] = ra_full.a[k]; ra.b[0] = ra_full.b[k];
+    ra.pe[0] = ra_full.pe[k]; ra.pdc[0] = ra_full.pdc[k]; ra.pdt[0] = ra_full.pdt[k];
+}
+static int launch_relax_args(mrc_graph *g, int kc, bool exact, const RelaxArgs &ra) {
     void *args[] = {(void *)&ra};
-    if (frontier_pass) {
-        const size_t smem = g->act_bytes;
-        static bool attr_set[4][2] = {{false, false}, {false, false}, {false, false}, {false, false}};
-        if (!attr_set[kt_index(KT)][exact ? 1 : 0]) {
-            CUDA_TRY(cudaFuncSetAttribute(relax_frontier_fn_of(KT, exact), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-            attr_set[kt_index(KT)][exact ? 1 : 0] = true;
-        }
-        CUDA_TRY(cudaLaunchKernel(relax_frontier_fn_of(KT, exact), dim3(g->sms), dim3(MRC_FRONTIER_THREADS), args, smem, g->stream));
-        return MRC_OK;
-    }
-    if (g->use_tma[kt_index(KT)]) {
-        CUDA_TRY(cudaLaunchKernel(relax_tma_fn_of(KT, exact), dim3(g->tma_blocks[kt_index(KT)][exact ? 1 : 0]),
-                                  dim3(MRC_TMA_THREADS), args, MRC_TMA_SMEM, g->stream));
-        return MRC_OK;
-    }
-    const int blocks = g->relax_blocks[kt_index(KT)][exact ? 1 : 0];
-    CUDA_TRY(cudaLaunchKernel(relax_fn_of(KT, exact), dim3(blocks), dim3(MRC_RELAX_THREADS), args, 0, g->stream));
+    const int blocks = g->relax_blocks[kt_index(kc)][exact ? 1 : 0];
+    CUDA_TRY(cudaLaunchKernel(relax_fn_of(kc, exact, ra.scen != 0), dim3(blocks), dim3(MRC_RELAX_THREADS), args, 0, g->stream));
     return MRC_OK;
+}
+static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_full, int compact_k = -1) {
+    RelaxArgs ra;
+    if (compact_k >= 0) { compact_args(g, compact_k, ra_full, ra); return launch_relax_args(g, 1, exact, ra); }
+    const int kc = narrow_args(g, KT, ra_full, ra);
+    return launch_relax_args(g, kc, exact, ra);
 }
 static int launch_check(mrc_graph *g, int KT, const CheckArgs &ca) {
     const int blocks = g->check_blocks[kt_index(KT)];
@@ -523,16 +489,25 @@ static int ensure_sparse(mrc_graph *g) {
     g->sparse_ready = true;
     return MRC_OK;
 }
-static int launch_sparse(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_full, int first, int cidx, int npasses) {
+static int launch_sparse(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_full, int first, int cidx, int npasses,
+                         int compact_k = -1) {
     SparseArgs sa;
     memset(&sa, 0, sizeof sa);
-    sa.kc = narrow_args(g, KT, ra_full, sa.r);
+    if (compact_k >= 0) { compact_args(g, compact_k, ra_full, sa.r); sa.kc = 1; }
+    else sa.kc = narrow_args(g, KT, ra_full, sa.r);
     sa.out_off = g->d_out_off; sa.out_edge = g->d_out_edge;
     sa.bm[0] = g->d_bm[0]; sa.bm[1] = g->d_bm[1]; sa.wl[0] = g->d_wl[0]; sa.wl[1] = g->d_wl[1];
     sa.st = g->d_status; sa.first = first; sa.cidx = cidx; sa.npasses = npasses;
     void *args[] = {(void *)&sa};
     const void *fn = exact ? (const void *)relax_sparse_kernel<true> : (const void *)relax_sparse_kernel<false>;
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(g->sparse_blocks[exact ? 1 : 0]), dim3(256), args, 0, g->stream));
+    return MRC_OK;
+}
+static int ensure_compact(mrc_graph *g) {
+    if (g->d_cdist) return MRC_OK;
+    DALLOC(g->d_cdist, (size_t)g->n * 8);
+    DALLOC(g->d_cpred, (size_t)g->n * 8);
+    DALLOC(g->d_cjump, (size_t)g->n * 4);
     return MRC_OK;
 }
 
@@ -551,6 +526,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     if (K < 1 || K > MRC_KMAX) return set_err(MRC_ERR_ARG, "K must be in [1,%d]", MRC_KMAX);
     if (exact && !g->has_int) return set_err(MRC_ERR_NOT_INTEGER, "Exact mode requires integer weights");
     if (exact && !g->patches.empty()) return set_err(MRC_ERR_ARG, "exact probes on a patched graph are not supported");
+    if (!exact && !(slack >= 0.0)) return set_err(MRC_ERR_ARG, "cycle slack must be >= 0");   // dist <= 0 is what makes the bit-pattern atomic a min
     CUDA_TRY(cudaSetDevice(g->device));
     const int KT = kt_of(K);
     const ll n = g->n, m = g->m;
@@ -567,7 +543,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     memset(&ra, 0, sizeof ra);
     ra.src = g->d_src; ra.dst = g->d_dst; ra.cost = g->d_cost; ra.time = g->d_time;
     ra.icost = g->d_icost; ra.itime = g->d_itime; ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = m;
-    ra.slack = slack; ra.n = n; ra.examined = &g->d_status->examined;
+    ra.slack = slack; ra.n = n; ra.examined = &g->d_status->examined; ra.decided = &g->d_status->decided;
     CheckArgs ca;
     memset(&ca, 0, sizeof ca);
     for (int k = 0; k < K; k++) {
@@ -593,6 +569,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
 
     CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)n * KT * 8, g->stream));      // dist = 0 (:1148 / :829)
     CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)n * KT * 8, g->stream));   // pred = none (:1154)
+    CUDA_TRY(cudaMemsetAsync(&g->d_status->decided, 0, sizeof(unsigned), g->stream));
     unsigned active = (1u << K) - 1u;
     const ll max_passes = n;   // n-1 passes + the detection pass
     ll passes = 0;
@@ -602,7 +579,7 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     bool any_neg = false;            // MRC_F_PATIENCE bookkeeping
     int new_verdicts = 0;
     // sparse passes (see relax_sparse_kernel): decided burst by burst from the number of vertices the last pass lowered
-    const bool use_sparse = g->sparse && !g->frontier && m >= g->sparse_min_edges && !g->use_tma[kt_index(KT)];
+    const bool use_sparse = g->sparse && m >= g->sparse_min_edges;
     if (use_sparse) MRC_TRY(ensure_sparse(g));
     bool sparse_mode = false;
     int sp_in = 0, sp_ci = 0;
@@ -610,6 +587,9 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     // compaction, worth it when a sweep costs 60-100 us (m >= 5 M edges), not when it costs 10-25 us
     const int look0 = g->sparse_look > 0 ? g->sparse_look : (m >= 5000000 ? 2 : MRC_MAX_BURST);
     int look = look0;
+    // compact survivor: once ONE candidate is left of a K >= 2 probe its column moves to [n][1] buffers
+    const bool may_compact = g->compact && KT > 1 && m >= g->compact_min_edges;
+    int ck = -1;   // slot served from the compact column, or -1
     while (active) {
         int nb = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
         // while sweeping densely with the sparse passes available, look at the active count every few sweeps:
@@ -620,6 +600,14 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
                 if ((active >> k) & 1u) { res[k].verdict = MRC_V_NEG_NOCYCLE; res[k].passes = passes; }
             break;
         }
+        if (may_compact && ck < 0 && !(active & (active - 1))) {
+            MRC_TRY(ensure_compact(g));
+            ck = __builtin_ctz(active);
+            column_copy_kernel<<<std::min<int>((int)((n + 255) / 256), 8 * g->sms), 256, 0, g->stream>>>(
+                (const ull *)g->d_dist + ck, g->d_pred + ck, KT, (ull *)g->d_cdist, g->d_cpred, 1, n);
+            CUDA_TRY(cudaGetLastError());
+            g->stats.other_launches++;
+        }
         CUDA_TRY(cudaMemsetAsync(g->d_status, 0, offsetof(DevStatus, cnt), g->stream));   // changed[] + examined
         CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
         ra.active = active;
@@ -628,31 +616,22 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         if (sparse_burst) {
             // one cooperative launch runs the nb worklist passes of this burst
             ra.changed = &g->d_status->changed[0];
-            ra.act_out = nullptr; ra.gate = nullptr; ra.reverse = 0;
-            MRC_TRY(launch_sparse(g, KT, exact, ra, sp_in, sp_ci, nb));
+            ra.act_out = nullptr; ra.gate = nullptr;
+            MRC_TRY(launch_sparse(g, KT, exact, ra, sp_in, sp_ci, nb, ck));
             g->bm1_dirty = true;   // either bitmap may now hold bits of a worklist that is never consumed
         }
         for (int i = 0; i < nb && !sparse_burst; i++) {
             ra.changed = &g->d_status->changed[i];
-            ra.reverse = g->alternate ? (int)((passes + i) & 1) : 0;
-            bool fpass = false;
             ra.act_out = nullptr;
-            if (g->frontier) {
-                // bitmap written by launch p is read by launch p+1; launches before frontier_from sweep densely
-                const ll pidx = passes + i;
-                ra.act_out = g->d_act[pidx & 1];
-                ra.act_in = g->d_act[(pidx + 1) & 1];
-                CUDA_TRY(cudaMemsetAsync(ra.act_out, 0, g->act_bytes, g->stream));
-                fpass = pidx + 1 >= g->frontier_from;
-            } else if (use_sparse && i == nb - 1) {
+            if (use_sparse && i == nb - 1) {
                 // the last dense launch of a burst records which vertices it lowered: the seed of a worklist
                 CUDA_TRY(cudaMemsetAsync(g->d_bm[0], 0, g->bm_bytes, g->stream));
                 ra.act_out = g->d_bm[0];
             }
-            if (!fpass) dense_launches++;
-            // launch i > 0 returns at once if launch i-1 moved none of the candidates still open
-            ra.gate = (i > 0 && !g->frontier && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
-            MRC_TRY(launch_relax(g, KT, exact, ra, fpass));
+            dense_launches++;
+            // launch i > 0 skips the candidates launch i-1 did not move (fixed point) and returns at once if that is all of them
+            ra.gate = (i > 0 && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
+            MRC_TRY(launch_relax(g, KT, exact, ra, ck));
         }
         if (use_sparse && !sparse_burst) {
             // bm[1] may hold the membership bits of a worklist nobody consumed (a probe that ended on a verified cycle,
@@ -666,9 +645,18 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
         const bool do_check = passes + nb >= next_check || passes + nb >= max_passes;
         if (do_check) {
-            ca.active = active;
             ca.gate = g->gate ? &g->d_status->changed[nb - 1] : nullptr;
-            MRC_TRY(launch_check(g, KT, ca));
+            if (ck >= 0) {   // the survivor's predecessor graph lives in the compact column: a 1-wide check, results in slot 0
+                CheckArgs cc = ca;
+                cc.pred = g->d_cpred; cc.dist = g->d_cdist; cc.jump = g->d_cjump; cc.cyc_edges = g->d_cyc_edges + (ll)ck * g->cyc_cap;
+                cc.active = 1u; cc.k0 = ck; cc.prune_above = 0;
+                cc.lam[0] = ca.lam[ck]; cc.a[0] = ca.a[ck]; cc.b[0] = ca.b[ck];
+                cc.pe[0] = ca.pe[ck]; cc.pdc[0] = ca.pdc[ck]; cc.pdt[0] = ca.pdt[ck];
+                MRC_TRY(launch_check(g, 1, cc));
+            } else {
+                ca.active = active; ca.k0 = 0;
+                MRC_TRY(launch_check(g, KT, ca));
+            }
             next_check = 2 * next_check + 2;
         }
         CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
@@ -681,16 +669,16 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
         const DevStatus &hs = *g->h_status;
         // launches / passes that did work: the first of the burst, and each one whose predecessor still moved something
         int ran = nb;
-        if (!g->frontier && (g->gate || sparse_burst))
+        if (g->gate || sparse_burst)
             for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
         if (sparse_burst) {
             dense_launches = 0;
             g->stats.sparse_passes += ran;
             g->stats.other_launches += 1;
             sp_in ^= nb & 1; sp_ci = (sp_ci + nb) % 3;
-            if ((ll)hs.act_count * g->sparse_div > 2 * n) sparse_mode = false;   // the frontier grew back: sweep densely again
+            if ((ll)hs.act_count * g->sparse_div > 2 * n) sparse_mode = false;   // the worklist grew back: sweep densely again
         } else {
-            if (!g->frontier) dense_launches = ran;
+            dense_launches = ran;
             g->stats.relax_launches += ran;
             g->stats.other_launches += nb - ran + (use_sparse ? 1 : 0);
             if (use_sparse) {
@@ -700,20 +688,32 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
                 look = scaled > 8 * n ? 8 * look0 : scaled > 4 * n ? 4 * look0 : scaled > 2 * n ? 2 * look0 : look0;
             }
         }
-        g->stats.relax_edge_visits += ((int64_t)dense_launches * m + (int64_t)g->h_status->examined) * __builtin_popcount(active);
-        g->stats.relax_edge_slots += (int64_t)ran * m * __builtin_popcount(active);
-        if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += g->h_status->cuts; }
+        // per-candidate work of the burst: launch i relaxed candidate k iff no earlier launch of the burst had left it unmoved
+        {
+            int64_t slots = 0;
+            for (int k = 0; k < K; k++) {
+                if (!((active >> k) & 1u)) continue;
+                int w = 1;
+                while (w < nb && ((hs.changed[w - 1] >> k) & 1u)) w++;
+                slots += w;
+            }
+            if (sparse_burst) g->stats.relax_edge_visits += (int64_t)hs.examined * __builtin_popcount(active);
+            else g->stats.relax_edge_visits += slots * m;
+            g->stats.relax_edge_slots += slots * m;
+        }
+        if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += hs.cuts; }
         g->stats.d2h_bytes += sizeof(DevStatus);
         for (int k = 0; k < K; k++) {
             if (!((active >> k) & 1u)) continue;
             int conv_at = -1;
             for (int i = 0; i < nb && conv_at < 0; i++) if (!((hs.changed[i] >> k) & 1u)) conv_at = i;
             ProbeOut &o = res[k];
+            const int ko = ck >= 0 ? 0 : k;   // slot of candidate k in the check's output
             if (conv_at >= 0) { o.verdict = MRC_V_NONNEG; o.passes = passes + conv_at + 1; }
-            else if (do_check && ((hs.cyc_mask >> k) & 1u) && hs.out[k].found) {
+            else if (do_check && ((hs.cyc_mask >> ko) & 1u) && hs.out[ko].found) {
                 // the check kernel extracted a cycle and tested it against lambda on the device:
                 // found == 1 verified negative, 2 rounding tie; cycles that are neither were cut there
-                const CycleOut &c = hs.out[k];
+                const CycleOut &c = hs.out[ko];
                 o.verdict = (c.found == 1) ? MRC_V_NEG : MRC_V_TIE;
                 o.len = c.len; o.minv = c.minv; o.start = c.pad; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
                 o.passes = passes + nb;
@@ -949,7 +949,7 @@ extern "C" int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passe
     ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = g->m; ra.slack = 1e-15;
     ra.active = (1u << K) - 1u;
     ra.changed = &g->d_status->changed[0];
-    for (int k = 0; k < K; k++) ra.lam[k] = lam[k];
+    for (int k = 0; k < MRC_KMAX; k++) { ra.lam[k] = k < K ? lam[k] : 0.0; ra.pe[k] = -1; }
     g->pot_valid = false;
     CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)g->n * KT * 8, g->stream));
     CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)g->n * KT * 8, g->stream));
@@ -958,15 +958,7 @@ extern "C" int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passe
     CUDA_TRY(cudaEventRecord(ev[0], g->stream));
     ra.n = g->n; ra.examined = &g->d_status->examined;
     for (int i = 0; i < passes; i++) {
-        ra.reverse = g->alternate ? (i & 1) : 0;
-        bool fpass = false;
-        if (g->frontier) {
-            ra.act_out = g->d_act[i & 1];
-            ra.act_in = g->d_act[(i + 1) & 1];
-            CUDA_TRY(cudaMemsetAsync(ra.act_out, 0, g->act_bytes, g->stream));
-            fpass = i + 1 >= g->frontier_from;
-        }
-        MRC_TRY(launch_relax(g, KT, false, ra, fpass));
+        MRC_TRY(launch_relax(g, KT, false, ra));
         CUDA_TRY(cudaEventRecord(ev[i + 1], g->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(g->stream));
@@ -977,18 +969,12 @@ extern "C" int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passe
 extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     if (!g || !name) return set_err(MRC_ERR_ARG, "NULL argument");
     std::string s(name);
-    if (s == "alternate") g->alternate = value != 0;
-    else if (s == "tma") { for (int i = 0; i < 4; i++) g->use_tma[i] = (value >> i) & 1; }
-    else if (s == "frontier") {
-        if (value && g->act_bytes + 2048 > 227 * 1024)
-            return set_err(MRC_ERR_ARG, "frontier mode keeps n/8 bytes of shared memory per SM: n too large");
-        g->frontier = value != 0;
-    }
-    else if (s == "stop_on_neg") g->stop_on_neg = std::max(0, value);
-    else if (s == "frontier_from") g->frontier_from = std::max(1, value);
+    if (s == "stop_on_neg") g->stop_on_neg = std::max(0, value);
     else if (s == "narrow") g->narrow = value != 0;
+    else if (s == "compact") g->compact = value != 0;
+    else if (s == "compact_min_edges") g->compact_min_edges = std::max(0, value);
+    else if (s == "lookahead") g->lookahead = value != 0;
     else if (s == "gate") g->gate = value != 0;
-    else if (s == "async") g->async_slots = value != 0;
     else if (s == "sparse") g->sparse = value != 0;
     else if (s == "sparse_div") g->sparse_div = std::max(1, value);
     else if (s == "sparse_look") g->sparse_look = std::max(0, value);
@@ -1023,225 +1009,6 @@ extern "C" int mrc_reduce_round(int K_total, const double *lam, const int32_t *v
     return MRC_OK;
 }
 
-/*
- * Asynchronous multisection (option "async", numeric, K >= 2, dense sweeps).  The round-based driver below ends a
- * round when its slowest candidate is decided, and the slowest is always a non-negative one just below lambda*
- * (21+ sweeps) while negative candidates finish in 2-6; the K-wide kernel then runs with one or two live slots for
- * most of its launches.  Here a slot is refilled the moment its candidate is decided or implied: with the certifier
- * of the best cycle known so far if none is running for it, else with the midpoint of the widest open gap of the
- * bracket.  Each slot keeps its own pass count and check schedule (2, 6, 14, ... sweeps after its reset); a burst runs
- * until the first slot is due.  Same verdict logic, same certificate at the end (no negative cycle at ratio - 0.75 tol).
- */
-static int solve_numeric_async(mrc_graph *g, double lo, double hi, int max_iter, double tol, double slack, int K,
-                               double max_seconds, std::vector<int> &best_cycle, double *best_sc, double *best_st,
-                               int *iterations, double *final_lo, double *final_hi, bool *have_best_out) {
-    CUDA_TRY(cudaSetDevice(g->device));
-    const auto t0 = std::chrono::steady_clock::now();
-    const int KT = kt_of(K);
-    const ll n = g->n, m = g->m;
-    g->pot_valid = false;
-    RelaxArgs ra;
-    memset(&ra, 0, sizeof ra);
-    ra.src = g->d_src; ra.dst = g->d_dst; ra.cost = g->d_cost; ra.time = g->d_time;
-    ra.icost = g->d_icost; ra.itime = g->d_itime; ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = m;
-    ra.slack = slack; ra.n = n; ra.examined = &g->d_status->examined;
-    CheckArgs ca;
-    memset(&ca, 0, sizeof ca);
-    ca.src = g->d_src; ca.cost = g->d_cost; ca.time = g->d_time; ca.icost = g->d_icost; ca.itime = g->d_itime;
-    ca.pred = g->d_pred; ca.dist = g->d_dist; ca.jump = g->d_jump; ca.cyc_edges = g->d_cyc_edges; ca.st = g->d_status;
-    ca.n = n; ca.cap = g->cyc_cap; ca.exact = 0; ca.prune_above = 0;   // slots are in no particular lambda order
-    { int r = 1; while (((ll)1 << r) < n + 1) r++; ca.rounds = std::min(r + 1, MRC_MAX_ROUNDS); }
-    for (int k = 0; k < MRC_KMAX; k++) { ra.pe[k] = ca.pe[k] = -1; }
-
-    struct Slot { bool run = false; double lam = 0; ll passes = 0, due = 0, last_check = 0; bool is_cert = false; double cert_of = 0; };
-    Slot sl[MRC_KMAX];
- bool have_cycle = false, have_best = false;
-    ProbeOut best_o;
-    std::vector<double> probed;            // every lambda started so far (no duplicates)
-    std::vector<int> verts;
-    ll launched = 0;
-    int waves = 0;
-    const ll max_candidates = (ll)std::max(1, max_iter) * K;
-    const bool trace = getenv("MRC_B200_TRACE") != nullptr;
-
-    auto running_mask = [&]() { unsigned mk = 0; for (int k = 0; k < K; k++) if (sl[k].run) mk |= 1u << k; return mk; };
-    auto was_probed = [&](double x) { for (double y : probed) if (y == x) return true; return false; };
-    // next candidate for a free slot, or NAN.  With a cycle in hand (hi = its ratio): the certifier of hi if none is
-    // running, then ONE generation of K-1 speculative candidates per value of hi on a geometric ladder below it,
-    // hi - (hi - lo) / 2^j: the rung just above lambda* yields the biggest Newton step, the rungs below it are
-    // non-negative and cheap as long as they are far from lambda*.  Nothing else is started until hi moves again, so
-    // the certifying sweeps of the final hi run with few live slots and no freshly reset ones.
-    int ladder_left = 0;
-    double ladder_hi = NAN;
-    auto next_candidate = [&](bool *is_cert) -> double {
-        *is_cert = false;
-        const double gap = hi - lo;
-        if (have_cycle) {
-            bool cert_running = false;
-            for (int k = 0; k < K; k++) cert_running |= sl[k].run && sl[k].is_cert && sl[k].cert_of == hi;
-            if (!cert_running) {
-                const double a = tol * 0.75, b = gap / (2.0 * K);
-                const double c = hi - (a < b ? a : b);
-                if (c > lo && !was_probed(c)) { *is_cert = true; return c; }
-            }
-            if (ladder_hi != hi) { ladder_hi = hi; ladder_left = K - 1; }
-            while (ladder_left > 0) {
-                const int j = K - ladder_left;
-                ladder_left--;
-                const double x = hi - gap / (double)(1u << j);
-                if (x > lo && hi - x > tol && !was_probed(x)) return x;
-            }
-            return NAN;
-        }
-        // no cycle yet: midpoint of the widest gap between lo, the running candidates inside (lo, hi) and hi
-        double pts[16];   // K + 2 <= 10 used (16: the size std::sort's insertion-sort path is analysed for)
-        int np = 0;
-        pts[np++] = lo;
-        for (int k = 0; k < K; k++) if (sl[k].run && sl[k].lam > lo && sl[k].lam < hi) pts[np++] = sl[k].lam;
-        pts[np++] = hi;
-        std::sort(pts, pts + np);
-        double best_w = 0, mid = NAN;
-        for (int i = 0; i + 1 < np; i++)
-            if (pts[i + 1] - pts[i] > best_w) { best_w = pts[i + 1] - pts[i]; mid = pts[i] + 0.5 * (pts[i + 1] - pts[i]); }
-        if (!(best_w > tol) || !(mid > lo && mid < hi) || was_probed(mid)) return NAN;
-        return mid;
-    };
-
-    // the first wave is the reference-like uniform spread of mrc_plan (no cycle known yet)
-    double first[MRC_KMAX];
-    mrc_plan(lo, hi, 0, tol, K, first);
-    int first_left = K;
-    ll P = 0;   // sweeps launched so far
-    for (;;) {
-        if (max_seconds > 0) {
-            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            if (el > max_seconds) return set_err(MRC_ERR_TIMEOUT, "Numeric solve exceeded time limit");
-        }
-        // ---- refill
-        unsigned reset_mask = 0;
-        for (int k = 0; k < K; k++) {
-            if (sl[k].run) continue;
-            double x; bool cert = false;
-            if (first_left > 0) { x = first[K - first_left]; first_left--; }
-            else x = next_candidate(&cert);
-            if (!(x == x) || launched >= max_candidates) continue;
-            sl[k] = Slot(); sl[k].run = true; sl[k].lam = x; sl[k].due = 2; sl[k].is_cert = cert; sl[k].cert_of = hi;
-            probed.push_back(x);
-            if (trace) fprintf(stderr, "  [P=%lld] slot %d <- %.9g%s  (lo=%.9g hi=%.12g)\n", (long long)P, k, x, cert ? " cert" : "", lo, hi);
-            ra.lam[k] = ca.lam[k] = x;
-            reset_mask |= 1u << k;
-            launched++;
-        }
-        if (reset_mask) {
-            reset_slots_kernel<<<(int)std::min<ll>((n * KT + 255) / 256, (ll)g->sms * 8), 256, 0, g->stream>>>(
-                g->d_dist, g->d_pred, n, KT, reset_mask);
-            CUDA_TRY(cudaGetLastError());
-            g->stats.other_launches++; g->stats.probes += __builtin_popcount(reset_mask);
-            waves++; g->stats.rounds++;
-        }
-        const unsigned active = running_mask();
-        if (!active) break;   // nothing left to ask and nothing running
-        // ---- burst: until the first slot is due for a cycle check
-        ll nbl = g->burst_max;
-        for (int k = 0; k < K; k++) if (sl[k].run) nbl = std::min(nbl, std::max<ll>(1, sl[k].due - sl[k].passes));
-        const int nb = (int)nbl;
-        CUDA_TRY(cudaMemsetAsync(g->d_status, 0, offsetof(DevStatus, cnt), g->stream));
-        CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
-        ra.active = active;
-        for (int i = 0; i < nb; i++) {
-            ra.changed = &g->d_status->changed[i];
-            ra.reverse = 0; ra.act_out = nullptr;
-            ra.gate = (i > 0 && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
-            MRC_TRY(launch_relax(g, KT, false, ra, false));
-        }
-        CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
-        // slots that are due, and those at least half way to their next check (keeps the checks of out-of-phase slots together)
-        unsigned check_mask = 0;
-        for (int k = 0; k < K; k++) {
-            if (!sl[k].run) continue;
-            const ll p = sl[k].passes + nb;
-            if (p >= sl[k].due || 2 * (p - sl[k].last_check) >= (sl[k].due - sl[k].last_check) || p >= n) check_mask |= 1u << k;
-        }
-        if (check_mask) {
-            ca.active = check_mask;
-            ca.gate = g->gate ? &g->d_status->changed[nb - 1] : nullptr;
-            MRC_TRY(launch_check(g, KT, ca));
-        }
-        CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
-        CUDA_TRY(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, g->stream));
-        CUDA_TRY(cudaStreamSynchronize(g->stream));
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->stats.relax_ms += ms;
-        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
-        const DevStatus &hs = *g->h_status;
-        int ran = nb;
-        if (g->gate) for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
-        g->stats.relax_launches += ran;
-        g->stats.other_launches += nb - ran;
-        g->stats.relax_edge_visits += (int64_t)ran * m * __builtin_popcount(active);
-        g->stats.relax_edge_slots += (int64_t)ran * m * __builtin_popcount(active);
-        if (check_mask) { g->stats.check_launches++; g->stats.false_cycles_cut += hs.cuts; }
-        g->stats.d2h_bytes += sizeof(DevStatus);
-        P += nb;
-        // ---- verdicts
-        for (int k = 0; k < K; k++) {
-            if (!sl[k].run) continue;
-            Slot &s_ = sl[k];
-            int conv_at = -1;
-            for (int i = 0; i < nb && conv_at < 0; i++) if (!((hs.changed[i] >> k) & 1u)) conv_at = i;
-            s_.passes += nb;
-            if (conv_at >= 0) {                                   // fixed point: no negative cycle at lam
-                if (trace) fprintf(stderr, "  [P=%lld] slot %d %.9g NONNEG after %lld\n", (long long)P, k, s_.lam, (long long)(s_.passes - nb + conv_at + 1));
-                if (s_.lam > lo) lo = s_.lam;
-                s_.run = false;
-                continue;
-            }
-            if ((check_mask >> k) & 1u) {
-                s_.last_check = s_.passes;
-                s_.due = 2 * s_.passes + 2;
-                if (((hs.cyc_mask >> k) & 1u) && hs.out[k].found) {
-                    const CycleOut &c = hs.out[k];
-                    const double r = c.sumc / c.sumt;
-                    if (trace) fprintf(stderr, "  [P=%lld] slot %d %.9g %s after %lld len %d r=%.12g\n", (long long)P, k, s_.lam, c.found == 1 ? "NEG" : "TIE", (long long)s_.passes, c.len, r);
-                    if (c.found == 2 && s_.lam > lo) lo = s_.lam;          // tie: lam ~ ratio of that cycle (mrc_reduce)
-                    if (have_cycle ? (r < hi) : (r <= hi)) {               // a better cycle: Newton step of the upper end
-                        ProbeOut o;
-                        o.verdict = c.found == 1 ? MRC_V_NEG : MRC_V_TIE;
-                        o.len = c.len; o.minv = c.minv; o.start = c.pad; o.sumc = c.sumc; o.sumt = c.sumt;
-                        MRC_TRY(stash_cycle(g, k, o));
-                        best_o = o;
-                        have_best = true;
-                        hi = r; have_cycle = true;
-                    }
-                    s_.run = false;
-                    continue;
-                }
-            }
-            if (s_.passes >= n) {                                 // reference rule :1252-1257: still relaxing after n passes
-                if (s_.lam < hi) { hi = s_.lam; have_cycle = false; }
-                s_.run = false;
-            }
-        }
-        if (lo > hi) lo = hi;   // rounding noise near lambda*
-        // implied verdicts: above the best cycle's ratio -> negative, below a non-negative candidate -> non-negative
-        for (int k = 0; k < K; k++)
-            if (sl[k].run && (sl[k].lam > hi || sl[k].lam < lo)) {
-                if (trace) fprintf(stderr, "  [P=%lld] slot %d %.9g implied after %lld\n", (long long)P, k, sl[k].lam, (long long)sl[k].passes);
-                sl[k].run = false;
-            }
-        if (hi - lo <= tol) break;
-        if (launched >= max_candidates && !running_mask()) break;
-    }
-    if (have_best) {
-        MRC_TRY(fetch_cycle(g, false, 0, best_o, verts, best_sc, best_st, nullptr, nullptr, g->d_best_edges));
-        best_cycle = verts;
-    }
-    *iterations = waves;
-    *final_lo = lo; *final_hi = hi;
-    *have_best_out = have_best;
-    return MRC_OK;
-}
-
 extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_cycle, int max_iter, double tol,
                                  double slack, int K, double max_seconds, double *ratio, double *sum_cost, double *sum_time,
                                  int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len, int32_t *iterations,
@@ -1257,14 +1024,7 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
     double lam[MRC_KMAX], cr[MRC_KMAX];
     int32_t vd[MRC_KMAX];
     ProbeOut res[MRC_KMAX];
-    const bool use_async = g->async_slots && K >= 2 && !hi_is_cycle && !g->frontier && !g->use_tma[kt_index(kt_of(K))] &&
-                           !(g->sparse && g->m >= g->sparse_min_edges);
-    if (use_async) {
-        MRC_TRY(solve_numeric_async(g, lo, hi, max_iter, tol, slack, K, max_seconds, best_cycle, &best_sc, &best_st, &iters,
-                                    &lo, &hi, &have_best));
-        it = (hi - lo > tol) ? max_iter - 1 : 0;   // for the convergence test of the common tail below
-    }
-    for (int i = 0; i < max_iter && !use_async; i++) {
+    for (int i = 0; i < max_iter; i++) {
         it = i;
         if (max_seconds > 0) {   // solver.py:1032-1041
             const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -15,6 +15,11 @@
 //   pred     u64[n][KT]   (src vertex << 32 | edge index) of the relaxation that last lowered dist, one
 //                       8-byte store so vertex and edge always belong together (cross-warp order is still
 //                       racy by design; cycles are verified on extraction)
+//
+// What bounds the sweep (tools/membench.cu, B200, C3 shape): the bare access pattern -- 24 B/edge stream + one
+// random 8..32-byte gather per edge + the dist[dst] read, no arithmetic -- runs in 53-57 us (stream alone: 32 us).
+// Every scattered lane of a gather is its own L1TEX wavefront (10 M per sweep, ~1 per clock per SM), so an
+// edge-parallel sweep of a random digraph cannot go much below that however few instructions it issues.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -27,13 +32,11 @@ typedef long long ll;
 typedef unsigned long long ull;
 
 #define MRC_MAX_BURST 32
-#ifndef MRC_CROWD_MIN
-#define MRC_CROWD_MIN 6   /* improving lanes per row above which the segmented scan replaces the pairwise loop */
-#endif
 #define MRC_MAX_ROUNDS 40
 #ifndef MRC_RELAX_THREADS
 #define MRC_RELAX_THREADS 256
 #endif
+#define MRC_FULL 0xffffffffu
 
 struct RelaxArgs {
     const int *src, *dst;
@@ -52,15 +55,15 @@ struct RelaxArgs {
     // dist and pred), the host pre-offsets dist/pred/lam/a/b/active/pe.. by the first slot `k0`, and `k0` only
     // shifts the bits of the changed word back.
     int ks, k0;
-    // Convergence gate: the changed word of the PREVIOUS launch of the same burst (NULL for the first).  If that
-    // launch lowered nothing for any candidate this launch serves, every one of them sits at its fixed point and
-    // the launch returns at once -- the host enqueues whole bursts without looking, the device stops on the pass.
+    // Convergence gate: the changed word of the PREVIOUS launch of the same burst (NULL for the first).  A candidate
+    // that launch did not move sits at its fixed point and is skipped; if that holds for every candidate this launch
+    // serves it returns at once -- the host enqueues whole bursts without looking, the device stops on the pass.
     const unsigned *gate;
-    int reverse;         // sweep the edge stream back to front (L2 reuse between consecutive passes)
-    // frontier mode (optional): one bit per vertex, "dist[v] was lowered for some candidate"
-    unsigned *act_out;         // set by this launch (NULL = not tracked)
-    const unsigned *act_in;    // set by the previous launch; read only by relax_kernel_frontier
-    ull *examined;             // edges actually relaxed by relax_kernel_frontier launches
+    // Candidates a cycle check has already decided on the device (DevStatus::decided, bit per slot of the layout):
+    // bursts enqueued before the host has read that check's result skip them.
+    const unsigned *decided;
+    unsigned *act_out;   // one bit per vertex, "dist[v] was lowered for some candidate" (seed of a worklist); NULL = not tracked
+    ull *examined;       // worklist passes: edges actually relaxed
     ll n;
     // scenario batching (numeric only): candidate k sees edge pe[k] with cost + pdc[k], time + pdt[k]
     int scen;
@@ -77,11 +80,14 @@ struct CycleOut {
 
 struct DevStatus {
     unsigned changed[MRC_MAX_BURST];
-    ull examined;                              // frontier launches: edges whose source was active (cleared with `changed`)
+    ull examined;                              // worklist passes: edges relaxed (cleared with `changed`)
     unsigned cnt[MRC_MAX_ROUNDS * MRC_KMAX];   // live vertices per doubling round and candidate
+    int minlive[MRC_MAX_ROUNDS * MRC_KMAX];    // smallest live vertex per doubling round and candidate
     unsigned cyc_mask, rounds_run, pend, cuts;
     int rep[MRC_KMAX * 6];   // [MRC_MAX_EXTRACT][MRC_KMAX]
     CycleOut out[MRC_KMAX];
+    ull sample_best[MRC_KMAX];   // cycle sampling: min over samples of (order key of the cycle ratio, 32 bit) << 32 | start vertex
+    unsigned decided;        // candidates for which this probe's checks reported a cycle (bit per slot); cleared by the host per probe
     unsigned act_count;      // sparse mode: vertices lowered by the last relaxation pass (size of the next worklist)
     unsigned act_cnt[3];     // worklist sizes, rotating: pass p reads [p % 3], appends to [(p+1) % 3], zeroes [(p+2) % 3]
 };
@@ -117,6 +123,8 @@ struct CheckArgs {
     int exact;
     int prune_above;        // candidates are in increasing lambda order and the caller prunes by monotonicity: once the
                             // lowest candidate with a cycle is known, the ones above it are not examined further
+    int k0;                 // first slot of the layout this (possibly narrowed) launch serves: shifts the bits of `decided`
+    int samples;            // cycle sampling: warps per candidate that each walk one cycle of the predecessor graph (0 = off)
     double lam[MRC_KMAX];
     ll a[MRC_KMAX], b[MRC_KMAX];
     int scen;
@@ -151,13 +159,8 @@ template <> struct DistVec<4> {
                      : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3]) : "l"(p));
     }
 };
-template <> struct DistVec<8> {
-    template <typename T> static __device__ __forceinline__ void load(T *r, const T *p) {
-        DistVec<4>::load(r, p); DistVec<4>::load(r + 4, p + 4);
-    }
-};
 
-// ---- one row of 32 consecutive edges, K candidates ------------------------------------------------------
+// ---- arithmetic of one relaxation ----------------------------------------------------------------------
 // numeric: w = cost - lam*time with a rounded product and a rounded difference (no FMA), exactly as
 // NumPy evaluates `self._C - lam * self._T` (solver.py:1144); improve test `cand < dist[v] - slack`
 // (:1161).  dist <= 0 always (starts at +0.0, only decreases), so for negative doubles
@@ -171,7 +174,7 @@ __device__ __forceinline__ ll mrc_cand(const RelaxArgs &p, int k, ll du, ll c, l
 }
 // scenario batching: candidate k re-solves the graph with ONE edge perturbed (sensitivity_analysis, solver.py:1716-1721)
 __device__ __forceinline__ void mrc_scenario_patch(const RelaxArgs &p, int k, int e, double &c, double &t) {
-    if (p.scen && e == p.pe[k]) { c = __dadd_rn(c, p.pdc[k]); t = __dadd_rn(t, p.pdt[k]); }
+    if (e == p.pe[k]) { c = __dadd_rn(c, p.pdc[k]); t = __dadd_rn(t, p.pdt[k]); }
 }
 __device__ __forceinline__ void mrc_scenario_patch(const RelaxArgs &, int, int, ll &, ll &) {}
 __device__ __forceinline__ bool mrc_improves(const RelaxArgs &p, double cand, double dv) {
@@ -180,371 +183,238 @@ __device__ __forceinline__ bool mrc_improves(const RelaxArgs &p, double cand, do
 __device__ __forceinline__ bool mrc_improves(const RelaxArgs &, ll cand, ll dv) { return cand < dv; }
 __device__ __forceinline__ double mrc_identity(double) { return __longlong_as_double(0x7ff0000000000000ll); }
 __device__ __forceinline__ ll mrc_identity(ll) { return 0x7fffffffffffffffll; }
-__device__ __forceinline__ bool mrc_atomic_lower(double *addr, double cand) {
-    const ull bits = (ull)__double_as_longlong(cand);
-    return atomicMax(reinterpret_cast<ull *>(addr), bits) < bits;
+// atomic min in two halves: the request (returns the value it found) and the test "did it lower dist?"
+__device__ __forceinline__ double mrc_atomic_min(double *addr, double cand) {
+    return __longlong_as_double((ll)atomicMax(reinterpret_cast<ull *>(addr), (ull)__double_as_longlong(cand)));
 }
-__device__ __forceinline__ bool mrc_atomic_lower(ll *addr, ll cand) { return cand < atomicMin(addr, cand); }
+__device__ __forceinline__ ll mrc_atomic_min(ll *addr, ll cand) { return atomicMin(addr, cand); }
+__device__ __forceinline__ bool mrc_lowered(double old, double cand) {
+    return (ull)__double_as_longlong(old) < (ull)__double_as_longlong(cand);
+}
+__device__ __forceinline__ bool mrc_lowered(ll old, ll cand) { return cand < old; }
+__device__ __forceinline__ bool mrc_atomic_lower(double *addr, double cand) { return mrc_lowered(mrc_atomic_min(addr, cand), cand); }
+__device__ __forceinline__ bool mrc_atomic_lower(ll *addr, ll cand) { return mrc_lowered(mrc_atomic_min(addr, cand), cand); }
 
-// Crowded row (first passes: many lanes improve): segmented min over the runs of equal destination (prefix-min
-// inside the run, read back from the run's last lane); the lowest lane holding the run minimum keeps `imp`.
-template <typename T>
-__device__ __forceinline__ bool mrc_resolve_crowded(bool imp, T cand, int v, int lane) {
-    const int vprev = __shfl_up_sync(0xffffffffu, v, 1);
-    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || v != vprev);
-    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+// ---- one row of 32 consecutive edges, K candidates ------------------------------------------------------
+// Edges are destination-sorted, so the lanes of a row that share a destination are contiguous: a row is a
+// sequence of RUNS.  Computed once per row (and only when something improves), shared by all K candidates.
+struct RowRuns { int start, end; unsigned mask; };
+__device__ __forceinline__ RowRuns mrc_row_runs(int v, int lane) {
+    const int vprev = __shfl_up_sync(MRC_FULL, v, 1);
+    const unsigned heads = __ballot_sync(MRC_FULL, lane == 0 || v != vprev);
+    RowRuns r;
+    r.start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
     const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
-    const int end = above ? (__ffs(above) - 2) : 31;
-    // inclusive prefix-min inside the run (5 shuffle steps); the run's last lane then holds the run minimum
-    T x = imp ? cand : mrc_identity(T(0));
+    r.end = above ? (__ffs(above) - 2) : 31;
+    r.mask = ((r.end == 31) ? 0xffffffffu : ((2u << r.end) - 1u)) & ~((1u << r.start) - 1u);
+    return r;
+}
+// Several in-edges of one destination sit in adjacent lanes, and in the first passes of a probe several of them
+// would lower dist[v] in the same instruction; if they all issued their atomic, the pred[v] store of a worse
+// candidate could land last, pred would name an edge that did NOT produce dist[v], and the predecessor graph could
+// close cycles that are not negative.  So per destination only ONE lane of the row issues the atomic: the one
+// holding the smallest candidate (which also removes most same-address atomics of the early passes).
+// numeric: an improving candidate is negative (cand < dist[v] - slack <= 0), more negative <=> larger raw bits, so
+// the run minimum is a segmented MAX-scan over the upper 32 bits (one shuffle per step instead of two); lanes that
+// tie there (candidates within 2^-20 of each other) are broken towards the lowest lane -- if that is not the exact
+// minimum, dist[v] receives a slightly larger, still valid value and the true minimum is applied by the next pass.
+__device__ __forceinline__ bool mrc_pick_winner(bool imp, double cand, const RowRuns &r, int lane) {
+    const unsigned hi = (unsigned)((ull)__double_as_longlong(cand) >> 32);
+    unsigned x = imp ? hi : 0u;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        const T a = __shfl_up_sync(0xffffffffu, x, off);
-        if (lane - off >= start && a < x) x = a;
+        const unsigned a = __shfl_up_sync(MRC_FULL, x, off);
+        if (lane - off >= r.start && a > x) x = a;
     }
-    const T runmin = __shfl_sync(0xffffffffu, x, end);
-    const unsigned eq = __ballot_sync(0xffffffffu, imp && cand == runmin);
-    const unsigned runmask = ((end == 31) ? 0xffffffffu : ((2u << end) - 1u)) & ~((1u << start) - 1u);
-    return imp && (__ffs(eq & runmask) - 1 == lane);
+    const unsigned runmax = __shfl_sync(MRC_FULL, x, r.end);
+    const unsigned eq = __ballot_sync(MRC_FULL, imp && hi == runmax);
+    return imp && (__ffs(eq & r.mask) - 1 == lane);
+}
+// exact: full 64-bit segmented min, lowest lane on ties (the reference's first-occurrence rule inside a row)
+__device__ __forceinline__ bool mrc_pick_winner(bool imp, ll cand, const RowRuns &r, int lane) {
+    ll x = imp ? cand : mrc_identity(ll(0));
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const ll a = __shfl_up_sync(MRC_FULL, x, off);
+        if (lane - off >= r.start && a < x) x = a;
+    }
+    const ll runmin = __shfl_sync(MRC_FULL, x, r.end);
+    const unsigned eq = __ballot_sync(MRC_FULL, imp && cand == runmin);
+    return imp && (__ffs(eq & r.mask) - 1 == lane);
 }
 
-// The row is warp-synchronous: every lane calls it (valid == false for lanes past the end).  Several
-// in-edges of one destination sit in adjacent lanes, and in the first passes several of them would lower
-// dist[v] in the same instruction; if they all issued their atomic, the pred[v] store of a worse
-// candidate could land last, pred would name an edge that did NOT produce dist[v], and the predecessor
-// graph could close cycles that are not negative.  So per destination only the lane with the smallest
-// candidate of the row issues the atomic (which also removes most same-address atomics of the early
-// passes).  Control flow never waits for an atomic's return value; rows in which nothing improves
-// (almost all rows after the first passes) cost one ballot per candidate.
-template <int K, typename T>
-__device__ __forceinline__ void relax_row(const RelaxArgs &p, bool valid, int lane, int e, int u, int v, T c, T t,
-                                          unsigned &chg) {
+// The row is warp-synchronous: every lane calls it (valid == false for lanes past the end).  Steady state (nothing
+// improves, almost every row after the first passes): two gathers, 4 flops + one compare per candidate, ONE vote.
+// Control flow never waits for an atomic's return value before all atomics of the row are in flight.
+template <int K, typename T, bool SCEN>
+__device__ __forceinline__ void relax_row(const RelaxArgs &p, unsigned act, bool valid, int lane, unsigned e, int u, int v,
+                                          T c, T t, unsigned &chg) {
     // K = 8 is processed as two halves of 4 candidates (two 256-bit gathers from the same 64-B group, one after
-    // the other), so its register footprint stays that of K = 4 and 4 CTAs remain resident per SM.
+    // the other), so its register footprint stays that of K = 4.
     constexpr int H = K > 4 ? 4 : K;
     T *dist = static_cast<T *>(p.dist);
 #pragma unroll
     for (int h = 0; h < K; h += H) {
-    if (!((p.active >> h) & ((1u << H) - 1u))) continue;   // warp-uniform: nothing active in this half
-    T du[H], dv[H];
-    if (valid) {
-        DistVec<H>::load(du, dist + (size_t)u * p.ks + h);
-        DistVec<H>::load(dv, dist + (size_t)v * p.ks + h);
-    }
-#pragma unroll
-    for (int k = h; k < h + H; k++) {
-        if (!((p.active >> k) & 1u)) continue;   // warp-uniform
-        T cand = 0;
-        bool imp = false;
+        const unsigned acth = (act >> h) & ((1u << H) - 1u);
+        if (!acth) continue;   // warp-uniform: nothing active in this half
+        T du[H], dv[H], cand[H];
         if (valid) {
+            DistVec<H>::load(du, dist + (size_t)u * p.ks + h);
+            DistVec<H>::load(dv, dist + (size_t)v * p.ks + h);
+        }
+        bool imp[H], any = false;
+#pragma unroll
+        for (int k = 0; k < H; k++) {
             T ck = c, tk = t;
-            mrc_scenario_patch(p, k, e, ck, tk);
-            cand = mrc_cand(p, k, du[k - h], ck, tk);
-            imp = mrc_improves(p, cand, dv[k - h]);
+            if (SCEN) mrc_scenario_patch(p, h + k, (int)e, ck, tk);
+            cand[k] = mrc_cand(p, h + k, du[k], ck, tk);
+            imp[k] = valid && ((acth >> k) & 1u) && mrc_improves(p, cand[k], dv[k]);
+            any |= imp[k];
         }
-        const unsigned im = __ballot_sync(0xffffffffu, imp);
-        if (im == 0) continue;                   // warp-uniform
-        const int nimp = __popc(im);
-        if (nimp > MRC_CROWD_MIN) {
-            imp = mrc_resolve_crowded<T>(imp, cand, v, lane);
-        } else if (nimp > 1) {
-            bool lose = false;
-            unsigned rest = im;
-            while (rest) {
-                const int l = __ffs(rest) - 1;
-                rest &= rest - 1;
-                const int vl = __shfl_sync(0xffffffffu, v, l);
-                const T cl = __shfl_sync(0xffffffffu, cand, l);
-                if (l != lane && vl == v && (cl < cand || (cl == cand && l < lane))) lose = true;
+        if (!__any_sync(MRC_FULL, any)) continue;   // warp-uniform
+        // ---- some lane improves some candidate: one winner per destination and candidate
+        const RowRuns rr = mrc_row_runs(valid ? v : -1 - lane, lane);
+        unsigned wins = 0;
+#pragma unroll
+        for (int k = 0; k < H; k++) {
+            const unsigned im = __ballot_sync(MRC_FULL, imp[k]);
+            if (im == 0) continue;               // warp-uniform
+            bool w = imp[k];
+            if (im & (im - 1)) w = mrc_pick_winner(imp[k], cand[k], rr, lane);
+            if (w) wins |= 1u << k;
+        }
+        T old[H];
+#pragma unroll
+        for (int k = 0; k < H; k++)
+            if ((wins >> k) & 1u) old[k] = mrc_atomic_min(dist + (size_t)v * p.ks + h + k, cand[k]);
+        bool lowered = false;
+#pragma unroll
+        for (int k = 0; k < H; k++)
+            if (((wins >> k) & 1u) && mrc_lowered(old[k], cand[k])) {
+                __stcg(p.pred + (size_t)v * p.ks + h + k, ((ull)(unsigned)u << 32) | e);
+                chg |= 1u << (h + k);
+                lowered = true;
             }
-            imp = imp && !lose;
-        }
-        if (imp && mrc_atomic_lower(dist + (size_t)v * p.ks + k, cand)) {
-            __stcg(p.pred + (size_t)v * p.ks + k, ((ull)(unsigned)u << 32) | (unsigned)e);
-            if (p.act_out) atomicOr(p.act_out + (v >> 5), 1u << (v & 31));
-            chg |= 1u << k;
-        }
-    }
+        if (lowered && p.act_out) atomicOr(p.act_out + (v >> 5), 1u << (v & 31));
     }
 }
 
 template <bool EXACT> struct WeightT { typedef double type; };
 template <> struct WeightT<true> { typedef ll type; };
 
-// Edge-parallel relaxation.  A warp owns MRC_ROWS rows of 32 CONSECUTIVE edges per step; lane i takes edge
+// Edge-parallel relaxation.  A warp owns ROWS rows of 32 CONSECUTIVE edges per step; lane i takes edge
 // base + 32*j + i, so every edge-stream load is one fully coalesced 128/256-B request and -- because
 // the edges are destination-sorted -- the 32 dist[dst] reads of a row collapse to one or two lines.
 // What remains is exactly one random line per edge (dist[src]); the kernel is bound by that L1TEX
 // gather rate and by the 24 B/edge HBM stream.  Persistent grid: occupancy x 148 SMs, warps walk
 // consecutive chunks so DRAM pages are streamed in order.
-// Tuned on B200 (tools/relax_variants.py, profiles/r01_relax_variants.txt): K <= 4 wants 2 rows per warp
-// step and 4 resident CTAs per SM (64 registers); K = 8 carries 2 x 64 B of dist per edge and is faster
-// with 4 rows and no register cap.
 #ifndef MRC_TUNE_ROWS
 #define MRC_TUNE_ROWS 2
 #endif
 #ifndef MRC_TUNE_MB
 #define MRC_TUNE_MB 4
 #endif
+#ifndef MRC_TUNE_MB12
+#define MRC_TUNE_MB12 4
+#endif
 #ifndef MRC_TUNE_PF
 #define MRC_TUNE_PF (K <= 2)
 #endif
-#ifndef MRC_TUNE_ROWS8
-#define MRC_TUNE_ROWS8 2
-#endif
-#ifndef MRC_TUNE_MB8
-#define MRC_TUNE_MB8 4
-#endif
-#ifndef MRC_TUNE_STAGE
-#define MRC_TUNE_STAGE false   /* measured slower than plain loads at every K (profiles/r01_relax_variants.txt) */
-#endif
-#ifndef MRC_TUNE_DEPTH
-#define MRC_TUNE_DEPTH 3
-#endif
 template <int K> struct RelaxTune {
-    static constexpr int rows = MRC_TUNE_ROWS, minblocks = MRC_TUNE_MB;
+    static constexpr int rows = MRC_TUNE_ROWS, minblocks = K <= 2 ? MRC_TUNE_MB12 : MRC_TUNE_MB;
+    // K <= 2 (registers to spare): the edge stream of the NEXT chunk is requested before this chunk's gathers are
+    // issued, so the HBM latency of the stream overlaps the L2 latency of the dist gathers (-8 % per pass at K = 1)
     static constexpr bool prefetch = MRC_TUNE_PF;
-    static constexpr bool stage = MRC_TUNE_STAGE;   // edge stream through a per-warp cp.async ring in shared memory
 };
-template <> struct RelaxTune<8> {
-    static constexpr int rows = MRC_TUNE_ROWS8, minblocks = MRC_TUNE_MB8;
-    static constexpr bool prefetch = false;
-    static constexpr bool stage = false;
-};
-__device__ __forceinline__ void mrc_cp_async4(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void mrc_cp_async8(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void mrc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void mrc_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-template <int K, bool EXACT>
+template <int K, bool EXACT, bool SCEN>
 __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) relax_kernel(const __grid_constant__ RelaxArgs p) {
     typedef typename WeightT<EXACT>::type W;
     const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
     const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
-    if (p.gate && !((__ldcg(p.gate) >> p.k0) & p.active)) return;
+    unsigned act = p.active;
+    if (p.decided) act &= ~(__ldcg(p.decided) >> p.k0);
+    if (p.gate) act &= __ldcg(p.gate) >> p.k0;
+    if (!act) return;
     unsigned chg = 0;
     const int lane = threadIdx.x & 31;
-    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    constexpr int MRC_ROWS = RelaxTune<K>::rows;
-    constexpr ll CH = 32 * MRC_ROWS;
-    const ll nchunks = (p.m + CH - 1) / CH;
-    // K <= 2 (registers to spare): the edge stream of the NEXT chunk is requested before this chunk's
-    // gathers are issued, so the HBM latency of the stream overlaps the L2 latency of the dist gathers.
-    // (Measured on B200, profiles/r01_relax_variants.txt: -8% per pass at K=1; at K>=4 the extra registers
-    // cost more occupancy than the overlap wins.  Hoisting all gathers of a chunk ahead of the first use
-    // was also measured and is slower at every K.)
-    constexpr bool PREFETCH = RelaxTune<K>::prefetch;
-    if constexpr (RelaxTune<K>::stage) {
-        // EXPERIMENT, off by default.  Stall sampling put 2/3 of the memory stalls on the first use of the edge
-        // stream, not on the gathers, so here every warp keeps its own DEPTH-deep ring of chunks in shared
-        // memory, filled with cp.async (LDGSTS: no registers, no block barrier).  Measured: 88 us (K=4) and
-        // 71 us (K=1) per launch against 74 / 58 us for plain loads on the same box -- the LDGSTS issue cost and
-        // the extra shared-memory round trip outweigh the overlap.
-        constexpr int D = MRC_TUNE_DEPTH;
-        constexpr int WARPS = MRC_RELAX_THREADS / 32;
-        __shared__ int s_src[WARPS][D][MRC_ROWS][32], s_dst[WARPS][D][MRC_ROWS][32];
-        __shared__ W s_cost[WARPS][D][MRC_ROWS][32], s_time[WARPS][D][MRC_ROWS][32];
-        const int w = threadIdx.x >> 5;
-        auto issue = [&](ll c, int slot) {
-            if (c < nchunks) {
-                const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int ROWS = RelaxTune<K>::rows;
+    constexpr unsigned CH = 32 * ROWS;
+    const unsigned m = (unsigned)p.m;
+    const unsigned nchunks = (m + CH - 1) / CH, nfull = m / CH;   // chunks [0, nfull) need no bounds checks
+    auto tail = [&](unsigned c) {   // the one partial chunk
 #pragma unroll
-                for (int j = 0; j < MRC_ROWS; j++) {
-                    const ll e = e0 + 32 * j;
-                    if (e < p.m) {
-                        mrc_cp_async4(&s_src[w][slot][j][lane], p.src + e);
-                        mrc_cp_async4(&s_dst[w][slot][j][lane], p.dst + e);
-                        mrc_cp_async8(&s_cost[w][slot][j][lane], cost + e);
-                        mrc_cp_async8(&s_time[w][slot][j][lane], time + e);
-                    }
-                }
-            }
-            mrc_cp_async_commit();
-        };
-#pragma unroll
-        for (int d = 0; d < D - 1; d++) issue(warp + (ll)d * nwarps, d);
-        int slot = 0;
-        for (ll c = warp; c < nchunks; c += nwarps) {
-            int nslot = slot + D - 1;
-            if (nslot >= D) nslot -= D;
-            issue(c + (ll)(D - 1) * nwarps, nslot);
-            mrc_cp_async_wait<D - 1>();
-            __syncwarp();
-            const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
-            if (e0 - lane + CH <= p.m) {
-#pragma unroll
-                for (int j = 0; j < MRC_ROWS; j++)
-                    relax_row<K, W>(p, true, lane, (int)(e0 + 32 * j), s_src[w][slot][j][lane], s_dst[w][slot][j][lane],
-                                    s_cost[w][slot][j][lane], s_time[w][slot][j][lane], chg);
-            } else {
-#pragma unroll
-                for (int j = 0; j < MRC_ROWS; j++) {
-                    const ll e = e0 + 32 * j;
-                    const bool ok = e < p.m;
-                    relax_row<K, W>(p, ok, lane, (int)e, ok ? s_src[w][slot][j][lane] : 0,
-                                    ok ? s_dst[w][slot][j][lane] : -1 - lane, ok ? s_cost[w][slot][j][lane] : W(0),
-                                    ok ? s_time[w][slot][j][lane] : W(0), chg);
-                }
-            }
-            __syncwarp();
-            slot = slot + 1 == D ? 0 : slot + 1;
+        for (int j = 0; j < ROWS; j++) {
+            const unsigned e = c * CH + 32 * j + lane;
+            const bool ok = e < m;
+            relax_row<K, W, SCEN>(p, act, ok, lane, e, ok ? p.src[e] : 0, ok ? p.dst[e] : 0, ok ? cost[e] : W(0),
+                                  ok ? time[e] : W(0), chg);
         }
-    } else if constexpr (!PREFETCH) {
-        for (ll c = warp; c < nchunks; c += nwarps) {
-            const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
-            if (e0 - lane + CH <= p.m) {
-                int s[MRC_ROWS], d[MRC_ROWS];
-                W cs[MRC_ROWS], tm[MRC_ROWS];
+    };
+    if constexpr (!RelaxTune<K>::prefetch) {
+        for (unsigned c = warp; c < nchunks; c += nwarps) {
+            if (c >= nfull) { tail(c); break; }
+            const unsigned e0 = c * CH + lane;
+            int s[ROWS], d[ROWS];
+            W cs[ROWS], tm[ROWS];
 #pragma unroll
-                for (int j = 0; j < MRC_ROWS; j++) {
-                    const ll e = e0 + 32 * j;
-                    s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
-                    cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
-                }
-#pragma unroll
-                for (int j = 0; j < MRC_ROWS; j++)
-                    relax_row<K, W>(p, true, lane, (int)(e0 + 32 * j), s[j], d[j], cs[j], tm[j], chg);
-            } else {
-#pragma unroll
-                for (int j = 0; j < MRC_ROWS; j++) {
-                    const ll e = e0 + 32 * j;
-                    const bool ok = e < p.m;
-                    relax_row<K, W>(p, ok, lane, (int)e, ok ? p.src[e] : 0, ok ? p.dst[e] : -1 - lane,
-                                    ok ? cost[e] : W(0), ok ? time[e] : W(0), chg);
-                }
+            for (int j = 0; j < ROWS; j++) {
+                const unsigned e = e0 + 32 * j;
+                s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
+                cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
             }
+#pragma unroll
+            for (int j = 0; j < ROWS; j++)
+                relax_row<K, W, SCEN>(p, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg);
         }
     } else {
-    int s[MRC_ROWS], d[MRC_ROWS], s2[MRC_ROWS], d2[MRC_ROWS];
-    W cs[MRC_ROWS], tm[MRC_ROWS], cs2[MRC_ROWS], tm2[MRC_ROWS];
-    auto chunk_base = [&](ll c) { return (p.reverse ? (nchunks - 1 - c) : c) * CH; };
-    auto is_full = [&](ll c) { return c < nchunks && chunk_base(c) + CH <= p.m; };
-    ll c = warp;
-    bool have = PREFETCH && is_full(c);
-    if (have) {
-        const ll e0 = chunk_base(c) + lane;
+        int s[ROWS], d[ROWS], s2[ROWS], d2[ROWS];
+        W cs[ROWS], tm[ROWS], cs2[ROWS], tm2[ROWS];
+        unsigned c = warp;
+        if (c < nfull) {
+            const unsigned e0 = c * CH + lane;
 #pragma unroll
-        for (int j = 0; j < MRC_ROWS; j++) {
-            const ll e = e0 + 32 * j;
-            s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
-            cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
-        }
-    }
-    while (c < nchunks) {
-        const ll nx = c + nwarps;
-        const bool have2 = PREFETCH && is_full(nx);
-        if (have2) {
-            const ll e0 = chunk_base(nx) + lane;
-#pragma unroll
-            for (int j = 0; j < MRC_ROWS; j++) {
-                const ll e = e0 + 32 * j;
-                s2[j] = __ldcs(p.src + e); d2[j] = __ldcs(p.dst + e);
-                cs2[j] = __ldcs(cost + e); tm2[j] = __ldcs(time + e);
+            for (int j = 0; j < ROWS; j++) {
+                const unsigned e = e0 + 32 * j;
+                s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
+                cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
             }
         }
-        const ll e0 = chunk_base(c) + lane;
-        if (e0 - lane + CH <= p.m) {   // full chunk: no per-lane validity predicate anywhere
-            if (!have) {
+        while (c < nchunks) {
+            if (c >= nfull) { tail(c); break; }
+            const unsigned nx = c + nwarps;
+            if (nx < nfull) {
+                const unsigned e0 = nx * CH + lane;
 #pragma unroll
-                for (int j = 0; j < MRC_ROWS; j++) {
-                    const ll e = e0 + 32 * j;
-                    s[j] = __ldcs(p.src + e); d[j] = __ldcs(p.dst + e);
-                    cs[j] = __ldcs(cost + e); tm[j] = __ldcs(time + e);
+                for (int j = 0; j < ROWS; j++) {
+                    const unsigned e = e0 + 32 * j;
+                    s2[j] = __ldcs(p.src + e); d2[j] = __ldcs(p.dst + e);
+                    cs2[j] = __ldcs(cost + e); tm2[j] = __ldcs(time + e);
                 }
             }
+            const unsigned e0 = c * CH + lane;
 #pragma unroll
-            for (int j = 0; j < MRC_ROWS; j++)
-                relax_row<K, W>(p, true, lane, (int)(e0 + 32 * j), s[j], d[j], cs[j], tm[j], chg);
-        } else {
+            for (int j = 0; j < ROWS; j++)
+                relax_row<K, W, SCEN>(p, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg);
 #pragma unroll
-            for (int j = 0; j < MRC_ROWS; j++) {
-                const ll e = e0 + 32 * j;
-                const bool ok = e < p.m;
-                relax_row<K, W>(p, ok, lane, (int)e, ok ? p.src[e] : 0, ok ? p.dst[e] : -1 - lane, ok ? cost[e] : W(0),
-                                ok ? time[e] : W(0), chg);
-            }
+            for (int j = 0; j < ROWS; j++) { s[j] = s2[j]; d[j] = d2[j]; cs[j] = cs2[j]; tm[j] = tm2[j]; }
+            c = nx;
         }
-        if (PREFETCH) {
-#pragma unroll
-            for (int j = 0; j < MRC_ROWS; j++) { s[j] = s2[j]; d[j] = d2[j]; cs[j] = cs2[j]; tm[j] = tm2[j]; }
-        }
-        have = have2;
-        c = nx;
-    }
     }
     // changed flag: warp vote, one atomic per warp at most
-    chg = __reduce_or_sync(0xffffffffu, chg);
+    chg = __reduce_or_sync(MRC_FULL, chg);
     if (lane == 0 && chg) atomicOr(p.changed, chg << p.k0);
 }
 
-// ---- frontier relaxation ------------------------------------------------------------------------------
-// After the first passes only a few per cent of the vertices still change, and an edge can only improve
-// its destination if its SOURCE was lowered since the edge was last looked at.  This variant keeps the
-// edge-parallel sweep but consults a one-bit-per-vertex "lowered in the previous launch" map, held in
-// shared memory (n/8 bytes, one 1024-thread CTA per SM): a row of 32 edges whose sources are all inactive
-// costs 128 B of src stream and nothing else; dst/cost/time and the dist gathers are issued for active lanes
-// only.  A launch that lowers nothing is still a true fixed point (an edge skipped now was examined after its
-// source's last change), so verdicts, potentials and parity are unchanged.  Requires n <= 8 * (smem - 1 KB).
-#define MRC_FRONTIER_THREADS 1024
-#ifndef MRC_FRONTIER_ROWS
-#define MRC_FRONTIER_ROWS 8
-#endif
-template <int K, bool EXACT>
-__global__ void __launch_bounds__(MRC_FRONTIER_THREADS, 1) relax_kernel_frontier(const __grid_constant__ RelaxArgs p) {
-    typedef typename WeightT<EXACT>::type W;
-    extern __shared__ __align__(16) unsigned s_act[];
-    const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
-    const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
-    const int words = (int)((p.n + 31) >> 5);
-    for (int i = threadIdx.x; i < words; i += MRC_FRONTIER_THREADS) s_act[i] = __ldcg(p.act_in + i);
-    __syncthreads();
-    unsigned chg = 0, seen = 0;
-    const int lane = threadIdx.x & 31;
-    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const ll nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
-    constexpr int R = MRC_FRONTIER_ROWS;
-    constexpr ll CH = 32 * R;
-    const ll nchunks = (p.m + CH - 1) / CH;
-    for (ll c = warp; c < nchunks; c += nwarps) {
-        const ll e0 = (p.reverse ? (nchunks - 1 - c) : c) * CH + lane;
-        int s[R];
-        bool act[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            const ll e = e0 + 32 * j;
-            s[j] = e < p.m ? __ldcs(p.src + e) : -1;
-        }
-#pragma unroll
-        for (int j = 0; j < R; j++) act[j] = s[j] >= 0 && ((s_act[s[j] >> 5] >> (s[j] & 31)) & 1u);
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            const unsigned am = __ballot_sync(0xffffffffu, act[j]);
-            if (am == 0) continue;   // warp-uniform: the whole row is skipped
-            seen += __popc(am);
-            const ll e = e0 + 32 * j;
-            int d = -1 - lane;
-            W cs = W(0), tm = W(0);
-            if (act[j]) { d = __ldcs(p.dst + e); cs = __ldcs(cost + e); tm = __ldcs(time + e); }
-            relax_row<K, W>(p, act[j], lane, (int)e, s[j], d, cs, tm, chg);
-        }
-    }
-    chg = __reduce_or_sync(0xffffffffu, chg);
-    if (lane == 0) {
-        if (chg) atomicOr(p.changed, chg << p.k0);
-        if (seen) atomicAdd(p.examined, (ull)seen);
-    }
-}
-
-// dist = 0, pred = none for the candidate slots in `mask` only (asynchronous multisection refills one slot while the
-// others keep relaxing)
-__global__ void reset_slots_kernel(void *dist, ull *pred, ll n, int KT, unsigned mask) {
-    ull *d = static_cast<ull *>(dist);   // +0.0 and int64 0 are the same bits
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n * KT; i += (ll)gridDim.x * blockDim.x) {
-        if ((mask >> (int)(i % KT)) & 1u) { __stcg(d + i, 0ull); __stcg(pred + i, ~0ull); }
+// Column copies between the [n][ks] candidate layout and a compact [n][1] one: once a round has narrowed to a single
+// live slot, its dist/pred column moves to compact buffers (16 MB at n = 1 M, ~5 us) so that the remaining sweeps
+// gather from 8 MB of contiguous doubles instead of every fourth double of 32 MB.
+__global__ void column_copy_kernel(const ull *__restrict__ sd, const ull *__restrict__ sp, int sks, ull *__restrict__ dd,
+                                   ull *__restrict__ dp, int dks, ll n) {
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
+        dd[i * dks] = __ldcg(sd + i * sks);
+        dp[i * dks] = __ldcg(sp + i * sks);
     }
 }
 
@@ -648,113 +518,6 @@ __global__ void __launch_bounds__(256) relax_sparse_kernel(const __grid_constant
     if (tid == 0) st->act_count = st->act_cnt[ci];
 }
 
-// ---- TMA-staged relaxation (sm_100a: cp.async.bulk + mbarrier) ------------------------------------------
-// Same relaxation as relax_kernel, but the edge stream never touches registers or the LSU on its way in:
-// one elected thread per CTA issues 1-D bulk copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) of
-// the four edge arrays of a 1024-edge tile into a 3-stage shared-memory ring; completion is signalled on
-// an mbarrier (complete_tx::bytes).  The copy engine runs 2 tiles (48 KB per CTA, 3 CTAs per SM) ahead of
-// the warps, so HBM latency is fully decoupled from the dist gathers, and the threads keep all their
-// registers for the K-wide gather/compare/atomic part.
-#ifndef MRC_TMA_TILE
-#define MRC_TMA_TILE 1024
-#endif
-#ifndef MRC_TMA_STAGES
-#define MRC_TMA_STAGES 3
-#endif
-#ifndef MRC_TMA_MB
-#define MRC_TMA_MB 3
-#endif
-#define MRC_TMA_THREADS 256
-#define MRC_TMA_STAGE_BYTES (MRC_TMA_TILE * 24)
-#define MRC_TMA_SMEM (MRC_TMA_STAGES * MRC_TMA_STAGE_BYTES + 64)
-
-__device__ __forceinline__ unsigned mrc_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mrc_mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mrc_mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mrc_mbar_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void mrc_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-template <int K, bool EXACT>
-__global__ void __launch_bounds__(MRC_TMA_THREADS, MRC_TMA_MB) relax_kernel_tma(const __grid_constant__ RelaxArgs p) {
-    typedef typename WeightT<EXACT>::type W;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
-    const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
-    constexpr int T = MRC_TMA_TILE, S = MRC_TMA_STAGES;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const ll ntiles = (p.m + T - 1) / T;
-    const unsigned bar0 = mrc_smem_u32(smem + S * MRC_TMA_STAGE_BYTES);
-    auto tile_of = [&](ll i) { return p.reverse ? (ntiles - 1 - i) : i; };
-    auto issue = [&](ll i, int slot) {   // elected thread: 4 bulk copies, one barrier
-        const ll e0 = tile_of(i) * T;
-        ll cnt = p.m - e0;
-        if (cnt > T) cnt = T;
-        const unsigned c4 = (unsigned)((cnt + 3) & ~3ll);   // arrays are padded to a multiple of 4 edges
-        const unsigned bar = bar0 + 8u * slot;
-        const unsigned base = mrc_smem_u32(smem + slot * MRC_TMA_STAGE_BYTES);
-        mrc_mbar_expect_tx(bar, c4 * 24u);
-        mrc_bulk_g2s(base, p.src + e0, c4 * 4u, bar);
-        mrc_bulk_g2s(base + T * 4, p.dst + e0, c4 * 4u, bar);
-        mrc_bulk_g2s(base + T * 8, cost + e0, c4 * 8u, bar);
-        mrc_bulk_g2s(base + T * 16, time + e0, c4 * 8u, bar);
-    };
-    if (tid == 0) {
-        for (int s_ = 0; s_ < S; s_++) mrc_mbar_init(bar0 + 8u * s_, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0)
-        for (int s_ = 0; s_ < S; s_++) {
-            const ll i = (ll)blockIdx.x + (ll)s_ * gridDim.x;
-            if (i < ntiles) issue(i, s_);
-        }
-    unsigned chg = 0;
-    for (ll it = 0;; it++) {
-        const ll i = (ll)blockIdx.x + it * gridDim.x;
-        if (i >= ntiles) break;
-        const int slot = (int)(it % S);
-        mrc_mbar_wait(bar0 + 8u * slot, (unsigned)((it / S) & 1));
-        const unsigned char *st = smem + slot * MRC_TMA_STAGE_BYTES;
-        const int *ssrc = reinterpret_cast<const int *>(st);
-        const int *sdst = reinterpret_cast<const int *>(st + T * 4);
-        const W *scost = reinterpret_cast<const W *>(st + T * 8);
-        const W *stime = reinterpret_cast<const W *>(st + T * 16);
-        const ll e0 = tile_of(i) * T;
-#pragma unroll
-        for (int r = 0; r < T / 32 / (MRC_TMA_THREADS / 32); r++) {
-            const int row = wid + r * (MRC_TMA_THREADS / 32);
-            const int o = row * 32 + lane;
-            const ll e = e0 + o;
-            const bool ok = e < p.m;
-            relax_row<K, W>(p, ok, lane, (int)e, ssrc[o], ok ? sdst[o] : -1 - lane, scost[o], stime[o], chg);
-        }
-        __syncthreads();   // every warp is done with this slot
-        if (tid == 0) {
-            const ll nx = i + (ll)S * gridDim.x;
-            if (nx < ntiles) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(nx, slot);
-            }
-        }
-    }
-    chg = __reduce_or_sync(0xffffffffu, chg);
-    if (lane == 0 && chg) atomicOr(p.changed, chg << p.k0);
-}
-
 // ---- predecessor-graph cycle check -----------------------------------------------------------------
 // One cooperative launch:
 //   0. jump[v][k] = src[pred[v][k]]  (or -1 at roots)
@@ -779,14 +542,14 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     DevStatus *st = p.st;
 
     if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < MRC_MAX_ROUNDS * MRC_KMAX; i += blockDim.x) st->cnt[i] = 0;
+        for (int i = threadIdx.x; i < MRC_MAX_ROUNDS * MRC_KMAX; i += blockDim.x) { st->cnt[i] = 0; st->minlive[i] = 0x7fffffff; }
     if (blockIdx.x == 0 && threadIdx.x < MRC_KMAX * MRC_MAX_EXTRACT) st->rep[threadIdx.x] = 0x7fffffff;
     if (blockIdx.x == 0 && threadIdx.x < MRC_KMAX) {
         st->out[threadIdx.x].found = 0;
         st->out[threadIdx.x].len = 0;
     }
     if (tid0 == 0) { st->cyc_mask = 0; st->pend = 0; st->cuts = 0; }
-    const unsigned active = p.gate ? (p.active & __ldcg(p.gate)) : p.active;
+    const unsigned active = p.gate ? (p.active & (__ldcg(p.gate) >> p.k0)) : p.active;
     if (!active) return;   // grid-uniform
     // jump = grandparent (two predecessor steps straight from pred, which nobody writes during this
     // phase): saves the separate init sweep, its grid sync and the src[] gather of an edge-only pred
@@ -808,8 +571,9 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     int r = 0;
     for (; r < p.rounds && moving; r++) {
         unsigned cnt[K];
+        int low[K];   // smallest vertex still alive after this round: the representative of the first extraction below
 #pragma unroll
-        for (int k = 0; k < K; k++) cnt[k] = 0;
+        for (int k = 0; k < K; k++) { cnt[k] = 0; low[k] = 0x7fffffff; }
         for (ll i = tid0; i < total; i += stride) {
             const int k = (int)(i % K);
             if (!((alive_mask >> k) & 1u)) continue;
@@ -821,8 +585,10 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                     __stcg(p.jump + i, jj);
                 }
                 if (jj >= 0) {
+                    const int v = (int)(i / K);
 #pragma unroll
-                    for (int kk = 0; kk < K; kk++) cnt[kk] += (kk == k);
+                    for (int kk = 0; kk < K; kk++)
+                        if (kk == k) { cnt[kk]++; low[kk] = v < low[kk] ? v : low[kk]; }
                 }
             }
         }
@@ -830,7 +596,10 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         for (int k = 0; k < K; k++) {
             if (!((alive_mask >> k) & 1u)) continue;
             const unsigned c = __reduce_add_sync(0xffffffffu, cnt[k]);
-            if ((threadIdx.x & 31) == 0 && c) atomicAdd(&st->cnt[r * MRC_KMAX + k], c);
+            if (c) {   // warp-uniform
+                const int lo = __reduce_min_sync(0xffffffffu, low[k]);
+                if ((threadIdx.x & 31) == 0) { atomicAdd(&st->cnt[r * MRC_KMAX + k], c); atomicMin(&st->minlive[r * MRC_KMAX + k], lo); }
+            }
         }
         grid.sync();
         unsigned na = 0, nm = 0;
@@ -856,7 +625,9 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     if (alive_mask == 0) return;
 
     unsigned pending = alive_mask;   // candidates whose predecessor graph still holds an unexamined cycle
+    const int r_last = r - 1;   // at least one doubling round ran
     for (int it = 0; it < MRC_MAX_EXTRACT && pending; it++) {
+        if (it > 0) {   // grid-uniform.  it == 0: the smallest live vertex was found by the last doubling round itself
         int best[K];
 #pragma unroll
         for (int k = 0; k < K; k++) best[k] = 0x7fffffff;
@@ -878,6 +649,7 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
             if ((threadIdx.x & 31) == 0 && b != 0x7fffffff) atomicMin(&st->rep[it * MRC_KMAX + k], b);
         }
         grid.sync();
+        }
         if (blockIdx.x < K && ((pending >> blockIdx.x) & 1u)) {   // block-uniform: block k serves candidate k
             const int k = blockIdx.x;
             __shared__ int s_x, s_len;
@@ -899,7 +671,7 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                 return cur;
             };
             if (threadIdx.x == 0) {
-                const int rep = __ldcg(&st->rep[it * MRC_KMAX + k]);
+                const int rep = it == 0 ? __ldcg(&st->minlive[r_last * MRC_KMAX + k]) : __ldcg(&st->rep[it * MRC_KMAX + k]);
                 int x = -1;
                 ll len = 0;
                 if (rep != 0x7fffffff) {
@@ -989,6 +761,7 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                         o.found = kind; o.len = len; o.minv = minv; o.pad = x;   // pad = vertex the recorded walk starts from
                         o.sumc = sc; o.sumt = stt; o.maxabs = mabs; o.isumc = isc; o.isumt = ist;
                         st->out[k] = o;
+                        atomicOr(&st->decided, 1u << (k + p.k0));   // relaxation launches already enqueued skip this candidate
                     } else {
                         // false cycle: mark its vertices dead for this launch and cut it for good
                         int cur = minv;

@@ -109,3 +109,70 @@ def test_c5_sensitivity_full_size(S, oracle_mod):
     assert changed >= 1                                # the scenario on the optimal cycle must move the optimum
     again = s.solve()
     assert again.ratio == base.ratio
+
+
+def test_c4_all_4096_currency_graphs(S, oracle_mod):
+    """BASELINE config 4 at its stated size: 4,096 currency graphs (n=64, m=4,032) in ONE batch call; every result is
+    certified by the oracle detector, and the graphs with a reference solve in the fixtures match it."""
+    from conftest import load_golden
+    from min_ratio_cycle_b200 import batch, synthetic
+    seeded = load_golden("seeded.json")
+    seeds = list(range(1000, 1000 + 4096))
+    graphs = [synthetic.currency_graph(64, s) for s in seeds]
+    res, stats = batch.solve_min_ratio_cycle_batch(graphs, S.SolverConfig(log_level=S.LogLevel.NONE), return_stats=True)
+    assert len(res) == 4096 and stats["relax_launches"] == 1
+    matched = 0
+    for s, (n, U, V, C, T), r in zip(seeds, graphs, res):
+        assert r.success and r.cycle[0] == r.cycle[-1]
+        o = oracle_mod.Oracle(n, U, V, C, T, all_int=False, preprocess=False)
+        o.set_quirks(False)
+        ok, why = o.certify(r.cycle, r.ratio)
+        assert ok, (s, why)
+        gold = seeded.get(f"currency_{s}")
+        if gold is not None:
+            assert abs(r.ratio - gold["solve"]["ratio"]) <= 1e-9 * max(1.0, abs(gold["solve"]["ratio"])), s
+            matched += 1
+    assert matched >= 1
+    print(f"C4: 4096 graphs, kernel {stats['relax_ms']:.2f} ms, {stats['relax_edge_visits'] / stats['relax_ms'] / 1e6:.0f} G relax/s")
+
+
+def test_c5_all_1024_scenarios(S, oracle_mod):
+    """BASELINE config 5 at its stated size: 1,024 single-edge perturbation re-solves of n=100k, m=2M.  Certified:
+    64 scenarios spread evenly over the list plus every scenario whose optimal cycle moved; all others must report
+    the unperturbed cycle with its sums re-costed under the scenario's weights."""
+    from min_ratio_cycle_b200 import synthetic
+    n, U, V, C, T = synthetic.random_float(100_000, 2_000_000, seed=5)
+    m = len(U)
+    s = S.MinRatioCycleSolver(n, S.SolverConfig(log_level=S.LogLevel.NONE, enable_preprocessing=False))
+    s.add_edges_arrays(U, V, C, T)
+    base = s.solve()
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, m, 1024)
+    sign = rng.choice([-1.0, 1.0], 1024)
+    hops = list(zip(base.cycle[:-1], base.cycle[1:]))
+    for j, (a, b) in enumerate(hops[:8]):               # a few scenarios hit the optimal cycle itself, both ways
+        idx[j] = int(np.flatnonzero((U == a) & (V == b))[0])
+        sign[j] = 1.0 if j % 2 == 0 else -1.0
+    scen = [{int(i): (float(sg * 0.1 * C[i]), 0.0)} for i, sg in zip(idx, sign)]
+    scen[0] = {int(idx[0]): (1000.0, 0.0)}              # ... and one makes that cycle useless
+    res = s.sensitivity_analysis(scen)
+    assert len(res) == 1024 and all(r.success for r in res)
+    moved = [k for k, r in enumerate(res) if r.cycle != base.cycle]
+    assert 0 in moved
+    check = sorted(set(range(0, 1024, 16)) | set(moved))
+    for k in check:
+        C2 = C.copy()
+        for i, (dc, dt) in scen[k].items():
+            C2[i] += dc
+        o = oracle_mod.Oracle(n, U, V, C2, T, all_int=False, preprocess=False, threads=8)
+        o.set_quirks(False)
+        ok, why = o.certify(res[k].cycle, res[k].ratio)
+        assert ok, (k, scen[k], why)
+    for k, r in enumerate(res):
+        if k in moved:
+            continue
+        (i, (dc, dt)), = scen[k].items()
+        exp_c = base.sum_cost + (dc if (int(U[i]), int(V[i])) in set(hops) else 0.0)
+        assert abs(r.sum_cost - exp_c) <= 1e-9 * max(1.0, abs(exp_c)), k
+    assert s.solve().ratio == base.ratio                # device arrays restored
+    print(f"C5: 1024 scenarios, {len(moved)} moved the optimum, {len(check)} certified")

@@ -480,7 +480,7 @@ def test_c1_three_way_statistics(mrc, oracle_mod):
 
 
 def test_every_kernel_variant_on_odd_sizes(mrc):
-    """Dense / TMA-staged / frontier relaxation at K=1,2,4,8, scenario probes, device patches, exact strategies,
+    """Dense (full-width, narrowed, compact-survivor) and worklist relaxation at K=1,2,4,8, scenario probes, device patches, exact strategies,
     batch kernel and device sort on sizes that exercise every tail path; all relaxation variants must agree."""
     import os
     import runpy
@@ -561,32 +561,4 @@ def test_probe_without_cycles_then_fetch_with_sums(mrc):
         for a, b in zip(cyc[:-1], cyc[1:]):
             rc += hop[(a, b)][0]; rt += hop[(a, b)][1]
         assert (rc, rt) == (sc, st)
-    g.close()
-
-
-@pytest.mark.parametrize("K", [2, 4, 8])
-def test_async_multisection_option_gives_the_same_optimum(K, oracle_mod):
-    """Option "async" (slots refilled as they are decided, solve_numeric_async): same ratio, certified cycle."""
-    from min_ratio_cycle_b200 import _native as N, synthetic
-    for gen, args in ((synthetic.random_float, (4000, 30000, 5)), (synthetic.ring_plus_random, (600, 2500, 8)),
-                      (synthetic.random_float, (20000, 200000, 6))):
-        n, U, V, C, T = gen(*args[:2], seed=args[2])
-        o = np.argsort(V, kind="stable")
-        g = N.DeviceGraph(n, U[o], V[o], C[o], T[o])
-        lo, hi = g.bounds()
-        want = g.solve_numeric(lo, hi, K=K)
-        g.set_option("async", 1)
-        for _ in range(2):
-            got = g.solve_numeric(lo, hi, K=K)
-            assert got["rc"] == 0 and abs(got["ratio"] - want["ratio"]) <= 1e-9 * max(1.0, abs(want["ratio"]))
-        orc = oracle_mod.Oracle(n, U, V, C, T, all_int=False)
-        orc.set_quirks(False)
-        ok, why = orc.certify(got["cycle"], got["ratio"])
-        assert ok, why
-        g.close()
-    # a graph without any cycle: the same error as the round-based driver
-    g = N.DeviceGraph(4, [0, 1, 2], [1, 2, 3], [1.0, -2.0, 3.0], [1.0, 1.0, 1.0])
-    g.set_option("async", 1)
-    lo, hi = g.bounds()
-    assert g.solve_numeric(lo, hi, K=K)["rc"] == N.ERR_NO_CYCLE
     g.close()

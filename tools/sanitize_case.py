@@ -15,10 +15,13 @@ lo, hi = g.bounds()
 ratios = []
 for K in (1, 2, 4, 8):
     ratios.append(g.solve_numeric(lo, hi, K=K)["ratio"])
-for opt in ("tma", "frontier"):
-    g.set_option(opt, 15 if opt == "tma" else 1)
-    ratios.append(g.solve_numeric(lo, hi, K=4)["ratio"])
-    g.set_option(opt, 0)
+g.set_option("compact_min_edges", 0)          # compact-survivor path (a K >= 2 probe narrowed to one slot)
+for opts in ({"compact": 1}, {"sparse": 1, "sparse_min_edges": 0}, {"narrow": 0, "compact": 0}):
+    for k, v in opts.items():
+        g.set_option(k, v)
+    for K in (2, 4, 8):
+        ratios.append(g.solve_numeric(lo, hi, K=K)["ratio"])
+g.set_option("sparse", 0); g.set_option("narrow", 1); g.set_option("compact", 1)
 assert max(ratios) - min(ratios) <= 1e-12, ratios
 r = ratios[0]
 out = g.probe_numeric_scenarios([r - 1e-12] * 3, [5, -1, 17002], [0.5, 0.0, -3.0], [0.0, 0.0, 0.1])
