@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MRC_ABI_VERSION 2   /* 2: mrc_stats grew (sparse_passes, sparse_ms) */
+#define MRC_ABI_VERSION 3   /* 2: mrc_stats grew (sparse_passes, sparse_ms); 3: mrc_comm_*, sharded solve, options pruned */
 #define MRC_KMAX 8 /* candidate lambdas evaluated by one relaxation launch */
 
 /* status codes */
@@ -42,6 +42,7 @@ extern "C" {
 #define MRC_ERR_NOT_INTEGER 10 /* "Exact mode requires integer weights", solver.py:689-697 */
 #define MRC_ERR_TIMEOUT 11     /* TimeoutError, solver.py:1032-1041 */
 #define MRC_ERR_EDGE_MISSING 12
+#define MRC_ERR_COMM 13         /* NCCL could not be loaded / a collective failed (multi-GPU entry points only) */
 
 /* per-candidate verdicts of a probe */
 #define MRC_V_NONNEG 0         /* relaxation reached a fixed point: no negative cycle at this lambda */
@@ -230,6 +231,69 @@ int mrc_solve_exact(mrc_graph *g, int64_t max_den, int64_t max_steps, int strate
                     int64_t cycle_cap, int64_t *cycle_len, int64_t *sum_cost, int64_t *sum_time, int64_t *a_out,
                     int64_t *b_out, int64_t *iterations, int64_t *probes_ab, int64_t probes_cap,
                     int64_t *nprobes);
+
+/* ---- several GPUs of one box (SURVEY 8b "mrc_comm_init / mrc_comm_destroy", 8e) -----------------------------------
+ * The reference has no counterpart: its lambda search is the sequential loop solver.py:1031-1076.  Here every GPU
+ * holds a full replica of the edge arrays and evaluates its own lambda candidates; the only traffic between GPUs is,
+ * per tick, ONE all-gather of 32 B per candidate (lambda, verdict, cycle ratio, cycle length) enqueued on the
+ * library's stream straight from the status block the cycle check wrote (NCCL over NVLink/NVSwitch), and one
+ * broadcast of the winning cycle at the end.  NCCL is loaded at run time (libnccl.so.2 already in the process --
+ * e.g. PyTorch's -- or the system one); nothing else in this header needs it.
+ *
+ * Two ways to get a communicator:
+ *   one process per GPU (torchrun): rank 0 calls mrc_comm_unique_id, ships the 128 bytes to the other ranks through
+ *     whatever channel the job already has (torch.distributed broadcast, MPI, a file), every rank then calls
+ *     mrc_comm_init_rank.  Collective.
+ *   one process, several GPUs: mrc_comm_init(ndev, devs) (ncclCommInitAll); the library runs one host thread per
+ *     device inside mrc_mgraph_* calls.  This is what SolverConfig.gpu_devices uses.
+ */
+typedef struct mrc_comm mrc_comm;
+#define MRC_UNIQUE_ID_BYTES 128
+int mrc_comm_unique_id(uint8_t *id /* [MRC_UNIQUE_ID_BYTES] */);
+int mrc_comm_init_rank(int nranks, int rank, const uint8_t *id, int device, mrc_comm **out);
+int mrc_comm_init(int ndev, const int *devs, mrc_comm **out);
+int mrc_comm_destroy(mrc_comm *c);
+int mrc_comm_info(const mrc_comm *c, int *nranks, int *rank /* -1: single-process group */, int *device);
+
+/* Replica of a graph on every rank: `root` passes the (destination-sorted) host arrays, the other ranks NULL; ONE
+ * host-to-device copy on the root, then ncclBroadcast over NVLink (n = 1 M, m = 10 M: 240 MB, a fraction of a
+ * millisecond per GPU) instead of one H2D copy per GPU.  Numeric graphs only.  Collective (rank communicators). */
+int mrc_graph_create_replicated(mrc_comm *c, int root, int64_t n, int64_t m, const int32_t *src, const int32_t *dst,
+                                const double *cost, const double *time, mrc_graph **out);
+
+/* Numeric lambda search with the candidates sharded over the ranks of `c` (replaces the loop solver.py:1031-1076;
+ * single-GPU form: mrc_solve_numeric).  Every rank runs probes of K_local candidates of its own on its replica `g`;
+ * after every burst the per-candidate records of all ranks are all-gathered on the device, every rank folds them
+ * into the same bracket [lo, hi] (a verified cycle lowers hi to its ratio, a converged candidate raises lo), abandons
+ * the candidates of its own that the bracket now implies (lambda >= hi: negative; lambda <= lo: not negative) and,
+ * when none is left, starts K_local fresh ones from the current bracket without waiting for the other ranks.  Ends
+ * when hi - lo <= tol (same test as solver.py:1075) on the tick every rank sees it.  Outputs as mrc_solve_numeric,
+ * identical on every rank (the owner of the best cycle broadcasts it); *iterations = probes started by this rank.
+ * Collective: every rank of `c` calls it with the same lo/hi/max_iter/tol/slack/K_local. */
+int mrc_solve_numeric_sharded(mrc_comm *c, mrc_graph *g, double lo, double hi, int max_iter, double tol, double slack,
+                              int K_local, double max_seconds, double *ratio, double *sum_cost, double *sum_time,
+                              int32_t *cycle, int64_t cycle_cap, int64_t *cycle_len, int32_t *iterations,
+                              double *final_lo, double *final_hi, int32_t *ticks);
+
+/* Single-process form: replicas of one graph on every device of a group communicator (mrc_comm_init), and the same
+ * sharded search driven by one host thread per device.  mrc_mgraph_graph(mg, i) is the replica on device i (for
+ * statistics / options; do not destroy it). */
+typedef struct mrc_mgraph mrc_mgraph;
+int mrc_mgraph_create(mrc_comm *c, int64_t n, int64_t m, const int32_t *src, const int32_t *dst, const double *cost,
+                      const double *time, mrc_mgraph **out);
+int mrc_mgraph_destroy(mrc_mgraph *mg);
+mrc_graph *mrc_mgraph_graph(mrc_mgraph *mg, int i);
+int mrc_mgraph_solve_numeric(mrc_mgraph *mg, double lo, double hi, int max_iter, double tol, double slack, int K_local,
+                             double max_seconds, double *ratio, double *sum_cost, double *sum_time, int32_t *cycle,
+                             int64_t cycle_cap, int64_t *cycle_len, int32_t *iterations, double *final_lo,
+                             double *final_hi, int32_t *ticks);
+
+/* Pure host helper of the sharded search (no device, no NCCL; the multi-rank logic is tested with it on CPU):
+ * folds the records of one tick -- rec[4*i .. 4*i+3] = (lambda, state, cycle ratio, cycle length), state = -1 while the
+ * candidate is still running, else its MRC_V_* verdict -- into the bracket.  *best_idx = index of the record whose
+ * cycle became the new best (or -1).  implied[i] (may be NULL) = 1 where a running candidate's verdict now follows
+ * from the bracket. */
+int mrc_shard_fold(int nrec, const double *rec, double *lo, double *hi, int *have_cycle, int *best_idx, uint8_t *implied);
 
 /* ---- device-side array build -------------------------------------------------------------------
  * The stable sort by destination of _build_arrays_if_needed (np.argsort(V, kind="stable") + gathers,

@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("MRC_B200_LIB") or os.path.join(HERE, "libmrc_b200.so"
 KMAX = 8
 
 OK, ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_OVERFLOW, ERR_NO_CYCLE, ERR_CONVERGENCE = range(7)
-ERR_LOWER_NEG, ERR_UPPER_NONNEG, ERR_SB_STEPS, ERR_NOT_INTEGER, ERR_TIMEOUT, ERR_EDGE_MISSING = range(7, 13)
+ERR_LOWER_NEG, ERR_UPPER_NONNEG, ERR_SB_STEPS, ERR_NOT_INTEGER, ERR_TIMEOUT, ERR_EDGE_MISSING, ERR_COMM = range(7, 14)
+UNIQUE_ID_BYTES = 128
 
 V_NONNEG, V_NEG, V_NEG_NOCYCLE, V_TIE, V_SKIPPED_NEG, V_SKIPPED_NONNEG, V_ABANDONED = range(7)
 F_MONOTONE_PRUNE = 1
@@ -32,6 +33,9 @@ EXPORTS = [
     "mrc_graph_restore", "mrc_probe_numeric", "mrc_solve_numeric", "mrc_plan_candidates", "mrc_reduce_round",
     "mrc_probe_exact", "mrc_potentials_exact", "mrc_tight_mask_exact", "mrc_zero_cycle_exact", "mrc_solve_exact",
     "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle", "mrc_fetch_cycle_sums", "mrc_sort_edges_by_dst", "mrc_probe_numeric_scenarios",
+    "mrc_comm_unique_id", "mrc_comm_init_rank", "mrc_comm_init", "mrc_comm_destroy", "mrc_comm_info",
+    "mrc_graph_create_replicated", "mrc_solve_numeric_sharded", "mrc_mgraph_create", "mrc_mgraph_destroy", "mrc_mgraph_graph",
+    "mrc_mgraph_solve_numeric", "mrc_shard_fold",
 ]
 
 
@@ -102,8 +106,24 @@ def lib():
     L.mrc_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.mrc_batch_solve_numeric.argtypes = [C.c_int64, p32, p64, p32, p32, pd, pd, C.c_int, C.c_double, C.c_double, C.c_int,
                                           C.c_int, pd, pd, pd, p32, p32, C.c_int64, p32, p32, C.POINTER(Stats)]
+    L.mrc_comm_unique_id.argtypes = [pu8]
+    L.mrc_comm_init_rank.argtypes = [C.c_int, C.c_int, pu8, C.c_int, C.POINTER(vp)]
+    L.mrc_comm_init.argtypes = [C.c_int, pi, C.POINTER(vp)]
+    L.mrc_comm_destroy.argtypes = [vp]
+    L.mrc_comm_info.argtypes = [vp, pi, pi, pi]
+    L.mrc_graph_create_replicated.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, p32, p32, pd, pd, C.POINTER(vp)]
+    sharded_tail = [C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, pd, pd, pd, p32, C.c_int64,
+                    p64, p32, pd, pd, p32]
+    L.mrc_solve_numeric_sharded.argtypes = [vp, vp] + sharded_tail
+    L.mrc_mgraph_create.argtypes = [vp, C.c_int64, C.c_int64, p32, p32, pd, pd, C.POINTER(vp)]
+    L.mrc_mgraph_destroy.argtypes = [vp]
+    L.mrc_mgraph_graph.argtypes = [vp, C.c_int]
+    L.mrc_mgraph_solve_numeric.argtypes = [vp] + sharded_tail
+    L.mrc_shard_fold.argtypes = [C.c_int, pd, pd, pd, pi, pi, pu8]
     for name in EXPORTS:
-        if name not in ("mrc_last_error",):
+        if name == "mrc_mgraph_graph":
+            getattr(L, name).restype = vp
+        elif name not in ("mrc_last_error",):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -150,9 +170,30 @@ class DeviceGraph:
         self.device = int(device)
         self.has_int = ic is not None
 
+    @classmethod
+    def _wrap(cls, handle, n: int, m: int, device: int, owned: bool = True):
+        g = cls.__new__(cls)
+        g._h, g.n, g.m, g.device, g.has_int, g._owned = handle, int(n), int(m), int(device), False, owned
+        return g
+
+    @classmethod
+    def replicated(cls, comm: "Comm", n: int, m: int, U=None, V=None, Cw=None, Tw=None, root: int = 0):
+        """Replica of a graph on this rank (mrc_graph_create_replicated): the root passes the destination-sorted
+        arrays, the other ranks None; one H2D on the root + NCCL broadcast.  Collective over the ranks of `comm`."""
+        arrs = [None] * 4
+        if U is not None:
+            arrs = [np.ascontiguousarray(U, dtype=np.int32), np.ascontiguousarray(V, dtype=np.int32),
+                    np.ascontiguousarray(Cw, dtype=np.float64), np.ascontiguousarray(Tw, dtype=np.float64)]
+        h = C.c_void_p()
+        check(lib().mrc_graph_create_replicated(comm._h, int(root), int(n), int(m), _ptr(arrs[0], C.c_int32),
+                                                _ptr(arrs[1], C.c_int32), _ptr(arrs[2], C.c_double),
+                                                _ptr(arrs[3], C.c_double), C.byref(h)))
+        return cls._wrap(h, n, m, comm.device)
+
     def close(self):
         if self._h is not None:
-            lib().mrc_graph_destroy(self._h)
+            if getattr(self, "_owned", True):
+                lib().mrc_graph_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -296,6 +337,13 @@ class DeviceGraph:
                     cycle=buf[: cl.value].tolist() if have else [], sum_cost=sc.value, sum_time=st.value,
                     ratio=ratio.value, iterations=it.value, lo=flo.value, hi=fhi.value)
 
+    def solve_numeric_sharded(self, comm: "Comm", lo: float, hi: float, max_iter: int = 60, tol: float = 1e-12,
+                              slack: float = 1e-15, K_local: int = 4, max_seconds: float = 0.0):
+        """mrc_solve_numeric_sharded on this rank's replica; collective over the ranks of `comm`.  Same dict as
+        solve_numeric plus `ticks`; every rank gets the same cycle."""
+        return _sharded_call(lambda *tail: lib().mrc_solve_numeric_sharded(comm._h, self._h, *tail), self.n, lo, hi, max_iter, tol,
+                             slack, K_local, max_seconds)
+
     def potentials_exact(self, a: int, b: int):
         ok = C.c_uint8()
         dist = np.zeros(self.n, np.int64)
@@ -337,6 +385,127 @@ class DeviceGraph:
                     cycle=buf[: cl.value].tolist() if rc == OK else [], sum_cost=sc.value, sum_time=st.value,
                     a=a.value, b=b.value, iterations=it.value,
                     probes=[(int(pr[2 * i]), int(pr[2 * i + 1])) for i in range(k)])
+
+
+def _sharded_call(fn, n, lo, hi, max_iter, tol, slack, K_local, max_seconds):
+    cap = int(n) + 1
+    buf = np.zeros(cap, np.int32)
+    ratio, sc, st, flo, fhi = (C.c_double() for _ in range(5))
+    cl = C.c_int64(); it = C.c_int32(); ticks = C.c_int32()
+    rc = fn(float(lo), float(hi), int(max_iter), float(tol), float(slack), int(K_local), float(max_seconds or 0.0),
+            C.byref(ratio), C.byref(sc), C.byref(st), _ptr(buf, C.c_int32), cap, C.byref(cl), C.byref(it), C.byref(flo),
+            C.byref(fhi), C.byref(ticks))
+    if rc not in (OK, ERR_CONVERGENCE, ERR_NO_CYCLE, ERR_TIMEOUT):
+        check(rc)
+    have = rc in (OK, ERR_CONVERGENCE)
+    return dict(rc=rc, message=lib().mrc_last_error().decode() if rc else "", cycle=buf[: cl.value].tolist() if have else [],
+                sum_cost=sc.value, sum_time=st.value, ratio=ratio.value, iterations=it.value, lo=flo.value, hi=fhi.value,
+                ticks=ticks.value)
+
+
+class Comm:
+    """
+    NCCL communicator owned by the library (mrc_comm).  Comm.from_torch(): one process per GPU, the unique id
+    travels through the job's torch.distributed group.  Comm.group(devices): one process driving several GPUs.
+    """
+
+    def __init__(self, handle, nranks: int, rank: int, device: int):
+        self._h, self.nranks, self.rank, self.device = handle, nranks, rank, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES)()
+        check(lib().mrc_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_id(cls, nranks: int, rank: int, uid: bytes, device: int):
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(uid)
+        h = C.c_void_p()
+        check(lib().mrc_comm_init_rank(int(nranks), int(rank), buf, int(device), C.byref(h)))
+        return cls(h, nranks, rank, device)
+
+    @classmethod
+    def from_torch(cls, device: int, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        on_gpu = "nccl" in str(dist.get_backend(group))
+        t = torch.zeros(UNIQUE_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8).clone()
+        if on_gpu:
+            t = t.to(torch.device("cuda", device))
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls.from_id(world, rank, bytes(t.cpu().numpy().tobytes()), device)
+
+    @classmethod
+    def group(cls, devices):
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(lib().mrc_comm_init(len(devices), devs, C.byref(h)))
+        return cls(h, len(devices), -1, int(devices[0]))
+
+    def close(self):
+        if self._h is not None:
+            lib().mrc_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiGraph:
+    """Replicas of one destination-sorted graph on every device of a group communicator (mrc_mgraph)."""
+
+    def __init__(self, comm: Comm, n, U, V, Cw, Tw):
+        self._h = None
+        self.comm, self.n, self.m = comm, int(n), int(len(U))
+        src = np.ascontiguousarray(U, dtype=np.int32)
+        dst = np.ascontiguousarray(V, dtype=np.int32)
+        cost = np.ascontiguousarray(Cw, dtype=np.float64)
+        time = np.ascontiguousarray(Tw, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().mrc_mgraph_create(comm._h, self.n, self.m, _ptr(src, C.c_int32), _ptr(dst, C.c_int32),
+                                      _ptr(cost, C.c_double), _ptr(time, C.c_double), C.byref(h)))
+        self._h = h
+
+    def replica(self, i: int) -> DeviceGraph:
+        """Borrowed handle of the replica on device i of the group (statistics, options, bounds)."""
+        h = lib().mrc_mgraph_graph(self._h, int(i))
+        if not h:
+            raise IndexError(i)
+        return DeviceGraph._wrap(C.c_void_p(h), self.n, self.m, -1, owned=False)
+
+    def solve_numeric(self, lo: float, hi: float, max_iter: int = 60, tol: float = 1e-12, slack: float = 1e-15,
+                      K_local: int = 4, max_seconds: float = 0.0):
+        return _sharded_call(lambda *tail: lib().mrc_mgraph_solve_numeric(self._h, *tail), self.n, lo, hi, max_iter, tol, slack,
+                             K_local, max_seconds)
+
+    def close(self):
+        if self._h is not None:
+            lib().mrc_mgraph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shard_fold(rec, lo: float, hi: float, have_cycle: bool):
+    """mrc_shard_fold: rec is an (nrec, 4) array of (lambda, state, ratio, length); returns (lo, hi, have_cycle, best_idx, implied)."""
+    rec = np.ascontiguousarray(rec, dtype=np.float64).reshape(-1, 4)
+    clo, chi = C.c_double(lo), C.c_double(hi)
+    hc, best = C.c_int(int(have_cycle)), C.c_int(-1)
+    imp = np.zeros(len(rec), np.uint8)
+    check(lib().mrc_shard_fold(len(rec), _ptr(rec, C.c_double), C.byref(clo), C.byref(chi), C.byref(hc), C.byref(best),
+                               _ptr(imp, C.c_uint8)))
+    return clo.value, chi.value, bool(hc.value), best.value, imp.astype(bool)
 
 
 def plan_candidates(lo: float, hi: float, have_cycle: bool, tol: float, K_total: int) -> np.ndarray:

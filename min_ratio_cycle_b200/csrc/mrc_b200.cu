@@ -94,6 +94,7 @@ struct mrc_graph {
     int narrow = 1;              // option "narrow": late passes run the narrowest kernel covering the undecided candidates
     int compact = 1;             // option "compact": a probe narrowed to ONE live slot continues on a compact [n][1] copy of its column
     ll compact_min_edges = 2000000;   // ... on graphs where a sweep is bandwidth-bound (smaller ones are launch-bound)
+    int check_every = 0;         // option "check_every" (experiments): cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
     int lookahead = 1;           // option "lookahead": the next burst is enqueued before the previous burst's status is read
     void *d_cdist = nullptr; ull *d_cpred = nullptr; int *d_cjump = nullptr;   // compact column (compact survivor)
     mrc_stats stats;
@@ -181,15 +182,11 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
     return MRC_OK;
 }
 
-extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const int32_t *dst, const double *cost,
-                                const double *time, const int64_t *icost, const int64_t *itime, int device,
-                                mrc_graph **out) {
-    if (!out) return set_err(MRC_ERR_ARG, "out is NULL");
+// Allocation of everything a graph handle owns on `device` (edge arrays uninitialised), launch geometry, options.
+static int graph_new(int64_t n, int64_t m, int device, bool with_int, mrc_graph **out) {
     *out = nullptr;
     if (n <= 0 || m <= 0) return set_err(MRC_ERR_ARG, "n and m must be positive (n=%lld m=%lld)", (ll)n, (ll)m);
     if (n > 0x7ffffff0ll || m > 0x7ffffff0ll) return set_err(MRC_ERR_ARG, "n, m must fit int32");
-    if (!src || !dst || !cost || !time) return set_err(MRC_ERR_ARG, "edge arrays are NULL");
-    if ((icost == nullptr) != (itime == nullptr)) return set_err(MRC_ERR_ARG, "icost/itime must both be set or both NULL");
     int ndev = 0;
     MRC_TRY(mrc_device_count(&ndev));
     if (device < 0 || device >= ndev) return set_err(MRC_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
@@ -212,18 +209,82 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
         const size_t m4 = ((size_t)m + 3) & ~(size_t)3;   // vector loads never read past the allocation
         DALLOC(g->d_src, m4 * 4); DALLOC(g->d_dst, m4 * 4);
         DALLOC(g->d_cost, m4 * 8); DALLOC(g->d_time, m4 * 8);
+        if (with_int) {
+            g->has_int = true;
+            DALLOC(g->d_icost, m4 * 8); DALLOC(g->d_itime, m4 * 8);
+            DALLOC(g->d_mask, (size_t)m);
+        }
+        DALLOC(g->d_dist, (size_t)n * MRC_KMAX * 8);
+        DALLOC(g->d_pred, (size_t)n * MRC_KMAX * 8);
+        DALLOC(g->d_jump, (size_t)n * MRC_KMAX * 4);
+        g->cyc_cap = n;
+        DALLOC(g->d_cyc_edges, (size_t)g->cyc_cap * MRC_KMAX * 4);
+        DALLOC(g->d_status, sizeof(DevStatus));
+        CUDA_TRY(cudaMemsetAsync(g->d_status, 0, sizeof(DevStatus), g->stream));
+        CUDA_TRY(cudaMallocHost(&g->h_status, sizeof(DevStatus)));
+        DALLOC(g->d_keys, 16);
+        DALLOC(g->d_verr, 4);
+        // launch geometry: persistent grids sized to whole waves of the 148 SMs
+        for (int KT : {1, 2, 4, 8})
+            for (int ex = 0; ex < 2; ex++) {
+                const int i = kt_index(KT);
+                if (di->occ_relax[i][ex] < 1 || di->occ_check[i] < 1) return set_err(MRC_ERR_CUDA, "kernel K=%d does not fit on an SM", KT);
+                const int rows = KT == 8 ? RelaxTune<8>::rows : RelaxTune<1>::rows;
+                const ll chunks = (m + 32 * rows - 1) / (32 * rows);   // one chunk per warp step
+                const ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
+                g->relax_blocks[i][ex] = (int)std::min<ll>(need, (ll)di->occ_relax[i][ex] * g->sms);
+                const ll needc = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
+                g->check_blocks[i] = (int)std::min<ll>(needc, (ll)di->occ_check[i] * g->sms);
+            }
+        if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
+        if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
+        if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
+        if (const char *env = getenv("MRC_B200_SPARSE_LOOK")) g->sparse_look = std::max(0, atoi(env));
+        if (const char *env = getenv("MRC_B200_SPARSE_MIN_EDGES")) g->sparse_min_edges = atoll(env);   // parity suite: 0
+        if (const char *env = getenv("MRC_B200_COMPACT_MIN_EDGES")) g->compact_min_edges = atoll(env);   // parity suite: 0
+        if (const char *env = getenv("MRC_B200_LOOKAHEAD")) g->lookahead = atoi(env) != 0;
+        return MRC_OK;
+    }();
+    if (rc) { mrc_graph_destroy(g); return rc; }
+    *out = g;
+    return MRC_OK;
+}
+
+// input validation on the device (the host never touches the 24 B/edge again); synchronises the stream
+static int graph_validate(mrc_graph *g) {
+    CUDA_TRY(cudaMemsetAsync(g->d_verr, 0, 4, g->stream));
+    validate_edges_kernel<<<(int)std::min<ll>((g->m + 255) / 256, (ll)g->sms * 8), 256, 0, g->stream>>>(
+        g->d_src, g->d_dst, g->d_time, g->n, g->m, g->d_verr);
+    CUDA_TRY(cudaGetLastError());
+    int verr = 0;
+    CUDA_TRY(cudaMemcpyAsync(&verr, g->d_verr, 4, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    g->stats.other_launches++;
+    if (verr & 1) return set_err(MRC_ERR_ARG, "an edge has an endpoint outside [0,n)");
+    if (verr & 2) return set_err(MRC_ERR_ARG, "edges are not destination-sorted");
+    if (verr & 4) return set_err(MRC_ERR_ARG, "edge time must be strictly positive");
+    return MRC_OK;
+}
+
+extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const int32_t *dst, const double *cost,
+                                const double *time, const int64_t *icost, const int64_t *itime, int device,
+                                mrc_graph **out) {
+    if (!out) return set_err(MRC_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!src || !dst || !cost || !time) return set_err(MRC_ERR_ARG, "edge arrays are NULL");
+    if ((icost == nullptr) != (itime == nullptr)) return set_err(MRC_ERR_ARG, "icost/itime must both be set or both NULL");
+    mrc_graph *g = nullptr;
+    MRC_TRY(graph_new(n, m, device, icost != nullptr, &g));
+    int rc = [&]() -> int {
         CUDA_TRY(cudaMemcpyAsync(g->d_src, src, (size_t)m * 4, cudaMemcpyHostToDevice, g->stream));
         CUDA_TRY(cudaMemcpyAsync(g->d_dst, dst, (size_t)m * 4, cudaMemcpyHostToDevice, g->stream));
         CUDA_TRY(cudaMemcpyAsync(g->d_cost, cost, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
         CUDA_TRY(cudaMemcpyAsync(g->d_time, time, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
         g->stats.h2d_bytes += (int64_t)m * 24;
         if (icost) {
-            g->has_int = true;
-            DALLOC(g->d_icost, m4 * 8); DALLOC(g->d_itime, m4 * 8);
             CUDA_TRY(cudaMemcpyAsync(g->d_icost, icost, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
             CUDA_TRY(cudaMemcpyAsync(g->d_itime, itime, (size_t)m * 8, cudaMemcpyHostToDevice, g->stream));
             g->stats.h2d_bytes += (int64_t)m * 16;
-            DALLOC(g->d_mask, (size_t)m);
             g->h_src.assign(src, src + m); g->h_dst.assign(dst, dst + m);
             g->h_icost.assign(icost, icost + m); g->h_itime.assign(itime, itime + m);
             g->h_starts.assign((size_t)n + 1, 0);
@@ -244,48 +305,7 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
             g->max_it = g->max_abs_it;
             g->min_ratio_i = mn; g->max_ratio_i = mx;
         }
-        DALLOC(g->d_dist, (size_t)n * MRC_KMAX * 8);
-        DALLOC(g->d_pred, (size_t)n * MRC_KMAX * 8);
-        DALLOC(g->d_jump, (size_t)n * MRC_KMAX * 4);
-        g->cyc_cap = n;
-        DALLOC(g->d_cyc_edges, (size_t)g->cyc_cap * MRC_KMAX * 4);
-        DALLOC(g->d_status, sizeof(DevStatus));
-        CUDA_TRY(cudaMemsetAsync(g->d_status, 0, sizeof(DevStatus), g->stream));
-        CUDA_TRY(cudaMallocHost(&g->h_status, sizeof(DevStatus)));
-        DALLOC(g->d_keys, 16);
-        // launch geometry: persistent grids sized to whole waves of the 148 SMs
-        for (int KT : {1, 2, 4, 8})
-            for (int ex = 0; ex < 2; ex++) {
-                const int i = kt_index(KT);
-                if (di->occ_relax[i][ex] < 1 || di->occ_check[i] < 1) return set_err(MRC_ERR_CUDA, "kernel K=%d does not fit on an SM", KT);
-                const int rows = KT == 8 ? RelaxTune<8>::rows : RelaxTune<1>::rows;
-                const ll chunks = (m + 32 * rows - 1) / (32 * rows);   // one chunk per warp step
-                const ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
-                g->relax_blocks[i][ex] = (int)std::min<ll>(need, (ll)di->occ_relax[i][ex] * g->sms);
-                const ll needc = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
-                g->check_blocks[i] = (int)std::min<ll>(needc, (ll)di->occ_check[i] * g->sms);
-            }
-        if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
-        if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
-        if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
-        if (const char *env = getenv("MRC_B200_SPARSE_LOOK")) g->sparse_look = std::max(0, atoi(env));
-        if (const char *env = getenv("MRC_B200_SPARSE_MIN_EDGES")) g->sparse_min_edges = atoll(env);   // parity suite: 0
-        if (const char *env = getenv("MRC_B200_COMPACT_MIN_EDGES")) g->compact_min_edges = atoll(env);   // parity suite: 0
-        if (const char *env = getenv("MRC_B200_LOOKAHEAD")) g->lookahead = atoi(env) != 0;
-        // input validation on the device (the host never touches the 24 B/edge again)
-        DALLOC(g->d_verr, 4);
-        CUDA_TRY(cudaMemsetAsync(g->d_verr, 0, 4, g->stream));
-        validate_edges_kernel<<<(int)std::min<ll>((m + 255) / 256, (ll)g->sms * 8), 256, 0, g->stream>>>(
-            g->d_src, g->d_dst, g->d_time, n, m, g->d_verr);
-        CUDA_TRY(cudaGetLastError());
-        int verr = 0;
-        CUDA_TRY(cudaMemcpyAsync(&verr, g->d_verr, 4, cudaMemcpyDeviceToHost, g->stream));
-        CUDA_TRY(cudaStreamSynchronize(g->stream));
-        g->stats.other_launches++;
-        if (verr & 1) return set_err(MRC_ERR_ARG, "an edge has an endpoint outside [0,n)");
-        if (verr & 2) return set_err(MRC_ERR_ARG, "edges are not destination-sorted");
-        if (verr & 4) return set_err(MRC_ERR_ARG, "edge time must be strictly positive");
-        return MRC_OK;
+        return graph_validate(g);
     }();
     if (rc) { mrc_graph_destroy(g); return rc; }
     *out = g;
@@ -519,18 +539,61 @@ static int ensure_compact(mrc_graph *g) {
  *   - the predecessor graph holds a cycle that verifies negative-> NEG
  *   - (numeric) the cycle's ratio is >= lambda but within the rounding noise of the walk -> TIE
  *   - n passes done and still relaxing (reference rule :1252-1257)       -> NEG_NOCYCLE
+ *
+ * ProbeRun is that loop cut at the host round trip, so that a driver can put work of its own between the burst
+ * and the read-back (the multi-GPU driver enqueues an all-gather of the per-candidate records there):
+ *   begin()           arguments, dist = 0, pred = none
+ *   enqueue_burst()   relaxation launches + cycle check of the next burst on the graph's stream; no host wait
+ *   enqueue_readback() + (caller: cudaStreamSynchronize) + collect()   verdicts of that burst
+ *   drop()            a candidate whose verdict is implied by something the caller knows
  */
-static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
-                     unsigned flags, ProbeOut *res) {
+struct ProbeRun {
+    mrc_graph *g = nullptr;
+    bool exact = false;
+    int K = 0, KT = 1;
+    unsigned flags = 0;
+    double lam[MRC_KMAX];
+    ll a[MRC_KMAX], b[MRC_KMAX];
+    ProbeOut *res = nullptr;
+    RelaxArgs ra;
+    CheckArgs ca;
+    unsigned active = 0;
+    ll passes = 0, next_check = 0, max_passes = 0;
+    int burst = 0;
+    bool any_neg = false;
+    int new_verdicts = 0;
+    bool use_sparse = false, sparse_mode = false, may_compact = false;
+    int sp_in = 0, sp_ci = 0, look0 = 0, look = 0;
+    int ck = -1;   // slot served from the compact column, or -1
+    // the burst in flight
+    int nb = 0, dense_launches = 0;
+    bool sparse_burst = false, do_check = false;
+
+    int begin(mrc_graph *g_, bool exact_, int K_, const double *lam_, const ll *a_, const ll *b_, double slack, unsigned flags_,
+              ProbeOut *res_);
+    int plan_burst(int cap) const;   // passes the next burst would run (0: the pass limit is reached)
+    int enqueue_burst(int cap = 0);
+    int enqueue_readback();
+    int collect();
+    void drop(int k, int verdict) { if ((active >> k) & 1u) { res[k].verdict = verdict; res[k].passes = passes; active &= ~(1u << k); } }
+    void finish();
+};
+
+int ProbeRun::begin(mrc_graph *g_, bool exact_, int K_, const double *lam_, const ll *a_, const ll *b_, double slack,
+                    unsigned flags_, ProbeOut *res_) {
+    g = g_; exact = exact_; K = K_; flags = flags_; res = res_;
     if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
     if (K < 1 || K > MRC_KMAX) return set_err(MRC_ERR_ARG, "K must be in [1,%d]", MRC_KMAX);
     if (exact && !g->has_int) return set_err(MRC_ERR_NOT_INTEGER, "Exact mode requires integer weights");
     if (exact && !g->patches.empty()) return set_err(MRC_ERR_ARG, "exact probes on a patched graph are not supported");
     if (!exact && !(slack >= 0.0)) return set_err(MRC_ERR_ARG, "cycle slack must be >= 0");   // dist <= 0 is what makes the bit-pattern atomic a min
     CUDA_TRY(cudaSetDevice(g->device));
-    const int KT = kt_of(K);
+    KT = kt_of(K);
     const ll n = g->n, m = g->m;
     g->pot_valid = false;
+    for (int k = 0; k < K; k++) {
+        if (exact) { a[k] = a_[k]; b[k] = b_[k]; lam[k] = 0; } else { lam[k] = lam_[k]; a[k] = 0; b[k] = 1; }
+    }
     if (exact) {
         for (int k = 0; k < K; k++) {
             if (b[k] <= 0) return set_err(MRC_ERR_ARG, "denominator must be positive");
@@ -539,12 +602,10 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
                 return set_err(MRC_ERR_OVERFLOW, "int64 overflow: |b*cost - a*time| * n exceeds 2^62 for a=%lld b=%lld", a[k], b[k]);
         }
     }
-    RelaxArgs ra;
     memset(&ra, 0, sizeof ra);
     ra.src = g->d_src; ra.dst = g->d_dst; ra.cost = g->d_cost; ra.time = g->d_time;
     ra.icost = g->d_icost; ra.itime = g->d_itime; ra.dist = g->d_dist; ra.pred = g->d_pred; ra.m = m;
     ra.slack = slack; ra.n = n; ra.examined = &g->d_status->examined; ra.decided = &g->d_status->decided;
-    CheckArgs ca;
     memset(&ca, 0, sizeof ca);
     for (int k = 0; k < K; k++) {
         if (exact) { ra.a[k] = ca.a[k] = a[k]; ra.b[k] = ca.b[k] = b[k]; } else ra.lam[k] = ca.lam[k] = lam[k];
@@ -570,201 +631,230 @@ static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const l
     CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)n * KT * 8, g->stream));      // dist = 0 (:1148 / :829)
     CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)n * KT * 8, g->stream));   // pred = none (:1154)
     CUDA_TRY(cudaMemsetAsync(&g->d_status->decided, 0, sizeof(unsigned), g->stream));
-    unsigned active = (1u << K) - 1u;
-    const ll max_passes = n;   // n-1 passes + the detection pass
-    ll passes = 0;
-    int burst = g->burst_init;
-    ll next_check = g->burst_init;   // cycle checks after 2, 6, 14, 30, ... passes; convergence flags every burst
+    active = (1u << K) - 1u;
+    max_passes = n;   // n-1 passes + the detection pass
+    passes = 0;
+    burst = g->burst_init;
+    next_check = g->burst_init;   // cycle checks after 2, 6, 14, 30, ... passes; convergence flags every burst
     g->stats.probes += K;
-    bool any_neg = false;            // MRC_F_PATIENCE bookkeeping
-    int new_verdicts = 0;
+    any_neg = false;
+    new_verdicts = 0;
     // sparse passes (see relax_sparse_kernel): decided burst by burst from the number of vertices the last pass lowered
-    const bool use_sparse = g->sparse && m >= g->sparse_min_edges;
+    use_sparse = g->sparse && m >= g->sparse_min_edges;
     if (use_sparse) MRC_TRY(ensure_sparse(g));
-    bool sparse_mode = false;
-    int sp_in = 0, sp_ci = 0;
+    sparse_mode = false;
+    sp_in = sp_ci = 0;
     // dense sweeps until the active count is looked at again: every look is a host round trip (~30 us) plus a
     // compaction, worth it when a sweep costs 60-100 us (m >= 5 M edges), not when it costs 10-25 us
-    const int look0 = g->sparse_look > 0 ? g->sparse_look : (m >= 5000000 ? 2 : MRC_MAX_BURST);
-    int look = look0;
+    look0 = g->sparse_look > 0 ? g->sparse_look : (m >= 5000000 ? 2 : MRC_MAX_BURST);
+    look = look0;
     // compact survivor: once ONE candidate is left of a K >= 2 probe its column moves to [n][1] buffers
-    const bool may_compact = g->compact && KT > 1 && m >= g->compact_min_edges;
-    int ck = -1;   // slot served from the compact column, or -1
-    while (active) {
-        int nb = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
-        // while sweeping densely with the sparse passes available, look at the active count every few sweeps:
-        // a worklist pass is 5-10x cheaper than a sweep as soon as it applies
-        if (use_sparse && !sparse_mode && nb > look) nb = look;
-        if (nb <= 0) {
-            for (int k = 0; k < K; k++)
-                if ((active >> k) & 1u) { res[k].verdict = MRC_V_NEG_NOCYCLE; res[k].passes = passes; }
-            break;
+    may_compact = g->compact && KT > 1 && m >= g->compact_min_edges;
+    ck = -1;
+    nb = 0;
+    return MRC_OK;
+}
+
+int ProbeRun::plan_burst(int cap) const {
+    int want = (int)std::min<ll>(std::min<ll>(burst, std::max<ll>(1, next_check - passes)), max_passes - passes);
+    // while sweeping densely with the sparse passes available, look at the active count every few sweeps:
+    // a worklist pass is 5-10x cheaper than a sweep as soon as it applies
+    if (use_sparse && !sparse_mode && want > look) want = look;
+    if (cap > 0 && want > cap) want = cap;
+    return want;
+}
+
+int ProbeRun::enqueue_burst(int cap) {
+    const ll n = g->n;
+    nb = plan_burst(cap);
+    if (nb <= 0) {
+        for (int k = 0; k < K; k++) drop(k, MRC_V_NEG_NOCYCLE);
+        nb = 0;
+        return MRC_OK;
+    }
+    if (may_compact && ck < 0 && active && !(active & (active - 1))) {
+        MRC_TRY(ensure_compact(g));
+        ck = __builtin_ctz(active);
+        column_copy_kernel<<<std::min<int>((int)((n + 255) / 256), 8 * g->sms), 256, 0, g->stream>>>(
+            (const ull *)g->d_dist + ck, g->d_pred + ck, KT, (ull *)g->d_cdist, g->d_cpred, 1, n);
+        CUDA_TRY(cudaGetLastError());
+        g->stats.other_launches++;
+    }
+    CUDA_TRY(cudaMemsetAsync(g->d_status, 0, offsetof(DevStatus, cnt), g->stream));   // changed[] + examined
+    CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
+    ra.active = active;
+    dense_launches = 0;
+    sparse_burst = sparse_mode;
+    if (sparse_burst) {
+        // one cooperative launch runs the nb worklist passes of this burst
+        ra.changed = &g->d_status->changed[0];
+        ra.act_out = nullptr; ra.gate = nullptr;
+        MRC_TRY(launch_sparse(g, KT, exact, ra, sp_in, sp_ci, nb, ck));
+        g->bm1_dirty = true;   // either bitmap may now hold bits of a worklist that is never consumed
+    }
+    for (int i = 0; i < nb && !sparse_burst; i++) {
+        ra.changed = &g->d_status->changed[i];
+        ra.act_out = nullptr;
+        if (use_sparse && i == nb - 1) {
+            // the last dense launch of a burst records which vertices it lowered: the seed of a worklist
+            CUDA_TRY(cudaMemsetAsync(g->d_bm[0], 0, g->bm_bytes, g->stream));
+            ra.act_out = g->d_bm[0];
         }
-        if (may_compact && ck < 0 && !(active & (active - 1))) {
-            MRC_TRY(ensure_compact(g));
-            ck = __builtin_ctz(active);
-            column_copy_kernel<<<std::min<int>((int)((n + 255) / 256), 8 * g->sms), 256, 0, g->stream>>>(
-                (const ull *)g->d_dist + ck, g->d_pred + ck, KT, (ull *)g->d_cdist, g->d_cpred, 1, n);
-            CUDA_TRY(cudaGetLastError());
-            g->stats.other_launches++;
-        }
-        CUDA_TRY(cudaMemsetAsync(g->d_status, 0, offsetof(DevStatus, cnt), g->stream));   // changed[] + examined
-        CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
-        ra.active = active;
-        int dense_launches = 0;
-        const bool sparse_burst = sparse_mode;
-        if (sparse_burst) {
-            // one cooperative launch runs the nb worklist passes of this burst
-            ra.changed = &g->d_status->changed[0];
-            ra.act_out = nullptr; ra.gate = nullptr;
-            MRC_TRY(launch_sparse(g, KT, exact, ra, sp_in, sp_ci, nb, ck));
-            g->bm1_dirty = true;   // either bitmap may now hold bits of a worklist that is never consumed
-        }
-        for (int i = 0; i < nb && !sparse_burst; i++) {
-            ra.changed = &g->d_status->changed[i];
-            ra.act_out = nullptr;
-            if (use_sparse && i == nb - 1) {
-                // the last dense launch of a burst records which vertices it lowered: the seed of a worklist
-                CUDA_TRY(cudaMemsetAsync(g->d_bm[0], 0, g->bm_bytes, g->stream));
-                ra.act_out = g->d_bm[0];
-            }
-            dense_launches++;
-            // launch i > 0 skips the candidates launch i-1 did not move (fixed point) and returns at once if that is all of them
-            ra.gate = (i > 0 && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
-            MRC_TRY(launch_relax(g, KT, exact, ra, ck));
-        }
-        if (use_sparse && !sparse_burst) {
-            // bm[1] may hold the membership bits of a worklist nobody consumed (a probe that ended on a verified cycle,
-            // or a switch back to dense sweeps): the next worklist pass deduplicates through it, so it must be clean
-            if (g->bm1_dirty) { CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0, g->bm_bytes, g->stream)); g->bm1_dirty = false; }
-            CUDA_TRY(cudaMemsetAsync(&g->d_status->act_count, 0, 4 * sizeof(unsigned), g->stream));   // act_count + act_cnt[3]
-            compact_active_kernel<<<std::min<int>((int)((g->bm_bytes / 4 + 255) / 256), 4 * g->sms), 256, 0, g->stream>>>(
-                g->d_bm[0], (int)(g->bm_bytes / 4), g->d_wl[0], g->d_status, 0);
-            CUDA_TRY(cudaGetLastError());
-        }
-        CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
-        const bool do_check = passes + nb >= next_check || passes + nb >= max_passes;
-        if (do_check) {
-            ca.gate = g->gate ? &g->d_status->changed[nb - 1] : nullptr;
-            if (ck >= 0) {   // the survivor's predecessor graph lives in the compact column: a 1-wide check, results in slot 0
-                CheckArgs cc = ca;
-                cc.pred = g->d_cpred; cc.dist = g->d_cdist; cc.jump = g->d_cjump; cc.cyc_edges = g->d_cyc_edges + (ll)ck * g->cyc_cap;
-                cc.active = 1u; cc.k0 = ck; cc.prune_above = 0;
-                cc.lam[0] = ca.lam[ck]; cc.a[0] = ca.a[ck]; cc.b[0] = ca.b[ck];
-                cc.pe[0] = ca.pe[ck]; cc.pdc[0] = ca.pdc[ck]; cc.pdt[0] = ca.pdt[ck];
-                MRC_TRY(launch_check(g, 1, cc));
-            } else {
-                ca.active = active; ca.k0 = 0;
-                MRC_TRY(launch_check(g, KT, ca));
-            }
-            next_check = 2 * next_check + 2;
-        }
-        CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
-        CUDA_TRY(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, g->stream));
-        CUDA_TRY(cudaStreamSynchronize(g->stream));
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]));
-        if (sparse_burst) g->stats.sparse_ms += ms; else g->stats.relax_ms += ms;
-        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
-        const DevStatus &hs = *g->h_status;
-        // launches / passes that did work: the first of the burst, and each one whose predecessor still moved something
-        int ran = nb;
-        if (g->gate || sparse_burst)
-            for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
-        if (sparse_burst) {
-            dense_launches = 0;
-            g->stats.sparse_passes += ran;
-            g->stats.other_launches += 1;
-            sp_in ^= nb & 1; sp_ci = (sp_ci + nb) % 3;
-            if ((ll)hs.act_count * g->sparse_div > 2 * n) sparse_mode = false;   // the worklist grew back: sweep densely again
+        dense_launches++;
+        // launch i > 0 skips the candidates launch i-1 did not move (fixed point) and returns at once if that is all of them
+        ra.gate = (i > 0 && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
+        MRC_TRY(launch_relax(g, KT, exact, ra, ck));
+    }
+    if (use_sparse && !sparse_burst) {
+        // bm[1] may hold the membership bits of a worklist nobody consumed (a probe that ended on a verified cycle,
+        // or a switch back to dense sweeps): the next worklist pass deduplicates through it, so it must be clean
+        if (g->bm1_dirty) { CUDA_TRY(cudaMemsetAsync(g->d_bm[1], 0, g->bm_bytes, g->stream)); g->bm1_dirty = false; }
+        CUDA_TRY(cudaMemsetAsync(&g->d_status->act_count, 0, 4 * sizeof(unsigned), g->stream));   // act_count + act_cnt[3]
+        compact_active_kernel<<<std::min<int>((int)((g->bm_bytes / 4 + 255) / 256), 4 * g->sms), 256, 0, g->stream>>>(
+            g->d_bm[0], (int)(g->bm_bytes / 4), g->d_wl[0], g->d_status, 0);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(g->ev[1], g->stream));
+    do_check = passes + nb >= next_check || passes + nb >= max_passes;
+    if (do_check) {
+        ca.gate = g->gate ? &g->d_status->changed[nb - 1] : nullptr;
+        if (ck >= 0) {   // the survivor's predecessor graph lives in the compact column: a 1-wide check, results in slot 0
+            CheckArgs cc = ca;
+            cc.pred = g->d_cpred; cc.dist = g->d_cdist; cc.jump = g->d_cjump; cc.cyc_edges = g->d_cyc_edges + (ll)ck * g->cyc_cap;
+            cc.active = 1u; cc.k0 = ck; cc.prune_above = 0;
+            cc.lam[0] = ca.lam[ck]; cc.a[0] = ca.a[ck]; cc.b[0] = ca.b[ck];
+            cc.pe[0] = ca.pe[ck]; cc.pdc[0] = ca.pdc[ck]; cc.pdt[0] = ca.pdt[ck];
+            MRC_TRY(launch_check(g, 1, cc));
         } else {
-            dense_launches = ran;
-            g->stats.relax_launches += ran;
-            g->stats.other_launches += nb - ran + (use_sparse ? 1 : 0);
-            if (use_sparse) {
-                const ll scaled = (ll)hs.act_cnt[0] * g->sparse_div;   // size of the worklist compacted from the last sweep
-                if (scaled < n) { sparse_mode = true; sp_in = 0; sp_ci = 0; }
-                // far from the threshold: look again later (every look costs a host round trip)
-                look = scaled > 8 * n ? 8 * look0 : scaled > 4 * n ? 4 * look0 : scaled > 2 * n ? 2 * look0 : look0;
-            }
+            ca.active = active; ca.k0 = 0;
+            MRC_TRY(launch_check(g, KT, ca));
         }
-        // per-candidate work of the burst: launch i relaxed candidate k iff no earlier launch of the burst had left it unmoved
-        {
-            int64_t slots = 0;
-            for (int k = 0; k < K; k++) {
-                if (!((active >> k) & 1u)) continue;
-                int w = 1;
-                while (w < nb && ((hs.changed[w - 1] >> k) & 1u)) w++;
-                slots += w;
-            }
-            if (sparse_burst) g->stats.relax_edge_visits += (int64_t)hs.examined * __builtin_popcount(active);
-            else g->stats.relax_edge_visits += slots * m;
-            g->stats.relax_edge_slots += slots * m;
+        next_check = g->check_every > 0 ? next_check + g->check_every : 2 * next_check + 2;
+    }
+    CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
+    return MRC_OK;
+}
+
+int ProbeRun::enqueue_readback() {
+    CUDA_TRY(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, g->stream));
+    return MRC_OK;
+}
+
+// after the stream has been synchronised: verdicts of the burst enqueue_burst() launched
+int ProbeRun::collect() {
+    if (nb <= 0) return MRC_OK;
+    const ll n = g->n, m = g->m;
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]));
+    if (sparse_burst) g->stats.sparse_ms += ms; else g->stats.relax_ms += ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
+    const DevStatus &hs = *g->h_status;
+    // launches / passes that did work: the first of the burst, and each one whose predecessor still moved something
+    int ran = nb;
+    if (g->gate || sparse_burst)
+        for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
+    if (sparse_burst) {
+        g->stats.sparse_passes += ran;
+        g->stats.other_launches += 1;
+        sp_in ^= nb & 1; sp_ci = (sp_ci + nb) % 3;
+        if ((ll)hs.act_count * g->sparse_div > 2 * n) sparse_mode = false;   // the worklist grew back: sweep densely again
+    } else {
+        g->stats.relax_launches += ran;
+        g->stats.other_launches += nb - ran + (use_sparse ? 1 : 0);
+        if (use_sparse) {
+            const ll scaled = (ll)hs.act_cnt[0] * g->sparse_div;   // size of the worklist compacted from the last sweep
+            if (scaled < n) { sparse_mode = true; sp_in = 0; sp_ci = 0; }
+            // far from the threshold: look again later (every look costs a host round trip)
+            look = scaled > 8 * n ? 8 * look0 : scaled > 4 * n ? 4 * look0 : scaled > 2 * n ? 2 * look0 : look0;
         }
-        if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += hs.cuts; }
-        g->stats.d2h_bytes += sizeof(DevStatus);
+    }
+    // per-candidate work of the burst: launch i relaxed candidate k iff no earlier launch of the burst had left it unmoved
+    {
+        int64_t slots = 0;
         for (int k = 0; k < K; k++) {
             if (!((active >> k) & 1u)) continue;
-            int conv_at = -1;
-            for (int i = 0; i < nb && conv_at < 0; i++) if (!((hs.changed[i] >> k) & 1u)) conv_at = i;
-            ProbeOut &o = res[k];
-            const int ko = ck >= 0 ? 0 : k;   // slot of candidate k in the check's output
-            if (conv_at >= 0) { o.verdict = MRC_V_NONNEG; o.passes = passes + conv_at + 1; }
-            else if (do_check && ((hs.cyc_mask >> ko) & 1u) && hs.out[ko].found) {
-                // the check kernel extracted a cycle and tested it against lambda on the device:
-                // found == 1 verified negative, 2 rounding tie; cycles that are neither were cut there
-                const CycleOut &c = hs.out[ko];
-                o.verdict = (c.found == 1) ? MRC_V_NEG : MRC_V_TIE;
-                o.len = c.len; o.minv = c.minv; o.start = c.pad; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
-                o.passes = passes + nb;
-                any_neg |= c.found == 1;
-            }
-            if (o.verdict >= 0) { active &= ~(1u << k); new_verdicts++; }
+            int w = 1;
+            while (w < nb && ((hs.changed[w - 1] >> k) & 1u)) w++;
+            slots += w;
         }
-        passes += nb;
-        if (flags & MRC_F_MONOTONE_PRUNE) {
-            // verdicts are monotone in lambda: NEG at x implies NEG above x, NONNEG at x implies NONNEG below x
-            for (int k = 0; k < K; k++) {
-                if (res[k].verdict != MRC_V_NEG && res[k].verdict != MRC_V_NONNEG) continue;
-                for (int j = 0; j < K; j++) {
-                    if (!((active >> j) & 1u)) continue;
-                    bool above = exact ? ((i128)a[j] * b[k] > (i128)a[k] * b[j]) : (lam[j] > lam[k]);
-                    bool below = exact ? ((i128)a[j] * b[k] < (i128)a[k] * b[j]) : (lam[j] < lam[k]);
-                    // a verified cycle of ratio r is negative for every lambda > r, not only above lambda_k
-                    if (res[k].verdict == MRC_V_NEG && !exact && res[k].sumt > 0 && lam[j] > res[k].sumc / res[k].sumt) above = true;
-                    if (res[k].verdict == MRC_V_NEG && exact && (i128)a[j] * res[k].isumt > (i128)res[k].isumc * b[j]) above = true;
-                    if (res[k].verdict == MRC_V_NEG && above) { res[j].verdict = MRC_V_SKIPPED_NEG; res[j].passes = passes; active &= ~(1u << j); }
-                    if (res[k].verdict == MRC_V_NONNEG && below) { res[j].verdict = MRC_V_SKIPPED_NONNEG; res[j].passes = passes; active &= ~(1u << j); }
-                }
-            }
-        }
-        // ... but not before the second check (pass 6): the candidates closest to lambda* close their cycle a few
-        // passes later than the far ones and are the ones worth waiting for (measured: stopping at pass 2
-        // needs 10 rounds instead of 4).
-        if ((flags & MRC_F_STOP_ON_NEG) && active && do_check && passes >= 6) {
-            bool neg_now = false;
-            for (int k = 0; k < K; k++) neg_now |= res[k].verdict == MRC_V_NEG;
-            if (neg_now) {
-                for (int k = 0; k < K; k++)
-                    if ((active >> k) & 1u) { res[k].verdict = MRC_V_ABANDONED; res[k].passes = passes; }
-                active = 0;
-            }
-        }
-        // MRC_F_PATIENCE: a negative cycle is in hand and a whole check interval (as long as everything before it)
-        // brought no further verdict -- what is still open is a slow candidate next to lambda*; leave it undecided.
-        if ((flags & MRC_F_PATIENCE) && active && do_check) {
-            if (any_neg && new_verdicts == 0) {
-                for (int k = 0; k < K; k++)
-                    if ((active >> k) & 1u) { res[k].verdict = MRC_V_ABANDONED; res[k].passes = passes; }
-                active = 0;
-            }
-            new_verdicts = 0;
-        }
-        burst = std::min(burst * 2, g->burst_max);
+        if (sparse_burst) g->stats.relax_edge_visits += (int64_t)hs.examined * __builtin_popcount(active);
+        else g->stats.relax_edge_visits += slots * m;
+        g->stats.relax_edge_slots += slots * m;
     }
+    if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += hs.cuts; }
+    g->stats.d2h_bytes += sizeof(DevStatus);
+    for (int k = 0; k < K; k++) {
+        if (!((active >> k) & 1u)) continue;
+        int conv_at = -1;
+        for (int i = 0; i < nb && conv_at < 0; i++) if (!((hs.changed[i] >> k) & 1u)) conv_at = i;
+        ProbeOut &o = res[k];
+        const int ko = ck >= 0 ? 0 : k;   // slot of candidate k in the check's output
+        if (conv_at >= 0) { o.verdict = MRC_V_NONNEG; o.passes = passes + conv_at + 1; }
+        else if (do_check && ((hs.cyc_mask >> ko) & 1u) && hs.out[ko].found) {
+            // the check kernel extracted a cycle and tested it against lambda on the device:
+            // found == 1 verified negative, 2 rounding tie; cycles that are neither were cut there
+            const CycleOut &c = hs.out[ko];
+            o.verdict = (c.found == 1) ? MRC_V_NEG : MRC_V_TIE;
+            o.len = c.len; o.minv = c.minv; o.start = c.pad; o.sumc = c.sumc; o.sumt = c.sumt; o.isumc = c.isumc; o.isumt = c.isumt;
+            o.passes = passes + nb;
+            any_neg |= c.found == 1;
+        }
+        if (o.verdict >= 0) { active &= ~(1u << k); new_verdicts++; }
+    }
+    passes += nb;
+    if (flags & MRC_F_MONOTONE_PRUNE) {
+        // verdicts are monotone in lambda: NEG at x implies NEG above x, NONNEG at x implies NONNEG below x
+        for (int k = 0; k < K; k++) {
+            if (res[k].verdict != MRC_V_NEG && res[k].verdict != MRC_V_NONNEG) continue;
+            for (int j = 0; j < K; j++) {
+                if (!((active >> j) & 1u)) continue;
+                bool above = exact ? ((i128)a[j] * b[k] > (i128)a[k] * b[j]) : (lam[j] > lam[k]);
+                bool below = exact ? ((i128)a[j] * b[k] < (i128)a[k] * b[j]) : (lam[j] < lam[k]);
+                // a verified cycle of ratio r is negative for every lambda > r, not only above lambda_k
+                if (res[k].verdict == MRC_V_NEG && !exact && res[k].sumt > 0 && lam[j] > res[k].sumc / res[k].sumt) above = true;
+                if (res[k].verdict == MRC_V_NEG && exact && (i128)a[j] * res[k].isumt > (i128)res[k].isumc * b[j]) above = true;
+                if (res[k].verdict == MRC_V_NEG && above) drop(j, MRC_V_SKIPPED_NEG);
+                if (res[k].verdict == MRC_V_NONNEG && below) drop(j, MRC_V_SKIPPED_NONNEG);
+            }
+        }
+    }
+    // ... but not before the second check (pass 6): the candidates closest to lambda* close their cycle a few
+    // passes later than the far ones and are the ones worth waiting for (measured: stopping at pass 2
+    // needs 10 rounds instead of 4).
+    if ((flags & MRC_F_STOP_ON_NEG) && active && do_check && passes >= 6) {
+        bool neg_now = false;
+        for (int k = 0; k < K; k++) neg_now |= res[k].verdict == MRC_V_NEG;
+        if (neg_now) for (int k = 0; k < K; k++) drop(k, MRC_V_ABANDONED);
+    }
+    // MRC_F_PATIENCE: a negative cycle is in hand and a whole check interval (as long as everything before it)
+    // brought no further verdict -- what is still open is a slow candidate next to lambda*; leave it undecided.
+    if ((flags & MRC_F_PATIENCE) && active && do_check) {
+        if (any_neg && new_verdicts == 0) for (int k = 0; k < K; k++) drop(k, MRC_V_ABANDONED);
+        new_verdicts = 0;
+    }
+    burst = std::min(burst * 2, g->burst_max);
+    nb = 0;
+    return MRC_OK;
+}
+
+void ProbeRun::finish() {
     if (exact && K == 1 && res[0].verdict == MRC_V_NONNEG) { g->pot_valid = true; g->pot_a = a[0]; g->pot_b = b[0]; }
     for (int k = 0; k < K; k++) g->last_res[k] = res[k];
     g->last_exact = exact; g->last_K = K;
+}
+
+static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
+                     unsigned flags, ProbeOut *res) {
+    ProbeRun pr;
+    MRC_TRY(pr.begin(g, exact, K, lam, a, b, slack, flags, res));
+    while (pr.active) {
+        MRC_TRY(pr.enqueue_burst());
+        if (pr.nb <= 0) break;
+        MRC_TRY(pr.enqueue_readback());
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        MRC_TRY(pr.collect());
+    }
+    pr.finish();
     return MRC_OK;
 }
 
@@ -974,6 +1064,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "compact") g->compact = value != 0;
     else if (s == "compact_min_edges") g->compact_min_edges = std::max(0, value);
     else if (s == "lookahead") g->lookahead = value != 0;
+    else if (s == "check_every") g->check_every = std::max(0, value);
     else if (s == "gate") g->gate = value != 0;
     else if (s == "sparse") g->sparse = value != 0;
     else if (s == "sparse_div") g->sparse_div = std::max(1, value);
@@ -1024,6 +1115,7 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
     double lam[MRC_KMAX], cr[MRC_KMAX];
     int32_t vd[MRC_KMAX];
     ProbeOut res[MRC_KMAX];
+    const bool trace = getenv("MRC_B200_TRACE") != nullptr;
     for (int i = 0; i < max_iter; i++) {
         it = i;
         if (max_seconds > 0) {   // solver.py:1032-1041
@@ -1042,6 +1134,11 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
         for (int k = 0; k < K; k++) {
             vd[k] = res[k].verdict;
             cr[k] = (vd[k] == MRC_V_NEG || vd[k] == MRC_V_TIE) ? res[k].sumc / res[k].sumt : NAN;
+        }
+        if (trace) {
+            fprintf(stderr, "  round %d:", i);
+            for (int k = 0; k < K; k++) fprintf(stderr, " [%.12g v%d p%lld len %d r=%.12g]", lam[k], vd[k], (long long)res[k].passes, res[k].len, cr[k]);
+            fprintf(stderr, "\n");
         }
         int best = -1;
         MRC_TRY(mrc_reduce_round(K, lam, vd, cr, &lo, &hi, &have_cycle, &best));
@@ -1453,3 +1550,4 @@ extern "C" int mrc_batch_solve_numeric(int64_t B, const int32_t *nverts, const i
     return rc;
 }
 
+#include "mrc_comm.cuh"

@@ -318,12 +318,14 @@ template <> struct WeightT<true> { typedef ll type; };
 #define MRC_TUNE_MB12 4
 #endif
 #ifndef MRC_TUNE_PF
-#define MRC_TUNE_PF (K <= 2)
+#define MRC_TUNE_PF (K <= 4)
 #endif
 template <int K> struct RelaxTune {
     static constexpr int rows = MRC_TUNE_ROWS, minblocks = K <= 2 ? MRC_TUNE_MB12 : MRC_TUNE_MB;
-    // K <= 2 (registers to spare): the edge stream of the NEXT chunk is requested before this chunk's gathers are
-    // issued, so the HBM latency of the stream overlaps the L2 latency of the dist gathers (-8 % per pass at K = 1)
+    // K <= 4: the edge stream of the NEXT chunk is requested before this chunk's gathers are issued, so the HBM latency
+    // of the stream overlaps the L2 latency of the dist gathers and, in the update-heavy first passes, the winner
+    // resolution (B200, C3: K=1 -8 % per steady pass; K=4 pass 1 157 -> 116 us, pass 2 103 -> 80, steady 60 -> 58);
+    // at K = 8 (two halves) the extra registers cost more than the overlap wins (101 -> 120 us)
     static constexpr bool prefetch = MRC_TUNE_PF;
 };
 template <int K, bool EXACT, bool SCEN>

@@ -1,51 +1,83 @@
 """
-Launched with torchrun on N GPUs: checks the two sharding modes against single-GPU results.
-  (1) lambda-candidate sharding on a 100k/1M float graph == local mrc_solve_numeric (ratio within 1e-12)
-  (2) graph-batch sharding of 64 currency graphs == local batch solve
+Multi-GPU checks of the in-library sharded search (csrc/mrc_comm.cuh) against single-GPU results.
+  torchrun (one process per GPU):  python -m torch.distributed.run --nproc-per-node N tools/multi_gpu_check.py
+      Comm.from_torch + DeviceGraph.replicated + solve_numeric_sharded on C3 (or N/M env) == local mrc_solve_numeric
+  single process:                  python tools/multi_gpu_check.py group
+      Comm.group(all devices) + MultiGraph.solve_numeric == local mrc_solve_numeric
 """
-import os, sys
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.distributed as dist
-from min_ratio_cycle_b200 import _native as N, sharded, synthetic, batch
-from min_ratio_cycle_b200.solver import SolverConfig, LogLevel
+import numpy as np
+from min_ratio_cycle_b200 import _native as N, synthetic
 
+n = int(os.environ.get("N", 1_000_000)); m = int(os.environ.get("M", 10_000_000)); K = int(os.environ.get("KLOCAL", 4))
+seeds = [int(x) for x in os.environ.get("SEEDS", "0").split(",")]
+reps = int(os.environ.get("REPS", 5))
+
+
+def graph(seed):
+    _, U, V, C, T = synthetic.random_float(n, m, seed=seed)
+    o = np.argsort(V, kind="stable")
+    return U[o].astype(np.int32), V[o].astype(np.int32), C[o], T[o]
+
+
+def same(a, b):
+    return a["rc"] == b["rc"] == N.OK and abs(a["ratio"] - b["ratio"]) <= 1e-12 * max(1.0, abs(b["ratio"])) and a["cycle"] == b["cycle"]
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "group":
+    ndev = N.device_count()
+    for W in sorted({1, min(2, ndev), ndev}):
+        comm = N.Comm.group(list(range(W)))
+        for seed in seeds:
+            U, V, C, T = graph(seed)
+            g = N.DeviceGraph(n, U, V, C, T)
+            lo, hi = g.bounds()
+            ref = g.solve_numeric(lo, hi, K=K)
+            t0 = time.perf_counter()
+            mg = N.MultiGraph(comm, n, U, V, C, T)
+            t_rep = time.perf_counter() - t0
+            for kl in (K, 1):
+                out = mg.solve_numeric(lo, hi, K_local=kl)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    out = mg.solve_numeric(lo, hi, K_local=kl)
+                dt = (time.perf_counter() - t0) / reps
+                assert same(out, ref), (W, seed, kl, out["ratio"], ref["ratio"], out["cycle"][:8], ref["cycle"][:8], out["rc"])
+                print(f"group x{W} seed {seed} K_local {kl}: {dt*1e3:.2f} ms/solve ticks {out['ticks']} probes(rank0) {out['iterations']} "
+                      f"(replication {t_rep*1e3:.1f} ms); single GPU K={K}: rounds {ref['iterations']}", flush=True)
+            mg.close(); g.close()
+        comm.close()
+    print("multi_gpu_check group OK")
+    sys.exit(0)
+
+import torch, torch.distributed as dist
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-n, U, V, C, T = synthetic.random_float(100_000, 1_000_000, seed=3)
-o = np.argsort(V, kind="stable")
-g = N.DeviceGraph(n, U[o], V[o], C[o], T[o], device=local)
-lo, hi = g.bounds()
-ref = g.solve_numeric(lo, hi, K=4)
-r = sharded.solve_numeric_sharded(lambda l, s, f: g.probe_numeric(l, s, f), lo, hi, K_local=4, fetch=g.fetch_cycle_sums)
-assert r.rc == N.OK and abs(r.ratio - ref["ratio"]) <= 1e-12, (r.ratio, ref["ratio"])
-assert r.cycle == ref["cycle"], (r.cycle, ref["cycle"])
-graphs = [synthetic.currency_graph(64, 2000 + i) for i in range(64)]
-cfg = SolverConfig(log_level=LogLevel.NONE, gpu_device=local)
-allr = batch.solve_min_ratio_cycle_batch_sharded(graphs, cfg)
-mine = batch.solve_min_ratio_cycle_batch(graphs, cfg)
-assert len(allr) == 64 and all(a.ratio == b.ratio and a.cycle == b.cycle for a, b in zip(allr, mine))
-# C4 at full size: 4,096 currency graphs split over the ranks (independent units, no data-path collective)
-import time
-B = 4096
-mine_idx = sharded.shard_units(B, rank, world)
-big = [synthetic.currency_graph(64, 1000 + i) for i in mine_idx]
-nv, off, S, D, Cs, Ts = batch._prepare(big, True)
-N.batch_solve_numeric(nv, off, S, D, Cs, Ts, K=4, device=local)           # warm-up
-torch.cuda.synchronize(); dist.barrier()
-t0 = time.perf_counter()
-outb = N.batch_solve_numeric(nv, off, S, D, Cs, Ts, K=4, device=local)
-torch.cuda.synchronize()
-loc = torch.tensor([time.perf_counter() - t0, outb["stats"]["relax_ms"] * 1e-3, float(outb["stats"]["relax_edge_visits"]),
-                    float((outb["status"] == 0).sum())], dtype=torch.float64, device="cuda")
-allv = [torch.zeros_like(loc) for _ in range(world)]
-dist.all_gather(allv, loc)
-allv = torch.stack(allv).cpu().numpy()
-dist.barrier()
+comm = N.Comm.from_torch(local)
+for seed in seeds:
+    U, V, C, T = graph(seed) if rank == 0 else (None, None, None, None)
+    t0 = time.perf_counter()
+    g = N.DeviceGraph.replicated(comm, n, m, U, V, C, T)
+    torch.cuda.synchronize(); dist.barrier()
+    t_rep = time.perf_counter() - t0
+    lo, hi = g.bounds()
+    ref = g.solve_numeric(lo, hi, K=K)
+    for kl in (K, 1):
+        out = g.solve_numeric_sharded(comm, lo, hi, K_local=kl)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = g.solve_numeric_sharded(comm, lo, hi, K_local=kl)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        assert same(out, ref), (rank, seed, kl, out["ratio"], ref["ratio"], out["cycle"][:8], ref["cycle"][:8], out["rc"])
+        if rank == 0:
+            print(f"torchrun x{world} seed {seed} K_local {kl}: {dt*1e3:.2f} ms/solve ticks {out['ticks']} probes(rank0) {out['iterations']} "
+                  f"(replication {t_rep*1e3:.1f} ms incl. barrier); single GPU K={K}: rounds {ref['iterations']}", flush=True)
+    g.close()
+comm.close()
 if rank == 0:
-    print(f"C4 sharded x{world}: {int(allv[:,3].sum())}/{B} solved; call time max over ranks {1e3*allv[:,0].max():.1f} ms "
-          f"(kernel {1e3*allv[:,1].max():.2f} ms); {allv[:,2].sum()/allv[:,1].max()/1e9:.0f} G edge-relax/s aggregate (kernel time)")
-if rank == 0:
-    print(f"multi_gpu_check OK world={world}: sharded ratio {r.ratio!r} rounds {r.iterations} (single-GPU rounds {ref['iterations']}); "
-          f"batch of 64 graphs identical across sharding")
+    print(f"multi_gpu_check torchrun OK world={world}")
 dist.destroy_process_group()
