@@ -62,6 +62,10 @@ extern "C" {
                                    interval (as long as everything before it) brought no further verdict; the open
                                    candidates -- slow ones next to lambda* -- are reported MRC_V_ABANDONED */
 
+#define MRC_F_CERT_FIRST 16u     /* the LAST candidate is the certifier of a cycle the caller already holds (lambda = its ratio minus a
+                                   sliver): the one probe that can end the search.  Once the second cycle check (pass 6) has
+                                   passed without any candidate turning negative, the other candidates -- whose verdicts could
+                                   only raise the lower end -- are reported MRC_V_ABANDONED and the certifier continues alone */
 #define MRC_F_NO_CYCLES 8u       /* do not bring the cycles to the host: cyc_len is the length each would have, the sums are the
                                    device's (accumulated along the predecessor walk); the one cycle the caller wants is
                                    fetched afterwards with mrc_fetch_cycle_sums.  Ignored by mrc_probe_numeric_scenarios. */
@@ -137,6 +141,14 @@ int mrc_probe_numeric_scenarios(mrc_graph *g, const double *lam, int K, double s
                                 const int64_t *patch_edge, const double *dcost, const double *dtime, int32_t *verdict,
                                 int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap, double *sum_cost,
                                 double *sum_time, int64_t *passes);
+
+/* sensitivity_analysis (solver.py:1699-1729) for S single-edge scenarios in one call: verdict[s] (MRC_V_*) of the probe at
+ * lam[s] on the graph with edge[s] (dst-sorted index, -1 = none) perturbed by (dcost[s], dtime[s]); K scenarios share every
+ * edge sweep, and every group starts from the converged potentials of ONE base probe at lam_base on the unperturbed graph
+ * (normally the certifier of the caller's optimum), so a scenario that leaves the optimum alone costs one or two sweeps.
+ * NONNEG = no negative cycle at lam[s] in that scenario.  The device-resident arrays are not modified. */
+int mrc_scenarios_certify(mrc_graph *g, int64_t S, const int64_t *edge, const double *dcost, const double *dtime,
+                          const double *lam, double lam_base, double slack, int K, int32_t *verdict, int64_t *passes);
 
 /* Full cycle of candidate k of the LAST probe (numeric or exact), for callers that probed with a small
  * cyc_cap: CLOSED vertex list; *cycle_len = 0 if that candidate extracted none. */

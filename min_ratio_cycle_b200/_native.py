@@ -26,6 +26,7 @@ F_MONOTONE_PRUNE = 1
 F_STOP_ON_NEG = 2
 F_PATIENCE = 4
 F_NO_CYCLES = 8
+F_CERT_FIRST = 16
 
 EXPORTS = [
     "mrc_abi_version", "mrc_last_error", "mrc_device_count", "mrc_graph_create", "mrc_graph_destroy",
@@ -35,7 +36,7 @@ EXPORTS = [
     "mrc_bench_relax", "mrc_set_option", "mrc_batch_solve_numeric", "mrc_fetch_cycle", "mrc_fetch_cycle_sums", "mrc_sort_edges_by_dst", "mrc_probe_numeric_scenarios",
     "mrc_comm_unique_id", "mrc_comm_init_rank", "mrc_comm_init", "mrc_comm_destroy", "mrc_comm_info",
     "mrc_graph_create_replicated", "mrc_solve_numeric_sharded", "mrc_mgraph_create", "mrc_mgraph_destroy", "mrc_mgraph_graph",
-    "mrc_mgraph_solve_numeric", "mrc_shard_fold",
+    "mrc_mgraph_solve_numeric", "mrc_shard_fold", "mrc_scenarios_certify",
 ]
 
 
@@ -120,6 +121,7 @@ def lib():
     L.mrc_mgraph_graph.argtypes = [vp, C.c_int]
     L.mrc_mgraph_solve_numeric.argtypes = [vp] + sharded_tail
     L.mrc_shard_fold.argtypes = [C.c_int, pd, pd, pd, pi, pi, pu8]
+    L.mrc_scenarios_certify.argtypes = [vp, C.c_int64, p64, pd, pd, pd, C.c_double, C.c_double, C.c_int, p32, p64]
     for name in EXPORTS:
         if name == "mrc_mgraph_graph":
             getattr(L, name).restype = vp
@@ -282,6 +284,20 @@ class DeviceGraph:
                                                 _ptr(st, C.c_double), _ptr(ps, C.c_int64)))
         return [dict(lam=float(lam[k]), verdict=int(vd[k]), cycle=self._cycle_of(k, buf, cap, int(cl[k])),
                      sum_cost=float(sc[k]), sum_time=float(st[k]), passes=int(ps[k])) for k in range(K)]
+
+    def scenarios_certify(self, edge, dcost, dtime, lams, lam_base: float, slack: float = 1e-15, K: int = 8):
+        """mrc_scenarios_certify: (verdicts int32[S], passes int64[S]) for S single-edge scenarios."""
+        edge = np.ascontiguousarray(edge, dtype=np.int64)
+        dc = np.ascontiguousarray(dcost, dtype=np.float64)
+        dt = np.ascontiguousarray(dtime, dtype=np.float64)
+        lam = np.ascontiguousarray(lams, dtype=np.float64)
+        S = len(edge)
+        verdict = np.full(S, -1, np.int32)
+        passes = np.zeros(S, np.int64)
+        check(lib().mrc_scenarios_certify(self._h, S, _ptr(edge, C.c_int64), _ptr(dc, C.c_double), _ptr(dt, C.c_double),
+                                          _ptr(lam, C.c_double), float(lam_base), float(slack), int(K),
+                                          _ptr(verdict, C.c_int32), _ptr(passes, C.c_int64)))
+        return verdict, passes
 
     def probe_exact(self, a, b, flags: int = 0, cyc_cap: int | None = None):
         a = np.ascontiguousarray(a, dtype=np.int64); b = np.ascontiguousarray(b, dtype=np.int64)

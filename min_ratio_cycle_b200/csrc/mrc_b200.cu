@@ -94,9 +94,12 @@ struct mrc_graph {
     int narrow = 1;              // option "narrow": late passes run the narrowest kernel covering the undecided candidates
     int compact = 1;             // option "compact": a probe narrowed to ONE live slot continues on a compact [n][1] copy of its column
     ll compact_min_edges = 2000000;   // ... on graphs where a sweep is bandwidth-bound (smaller ones are launch-bound)
+    int cert_first = 1;          // option "cert_first": mrc_solve_numeric passes MRC_F_CERT_FIRST to the probes of rounds that hold a cycle
+    int tick_max = 8;            // option "tick_max": longest tick (passes between two exchanges) of the sharded search
     int check_every = 0;         // option "check_every" (experiments): cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
     int lookahead = 1;           // option "lookahead": the next burst is enqueued before the previous burst's status is read
     void *d_cdist = nullptr; ull *d_cpred = nullptr; int *d_cjump = nullptr;   // compact column (compact survivor)
+    void *d_base = nullptr;      // [n] potentials of the base probe of mrc_scenarios_certify
     mrc_stats stats;
 };
 
@@ -171,7 +174,7 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
         void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
                         g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
                         g->d_keys, g->d_verr, g->d_out_off, g->d_out_edge,
-                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges, g->d_cdist, g->d_cpred, g->d_cjump};
+                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges, g->d_cdist, g->d_cpred, g->d_cjump, g->d_base};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
         cudaStreamSynchronize(g->stream);
     }
@@ -565,6 +568,7 @@ struct ProbeRun {
     bool use_sparse = false, sparse_mode = false, may_compact = false;
     int sp_in = 0, sp_ci = 0, look0 = 0, look = 0;
     int ck = -1;   // slot served from the compact column, or -1
+    const void *warm_from = nullptr;   // [n] potentials every candidate starts from instead of zero (set before begin())
     // the burst in flight
     int nb = 0, dense_launches = 0;
     bool sparse_burst = false, do_check = false;
@@ -628,7 +632,12 @@ int ProbeRun::begin(mrc_graph *g_, bool exact_, int K_, const double *lam_, cons
     }
     { int r = 1; while (((ll)1 << r) < n + 1) r++; ca.rounds = std::min(r + 1, MRC_MAX_ROUNDS); }
 
-    CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)n * KT * 8, g->stream));      // dist = 0 (:1148 / :829)
+    if (warm_from) {
+        broadcast_column_kernel<<<std::min<int>((int)((n * KT + 255) / 256), 8 * g->sms), 256, 0, g->stream>>>(
+            (const ull *)warm_from, (ull *)g->d_dist, KT, n);
+        CUDA_TRY(cudaGetLastError());
+        g->stats.other_launches++;
+    } else CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)n * KT * 8, g->stream));   // dist = 0 (:1148 / :829)
     CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)n * KT * 8, g->stream));   // pred = none (:1154)
     CUDA_TRY(cudaMemsetAsync(&g->d_status->decided, 0, sizeof(unsigned), g->stream));
     active = (1u << K) - 1u;
@@ -826,6 +835,14 @@ int ProbeRun::collect() {
         for (int k = 0; k < K; k++) neg_now |= res[k].verdict == MRC_V_NEG;
         if (neg_now) for (int k = 0; k < K; k++) drop(k, MRC_V_ABANDONED);
     }
+    // MRC_F_CERT_FIRST: nothing turned negative by the second check and the certifier (last candidate) is still
+    // relaxing -- its companions can only raise lo, which is worthless if the certifier converges and unnecessary if it
+    // does not (its cycle then moves hi); it continues alone (1-wide kernel, compact column)
+    if ((flags & MRC_F_CERT_FIRST) && do_check && passes >= 6 && K > 1 && ((active >> (K - 1)) & 1u) && (active & (active - 1))) {
+        bool neg_seen = false;
+        for (int k = 0; k < K; k++) neg_seen |= res[k].verdict == MRC_V_NEG || res[k].verdict == MRC_V_TIE || res[k].verdict == MRC_V_SKIPPED_NEG;
+        if (!neg_seen) for (int k = 0; k + 1 < K; k++) drop(k, MRC_V_ABANDONED);
+    }
     // MRC_F_PATIENCE: a negative cycle is in hand and a whole check interval (as long as everything before it)
     // brought no further verdict -- what is still open is a slow candidate next to lambda*; leave it undecided.
     if ((flags & MRC_F_PATIENCE) && active && do_check) {
@@ -1017,6 +1034,58 @@ extern "C" int mrc_probe_numeric_scenarios(mrc_graph *g, const double *lam, int 
     return rc;
 }
 
+/*
+ * sensitivity_analysis (solver.py:1699-1729), the part that dominates it: S single-edge scenarios, for each the question
+ * "is there a negative cycle at lam[s] on the graph with edge[s] perturbed?" -- lam[s] being the ratio of the cycle the
+ * caller holds under that scenario's weights minus a sliver, so NONNEG means that cycle is still optimal there.
+ * One base probe at lam_base on the UNPERTURBED graph leaves converged potentials; every group of K scenarios then
+ * starts from them instead of zero.  An edge whose cost went up leaves those potentials feasible (one sweep that
+ * lowers nothing); one whose cost went down lowers a few vertices around it.  Either way a scenario costs a sweep or
+ * two instead of the 20-50 a cold probe needs, and no host language loop runs between the groups.
+ */
+extern "C" int mrc_scenarios_certify(mrc_graph *g, int64_t S, const int64_t *edge, const double *dcost, const double *dtime,
+                                     const double *lam, double lam_base, double slack, int K, int32_t *verdict,
+                                     int64_t *passes) {
+    if (!g || S < 0 || (S && (!edge || !dcost || !dtime || !lam || !verdict))) return set_err(MRC_ERR_ARG, "NULL argument");
+    if (K < 1 || K > MRC_KMAX) return set_err(MRC_ERR_ARG, "K must be in [1,%d]", MRC_KMAX);
+    for (ll s = 0; s < S; s++)
+        if (edge[s] >= g->m) return set_err(MRC_ERR_ARG, "edge index out of range");
+    if (S == 0) return MRC_OK;
+    CUDA_TRY(cudaSetDevice(g->device));
+    // base potentials: the fixed point at lam_base on the unperturbed graph (if it does not exist the groups start cold)
+    ProbeOut base;
+    MRC_TRY(run_probe(g, false, 1, &lam_base, nullptr, nullptr, slack, 0, &base));
+    const bool warm = base.verdict == MRC_V_NONNEG;
+    if (warm) {
+        if (!g->d_base) DALLOC(g->d_base, (size_t)g->n * 8);
+        CUDA_TRY(cudaMemcpyAsync(g->d_base, g->d_dist, (size_t)g->n * 8, cudaMemcpyDeviceToDevice, g->stream));   // K = 1 layout: [n][1]
+    }
+    ProbeOut res[MRC_KMAX];
+    for (ll s0 = 0; s0 < S; s0 += K) {
+        const int kk = (int)std::min<ll>(K, S - s0);
+        for (int k = 0; k < kk; k++) {
+            g->scen_pe[k] = edge[s0 + k] < 0 ? -1 : (int)edge[s0 + k];
+            g->scen_dc[k] = dcost[s0 + k]; g->scen_dt[k] = dtime[s0 + k];
+        }
+        g->scen_on = true;
+        ProbeRun pr;
+        pr.warm_from = warm ? g->d_base : nullptr;
+        int rc = pr.begin(g, false, kk, lam + s0, nullptr, nullptr, slack, 0, res);
+        while (!rc && pr.active) {
+            rc = pr.enqueue_burst();
+            if (rc || pr.nb <= 0) break;
+            rc = pr.enqueue_readback();
+            if (!rc && cudaStreamSynchronize(g->stream) != cudaSuccess) rc = set_err(MRC_ERR_CUDA, "stream synchronize failed");
+            if (!rc) rc = pr.collect();
+        }
+        g->scen_on = false;
+        if (rc) return rc;
+        pr.finish();
+        for (int k = 0; k < kk; k++) { verdict[s0 + k] = res[k].verdict; if (passes) passes[s0 + k] = res[k].passes; }
+    }
+    return MRC_OK;
+}
+
 extern "C" int mrc_probe_exact(mrc_graph *g, const int64_t *a, const int64_t *b, int K, uint32_t flags,
                                int32_t *verdict, int32_t *cyc_len, int32_t *cyc_buf, int64_t cyc_cap,
                                int64_t *sum_cost, int64_t *sum_time, int64_t *passes) {
@@ -1065,6 +1134,8 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "compact_min_edges") g->compact_min_edges = std::max(0, value);
     else if (s == "lookahead") g->lookahead = value != 0;
     else if (s == "check_every") g->check_every = std::max(0, value);
+    else if (s == "cert_first") g->cert_first = value != 0;
+    else if (s == "tick_max") g->tick_max = std::max(1, std::min(value, MRC_MAX_BURST));
     else if (s == "gate") g->gate = value != 0;
     else if (s == "sparse") g->sparse = value != 0;
     else if (s == "sparse_div") g->sparse_div = std::max(1, value);
@@ -1130,7 +1201,7 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
         // which nothing is negative still runs to convergence and proves the lower end.
         MRC_TRY(run_probe(g, false, K, lam, nullptr, nullptr, slack,
                           MRC_F_MONOTONE_PRUNE | ((g->stop_on_neg && K >= g->stop_on_neg) ? MRC_F_STOP_ON_NEG : 0u) |
-                              (g->patience ? MRC_F_PATIENCE : 0u), res));
+                              (g->patience ? MRC_F_PATIENCE : 0u) | ((have_cycle && g->cert_first) ? MRC_F_CERT_FIRST : 0u), res));
         for (int k = 0; k < K; k++) {
             vd[k] = res[k].verdict;
             cr[k] = (vd[k] == MRC_V_NEG || vd[k] == MRC_V_TIE) ? res[k].sumc / res[k].sumt : NAN;

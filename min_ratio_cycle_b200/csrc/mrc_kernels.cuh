@@ -409,6 +409,14 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
     if (lane == 0 && chg) atomicOr(p.changed, chg << p.k0);
 }
 
+// dist[v][0..ks) = base[v] for every vertex: a probe that starts from the converged potentials of a neighbouring
+// problem instead of zero (scenario batches of sensitivity_analysis).  Any start <= 0 is legitimate: a pass that
+// lowers nothing leaves feasible potentials, which is the certificate "no negative cycle", whatever the start was.
+__global__ void broadcast_column_kernel(const ull *__restrict__ base, ull *__restrict__ dist, int ks, ll n) {
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n * ks; i += (ll)gridDim.x * blockDim.x)
+        dist[i] = __ldg(base + i / ks);
+}
+
 // Column copies between the [n][ks] candidate layout and a compact [n][1] one: once a round has narrowed to a single
 // live slot, its dist/pred column moves to compact buffers (16 MB at n = 1 M, ~5 us) so that the remaining sweeps
 // gather from 8 MB of contiguous doubles instead of every fourth double of 32 MB.

@@ -72,6 +72,9 @@ class SolverConfig:
     max_memory_mb: int | None = None
     # additive GPU knobs
     gpu_device: int = 0
+    gpu_devices: list | None = None    # several GPUs of one box (e.g. [0, 1, 2, 3]): the edge arrays are replicated over
+                                       # NVLink and the lambda candidates of the numeric search are sharded over the
+                                       # devices inside the library (mrc_comm_init / mrc_mgraph_*); None = gpu_device only
     gpu_candidates: int = 1            # lambdas evaluated per relaxation launch (1..8).  1 = Newton steps on the best cycle's
                                        # ratio + one certifying probe: on ONE GPU that is 1.5-2.8x faster than 4-way
                                        # multisection on most graphs (a negative probe costs 2-6 sweeps, a non-negative
@@ -185,6 +188,8 @@ class MinRatioCycleSolver:
         self._last_result: SolverResult | None = None
         self._metrics = SolverMetrics() if self.config.collect_metrics else None
         self._dev: N.DeviceGraph | None = None
+        self._mg = None                    # N.MultiGraph when config.gpu_devices names several GPUs
+        self._comm = None
         self._last_exact: dict | None = None
         self.logger.info("Initialized solver with %d vertices", n_vertices)
 
@@ -210,9 +215,20 @@ class MinRatioCycleSolver:
     def _num_edges(self) -> int:
         return len(self._edges) + sum(len(b[0]) for b in self._bulk)
 
+    def _close_multi(self) -> None:
+        if self._mg is not None:
+            self._mg.close()
+            self._mg = None
+            self._dev = None               # was a borrowed replica of the multi-graph
+        if self._comm is not None:
+            self._comm.close()
+            self._comm = None
+
     def __del__(self):
         try:
-            if self._dev is not None:
+            if self._mg is not None:
+                self._close_multi()
+            elif self._dev is not None:
                 self._dev.close()
         except Exception:
             pass
@@ -368,9 +384,22 @@ class MinRatioCycleSolver:
         self._is_sparse = len(self._U) / (self.n * self.n) < self.config.sparse_threshold
         if self._dev is not None:
             self._dev.close()
-        self._dev = N.DeviceGraph(self.n, self._U if u32 is None else u32, self._V if v32 is None else v32,
-                                  self._C, self._T, self._Ci, self._Ti, device=self.config.gpu_device)
-        self._dev.set_option("sparse", 1 if self.config.gpu_sparse else 0)
+        self._close_multi()
+        devs = [int(d) for d in (self.config.gpu_devices or [])]
+        if len(devs) > 1 and not self._all_int:
+            # numeric graph on several GPUs: replicas of the sorted arrays on every device (one H2D + NCCL broadcast);
+            # the replica on devs[0] doubles as the single-device handle for bounds, properties and probes
+            self._comm = N.Comm.group(devs)
+            self._mg = N.MultiGraph(self._comm, self.n, self._U if u32 is None else u32, self._V if v32 is None else v32,
+                                    self._C, self._T)
+            self._dev = self._mg.replica(0)
+            self._dev.device = devs[0]
+        else:
+            self._dev = N.DeviceGraph(self.n, self._U if u32 is None else u32, self._V if v32 is None else v32,
+                                      self._C, self._T, self._Ci, self._Ti,
+                                      device=devs[0] if devs else self.config.gpu_device)
+        for g in ([self._mg.replica(i) for i in range(len(devs))] if self._mg is not None else [self._dev]):
+            g.set_option("sparse", 1 if self.config.gpu_sparse else 0)
         self._arrays_built = True
         if self._metrics:
             self._metrics.preprocessing_time = _time.time() - t0
@@ -577,9 +606,13 @@ class MinRatioCycleSolver:
                     lambda_hi = warm_sums[0] / warm_sums[1]
                 else:
                     warm = None
-            out = dev.solve_numeric(lambda_lo, lambda_hi, max_iter, tol, slack, K=self.config.gpu_candidates,
-                                    max_seconds=-1.0 if limit is None else max(float(limit), 1e-300),
-                                    hi_is_cycle=bool(warm))
+            if self._mg is not None and not warm and not kwargs.get("_single_device"):
+                out = self._mg.solve_numeric(lambda_lo, lambda_hi, max_iter, tol, slack, K_local=self.config.gpu_candidates,
+                                             max_seconds=-1.0 if limit is None else max(float(limit), 1e-300))
+            else:
+                out = dev.solve_numeric(lambda_lo, lambda_hi, max_iter, tol, slack, K=self.config.gpu_candidates,
+                                        max_seconds=-1.0 if limit is None else max(float(limit), 1e-300),
+                                        hi_is_cycle=bool(warm))
             if warm and out["rc"] in (N.OK, N.ERR_CONVERGENCE) and not out["cycle"]:
                 out["cycle"] = list(warm)          # no better cycle exists: the warm-start cycle stands
             if out["rc"] == N.ERR_TIMEOUT:
@@ -741,7 +774,7 @@ class MinRatioCycleSolver:
             self._C[pos] += dc
             self._T[pos] += dt
             try:
-                res = self._solve_numeric(_warm_cycle=warm)
+                res = self._solve_numeric(_warm_cycle=warm, _single_device=True)   # only replica 0 carries the patch
                 if self.config.validate_cycles:
                     res = self._validate_result(res)
                 res.config_used = self.config

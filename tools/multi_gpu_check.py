@@ -27,15 +27,16 @@ def same(a, b):
 
 if len(sys.argv) > 1 and sys.argv[1] == "group":
     ndev = N.device_count()
-    for W in sorted({1, min(2, ndev), ndev}):
-        comm = N.Comm.group(list(range(W)))
-        for seed in seeds:
-            U, V, C, T = graph(seed)
-            g = N.DeviceGraph(n, U, V, C, T)
-            lo, hi = g.bounds()
-            ref = g.solve_numeric(lo, hi, K=K)
+    widths = [w for w in (1, 2, 4, 8) if w <= ndev]
+    comms = {W: N.Comm.group(list(range(W))) for W in widths}
+    for seed in seeds:
+        U, V, C, T = graph(seed)
+        g = N.DeviceGraph(n, U, V, C, T)
+        lo, hi = g.bounds()
+        ref = g.solve_numeric(lo, hi, K=K)
+        for W in widths:
             t0 = time.perf_counter()
-            mg = N.MultiGraph(comm, n, U, V, C, T)
+            mg = N.MultiGraph(comms[W], n, U, V, C, T)
             t_rep = time.perf_counter() - t0
             for kl in (K, 1):
                 out = mg.solve_numeric(lo, hi, K_local=kl)
@@ -44,10 +45,17 @@ if len(sys.argv) > 1 and sys.argv[1] == "group":
                     out = mg.solve_numeric(lo, hi, K_local=kl)
                 dt = (time.perf_counter() - t0) / reps
                 assert same(out, ref), (W, seed, kl, out["ratio"], ref["ratio"], out["cycle"][:8], ref["cycle"][:8], out["rc"])
+                if os.environ.get("TRACE_W") == str(W) and os.environ.get("TRACE_K") == str(kl):
+                    os.environ["MRC_B200_TRACE"] = "1"; mg.solve_numeric(lo, hi, K_local=kl); os.environ.pop("MRC_B200_TRACE")
+                visits = sum(mg.replica(i).stats()["relax_edge_visits"] for i in range(W))
+                for i in range(W):
+                    mg.replica(i).reset_stats()
                 print(f"group x{W} seed {seed} K_local {kl}: {dt*1e3:.2f} ms/solve ticks {out['ticks']} probes(rank0) {out['iterations']} "
-                      f"(replication {t_rep*1e3:.1f} ms); single GPU K={K}: rounds {ref['iterations']}", flush=True)
-            mg.close(); g.close()
-        comm.close()
+                      f"(replication {t_rep*1e3:.1f} ms)", flush=True)
+            mg.close()
+        g.close()
+    for c in comms.values():
+        c.close()
     print("multi_gpu_check group OK")
     sys.exit(0)
 
