@@ -396,6 +396,82 @@ def secondary_records(args, N, g, world, rank, local_rank, comm, out, search, ga
         rec["modes"] = dict(modes, note="solve_ms_default = SolverConfig defaults (gpu_candidates=1, gpu_sparse=True): Newton steps on the best "
                                         "cycle's ratio + one certifying probe, late passes as worklist passes; fewer relaxations are executed, so the "
                                         "throughput headline keeps dense sweeps")
+        # harder instances of the same size (seed 0's optimum is a 4-vertex cycle; seeds 1 and 3: 145 and 49 vertices, 80-90 sweeps
+        # for the certifying probe): time to solution, headline configuration and product default
+        hard = {}
+        from min_ratio_cycle_b200 import synthetic
+        for seed in (1, 3):
+            _, U2, V2, C2, T2 = synthetic.random_float(n, len(pU), seed=seed)
+            o2 = np.argsort(V2, kind="stable")
+            g2 = N.DeviceGraph(n, U2[o2].astype(np.int32), V2[o2].astype(np.int32), C2[o2], T2[o2], device=local_rank)
+            l2, h2 = g2.bounds()
+            row = {}
+            for name, K_, sp in ((f"k{args.klocal}_dense", args.klocal, 0), ("default_k1_sparse", 1, 1)):
+                g2.set_option("sparse", sp)
+                g2.solve_numeric(l2, h2, max_iter, tol, slack, K=K_)
+                g2.reset_stats()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    o = g2.solve_numeric(l2, h2, max_iter, tol, slack, K=K_)
+                torch.cuda.synchronize()
+                st = g2.stats()
+                row[name] = {"solve_ms": 1e3 * (time.perf_counter() - t0) / 3, "probes": o["iterations"],
+                             "relax_us_per_pass": 1e3 * st["relax_ms"] / max(st["relax_launches"], 1)}
+                row["ratio"], row["cycle_len"] = o["ratio"], len(o["cycle"]) - 1
+            hard[f"seed{seed}"] = row
+            g2.close()
+        rec["hard_instances"] = hard
+        # the public API end to end: insertion-order arrays -> add_edges_arrays -> solve() (preprocessing, device sort, upload,
+        # search, validation, metrics)
+        import min_ratio_cycle_b200.solver as S
+        from min_ratio_cycle_b200 import synthetic as syn
+        _, Ui, Vi, Ci, Ti = syn.random_float(n, len(pU), seed=SEED)
+        fac = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            sv = S.MinRatioCycleSolver(n, S.SolverConfig(log_level=S.LogLevel.NONE))
+            sv.add_edges_arrays(Ui, Vi, Ci, Ti)
+            r = sv.solve()
+            fac.append(time.perf_counter() - t0)
+            if abs(r.ratio - out["ratio"]) > 1e-9 * max(1.0, abs(out["ratio"])):
+                raise RuntimeError(f"facade changed the answer: {r.ratio!r} vs {out['ratio']!r}")
+            del sv
+        rec["e2e_facade"] = {"ms": 1e3 * min(fac), "ms_first": 1e3 * fac[0], "path": "MinRatioCycleSolver.add_edges_arrays + solve() from insertion-order NumPy arrays"}
+    # ---- BASELINE config 4: 4,096 currency graphs, sharded over the ranks by graph (independent units, no collective)
+    from min_ratio_cycle_b200 import batch, sharded, synthetic
+    B = 4096
+    mine = sharded.shard_units(B, rank, world)
+    graphs = [synthetic.currency_graph(64, 1000 + i) for i in mine]
+    nv, off, Sx, Dx, Cs, Ts = batch._prepare(graphs, True)
+    N.batch_solve_numeric(nv, off, Sx, Dx, Cs, Ts, K=1, device=local_rank)           # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    ob = N.batch_solve_numeric(nv, off, Sx, Dx, Cs, Ts, K=1, device=local_rank)
+    torch.cuda.synchronize()
+    v4 = gather([time.perf_counter() - t0, ob["stats"]["relax_ms"] * 1e-3, float(ob["stats"]["relax_edge_visits"]),
+                 float((ob["status"] == 0).sum())])
+    rec["c4_batch"] = {"graphs": B, "solved": int(v4[:, 3].sum()), "call_ms": 1e3 * float(v4[:, 0].max()),
+                       "kernel_ms": 1e3 * float(v4[:, 1].max()), "value": float(v4[:, 2].sum()) / float(v4[:, 1].max()) / 1e9,
+                       "unit": UNIT + " over kernel time", "path": "mrc_batch_solve_numeric (one CTA per graph), graphs split over the ranks"}
+    # ---- BASELINE config 5: 1,024 single-edge perturbation re-solves of n=100k m=2M, sharded over the ranks by scenario
+    import min_ratio_cycle_b200.solver as S
+    n5, U5, V5, C5, T5 = synthetic.random_float(100_000, 2_000_000, seed=5)
+    sv = S.MinRatioCycleSolver(n5, S.SolverConfig(log_level=S.LogLevel.NONE, enable_preprocessing=False, gpu_device=local_rank))
+    sv.add_edges_arrays(U5, V5, C5, T5)
+    base = sv.solve()
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, len(U5), 1024)
+    sign = rng.choice([-1.0, 1.0], 1024)
+    scen = [{int(i): (float(sg * 0.1 * C5[i]), 0.0)} for i, sg in zip(idx, sign)]
+    run5 = (lambda: sv.sensitivity_analysis(scen)) if world == 1 else (lambda: sharded.sensitivity_analysis_sharded(sv, scen))
+    run5()
+    barrier()
+    t0 = time.perf_counter()
+    res5 = run5()
+    torch.cuda.synchronize()
+    v5 = gather([time.perf_counter() - t0])
+    rec["c5_sensitivity"] = {"scenarios": len(scen), "ms": 1e3 * float(v5[:, 0].max()), "moved": int(sum(r.cycle != base.cycle for r in res5)),
+                             "path": "sensitivity_analysis: mrc_scenarios_certify (8 scenarios per edge sweep, warm-started), scenarios split over the ranks"}
     return rec
 
 

@@ -134,3 +134,19 @@ def shard_units(n_units: int, rank: int, world: int) -> range:
     base, extra = divmod(n_units, world)
     start = rank * base + min(rank, extra)
     return range(start, start + base + (1 if rank < extra else 0))
+
+
+def sensitivity_analysis_sharded(solver, edge_perturbations, group=None):
+    """
+    BASELINE config 5 over several GPUs, one process per GPU: every rank holds the same solver
+    (same graph, already solved once so that the warm-start cycle is the same everywhere), evaluates the contiguous
+    block shard_units(len(scenarios), rank, world) with MinRatioCycleSolver.sensitivity_analysis and one
+    all_gather_object returns the full result list on every rank.  No collective on the data path.
+    """
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = shard_units(len(edge_perturbations), rank, world)
+    local = solver.sensitivity_analysis([edge_perturbations[i] for i in mine]) if len(mine) else []
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local, group=group)
+    return [r for part in gathered for r in part]

@@ -80,7 +80,7 @@ class SolverConfig:
                                        # multisection on most graphs (a negative probe costs 2-6 sweeps, a non-negative
                                        # one next to lambda* 20-100, profiles/r01e_policy.txt section 11); K > 1 is the
                                        # throughput / multi-GPU configuration (bench.py, sharded.py)
-    gpu_scenarios_per_sweep: int = 4   # sensitivity_analysis: single-edge scenarios that share one edge sweep (1..8)
+    gpu_scenarios_per_sweep: int = 8   # sensitivity_analysis: single-edge scenarios that share one edge sweep (1..8)
     gpu_exact_strategy: int = 1        # 0: every Stern-Brocot step probes the GPU; 1: Newton + replay
     gpu_sparse: bool = True            # late passes walk only the out-edges of the vertices still being lowered
                                        # (worklist + out-edge index; same fixed point and verdicts, shorter solves)
@@ -706,6 +706,51 @@ class MinRatioCycleSolver:
             return result
 
     # ------------------------------------------------------------------ analytics (:1699-1759)
+    def _certify_single_edge_scenarios(self, warm, pos, dc, dt, tol, slack):
+        """
+        For S scenarios "sorted-array edge pos[s] perturbed by (dc[s], dt[s])": list of (sum_cost, sum_time) of the cycle
+        `warm` under the scenario's weights where that cycle is still optimal to within tol there, None elsewhere.
+        Everything per scenario is array arithmetic; the probes run inside the library, K scenarios per edge sweep,
+        warm-started from one base probe, sharded over the devices of config.gpu_devices (independent units: no
+        collective on the data path).
+        """
+        cyc = warm[:-1]
+        sc0, st0 = self._compute_cycle_weights_float(cyc)
+        S = len(pos)
+        sums = [(sc0, st0)] * S
+        lams = np.full(S, sc0 / st0 - 0.75 * tol)
+        # scenarios on a (u, v) pair the cycle uses: the hop rule (:1309-1313) may pick another parallel edge there
+        hop_keys = np.array([u * self.n + v for u, v in zip(cyc, cyc[1:] + cyc[:1])], dtype=np.int64)
+        touched = np.flatnonzero(np.isin(self._U[pos] * self.n + self._V[pos], hop_keys))
+        sums = list(sums)
+        for j in touched:
+            p1 = np.array([pos[j]])
+            saved = (self._C[p1].copy(), self._T[p1].copy())   # restore bit-exactly, not by subtracting
+            self._C[p1] += dc[j]; self._T[p1] += dt[j]
+            try:
+                sums[j] = self._compute_cycle_weights_float(cyc)
+            finally:
+                self._C[p1], self._T[p1] = saved
+            lams[j] = sums[j][0] / sums[j][1] - 0.75 * tol if sums[j][1] > 0 else np.inf
+        K = max(1, min(int(self.config.gpu_scenarios_per_sweep), N.KMAX))
+        lam_base = sc0 / st0 - 0.75 * tol
+        graphs = [self._dev] if self._mg is None else [self._mg.replica(i) for i in range(self._comm.nranks)]
+        verdict = np.full(S, -1, np.int32)
+        if len(graphs) == 1 or S < 4 * K * len(graphs):
+            verdict[:], _ = graphs[0].scenarios_certify(pos, dc, dt, lams, lam_base, slack, K)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            from .sharded import shard_units
+            parts = [shard_units(S, r, len(graphs)) for r in range(len(graphs))]
+
+            def run(r):
+                sl = slice(parts[r].start, parts[r].stop)
+                return graphs[r].scenarios_certify(pos[sl], dc[sl], dt[sl], lams[sl], lam_base, slack, K)[0]
+            with ThreadPoolExecutor(len(graphs)) as ex:      # ctypes releases the GIL: one host thread per device
+                for r, v in enumerate(ex.map(run, range(len(graphs)))):
+                    verdict[parts[r].start:parts[r].stop] = v
+        return [sums[j] if verdict[j] == N.V_NONNEG and sums[j][1] > 0 else None for j in range(S)]
+
     def sensitivity_analysis(self, edge_perturbations: list[dict[int, tuple[float, float]]]) -> list[SolverResult]:
         """
         One re-solve per scenario {edge index: (delta_cost, delta_time)} (:1699-1729).  Edge indices are
@@ -739,31 +784,19 @@ class MinRatioCycleSolver:
         results: list[SolverResult | None] = [None] * len(scen_arrays)
         tol, slack = self.config.numeric_tolerance, self.config.numeric_cycle_slack
 
-        def recost(pos, dc, dt, cyc):
-            keep = (self._C[pos].copy(), self._T[pos].copy())   # restore bit-exactly, not by subtracting
-            self._C[pos] += dc; self._T[pos] += dt
-            try:
-                return self._compute_cycle_weights_float(cyc)
-            finally:
-                self._C[pos], self._T[pos] = keep
-
-        # Fast path: K single-edge scenarios share every edge read (mrc_probe_numeric_scenarios).  Each one probes
-        # its own certifier, (ratio of the unperturbed optimum under that scenario's weights) - 0.75 tol; no
-        # negative cycle there means that cycle is still optimal to within tol -- the answer the sequential path
-        # below would give.  Scenarios whose optimum moves (or that touch several edges) fall through to it.
+        # Fast path, one library call for all single-edge scenarios (mrc_scenarios_certify): each one probes its own
+        # certifier, (ratio of the unperturbed optimum under that scenario's weights) - 0.75 tol; no negative cycle there
+        # means that cycle is still optimal to within tol -- the answer the sequential path below would give.  Scenarios
+        # whose optimum moves (or that touch several edges) fall through to it.
         if warm is not None:
-            K = max(1, min(int(self.config.gpu_scenarios_per_sweep), N.KMAX))
-            singles = [i for i, sa in enumerate(scen_arrays) if len(sa[0]) == 1]
-            for b0 in range(0, len(singles), K):
-                grp = singles[b0: b0 + K]
-                sums = [recost(*scen_arrays[i], warm[:-1]) for i in grp]
-                lams = [sc / st - 0.75 * tol for sc, st in sums]
-                out = self._dev.probe_numeric_scenarios(lams, [int(scen_arrays[i][0][0]) for i in grp],
-                                                        [float(scen_arrays[i][1][0]) for i in grp],
-                                                        [float(scen_arrays[i][2][0]) for i in grp], slack)
-                for i, (sc, st), o in zip(grp, sums, out):
-                    if o["verdict"] == N.V_NONNEG and st > 0:
-                        results[i] = SolverResult(cycle=list(warm), sum_cost=sc, sum_time=st, ratio=sc / st, success=True,
+            singles = np.array([i for i, sa in enumerate(scen_arrays) if len(sa[0]) == 1], dtype=np.int64)
+            if len(singles):
+                keep = self._certify_single_edge_scenarios(warm, np.array([scen_arrays[i][0][0] for i in singles]),
+                                                           np.array([scen_arrays[i][1][0] for i in singles]),
+                                                           np.array([scen_arrays[i][2][0] for i in singles]), tol, slack)
+                for i, k in zip(singles, keep):
+                    if k is not None:
+                        results[i] = SolverResult(cycle=list(warm), sum_cost=k[0], sum_time=k[1], ratio=k[0] / k[1], success=True,
                                                   metrics=SolverMetrics(iterations=1, mode_used="numeric"),
                                                   config_used=self.config)
         for i, (pos, dc, dt) in enumerate(scen_arrays):
@@ -787,15 +820,31 @@ class MinRatioCycleSolver:
         return results
 
     def stability_region(self, epsilon: float = 0.01) -> dict[int, bool]:
+        """{edge index: does the optimal cycle survive cost*(1+eps), time*(1+eps) on that edge} (:1731-1759).  The
+        reference re-solves once per edge; here all m single-edge scenarios go through ONE batched call
+        (mrc_scenarios_certify) and only the edges whose scenario moves the optimum are re-solved."""
         base = self._last_result if self._last_result is not None else self.solve()
+        self._preprocess_graph()
         self._build_arrays_if_needed()
         m = self._num_edges()
-        U, V, Cw, Tw = self._insertion_arrays()
-        # the reference re-solves once per edge (:1750-1757); the scenarios are independent, so they go to
-        # sensitivity_analysis in one call and share edge sweeps K at a time (mrc_probe_numeric_scenarios)
-        scenarios = [{idx: (float(Cw[idx]) * epsilon, float(Tw[idx]) * epsilon)} for idx in range(m)]
-        res = self.sensitivity_analysis(scenarios)
-        return {idx: res[idx].cycle == base.cycle for idx in range(m)}
+        ok, _ = self._verify_cycle_exists(base.cycle) if base.cycle else (False, [])
+        if not ok:
+            res = self.sensitivity_analysis([{idx: (float(self._C[p]) * epsilon, float(self._T[p]) * epsilon)}
+                                             for idx, p in enumerate(np.argsort(self._order))])
+            return {idx: res[idx].cycle == base.cycle for idx in range(m)}
+        inv = np.empty(m, dtype=np.int64)
+        inv[self._order] = np.arange(m)                      # insertion index -> sorted position
+        keep = self._certify_single_edge_scenarios(list(base.cycle), inv, self._C[inv] * epsilon, self._T[inv] * epsilon,
+                                                   self.config.numeric_tolerance, self.config.numeric_cycle_slack)
+        out = {}
+        moved = [idx for idx in range(m) if keep[idx] is None]
+        for idx in range(m):
+            out[idx] = keep[idx] is not None
+        if moved:
+            res = self.sensitivity_analysis([{idx: (float(self._C[inv[idx]]) * epsilon, float(self._T[inv[idx]]) * epsilon)} for idx in moved])
+            for idx, r in zip(moved, res):
+                out[idx] = r.cycle == base.cycle
+        return out
 
     # ------------------------------------------------------------------ misc (:1631-1693, :1814-1933)
     def get_debug_info(self) -> str:
