@@ -317,6 +317,27 @@ int mrc_sort_edges_by_dst(int64_t n, int64_t m, const int32_t *src, const int32_
                           const double *time, int device, int32_t *src_out, int32_t *dst_out, double *cost_out,
                           double *time_out, int32_t *order_out, int64_t *dup_pairs_out);
 
+/* _preprocess_graph + _build_arrays_if_needed + upload in ONE step (solver.py:450-575): host arrays in INSERTION order
+ * (vertex ids as int32 or int64: index_bytes 4 / 8) are uploaded by four host threads through pinned staging buffers;
+ * range checks, _remove_dominated_edges (:531-575; remove_dominated != 0), the stable sort by destination (:476-478) and
+ * the CSR offsets (:480-489) run on the device and the sorted arrays stay there -- no device -> host -> device round trip
+ * of the 24 B/edge.  *m_out = edges left after preprocessing, *dup_pairs = edges whose (u,v) also occurs earlier,
+ * *removed = dominated edges dropped.  Numeric graphs only (exact mode needs host mirrors: mrc_graph_create). */
+int mrc_graph_build(int64_t n, int64_t m, const void *src, const void *dst, int index_bytes, const double *cost,
+                    const double *time, int remove_dominated, int device, mrc_graph **out, int64_t *m_out,
+                    int64_t *dup_pairs, int64_t *removed);
+/* The destination-sorted arrays of a graph back on the host (any pointer may be NULL): the reference's _U/_V/_C/_T
+ * (solver.py:488-491).  order[i] = insertion index, among the edges that survived preprocessing, of sorted edge i and
+ * keep[j] (one byte per INPUT edge) = 1 where input edge j survived: graphs made by mrc_graph_build only. */
+int mrc_graph_fetch_arrays(mrc_graph *g, int32_t *src, int32_t *dst, double *cost, double *time, int32_t *order,
+                           uint8_t *keep);
+/* _compute_cycle_weights_float + _verify_cycle_exists (solver.py:1296-1327, :1563-1582) on the resident arrays: closed
+ * cycle of L hops (L + 1 vertex ids) in; per hop the first edge with minimal cost/time among the parallel (u,v) edges
+ * (:1309-1313); sums accumulated in cycle order from 0.0.  *missing_hop = first hop without an edge, or -1;
+ * hop_edges (L ints, may be NULL) = dst-sorted index of each hop's edge (-1 where missing). */
+int mrc_cycle_weights(mrc_graph *g, int64_t L, const int32_t *closed_cycle, double *sum_cost, double *sum_time,
+                      int32_t *missing_hop, int32_t *hop_edges);
+
 /* ---- batches of small graphs -------------------------------------------------------------------
  * Replaces a loop of B independent solve() calls (each _solve_numeric, solver.py:1001-1122) for graphs that
  * fit one SM's shared memory (n <= 65535, 20*m + 28*K*n bytes <= ~220 KB; BASELINE config 4: n=64, m=4032):

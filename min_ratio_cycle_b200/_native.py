@@ -37,6 +37,7 @@ EXPORTS = [
     "mrc_comm_unique_id", "mrc_comm_init_rank", "mrc_comm_init", "mrc_comm_destroy", "mrc_comm_info",
     "mrc_graph_create_replicated", "mrc_solve_numeric_sharded", "mrc_mgraph_create", "mrc_mgraph_destroy", "mrc_mgraph_graph",
     "mrc_mgraph_solve_numeric", "mrc_shard_fold", "mrc_scenarios_certify",
+    "mrc_graph_build", "mrc_graph_fetch_arrays", "mrc_cycle_weights",
 ]
 
 
@@ -121,6 +122,9 @@ def lib():
     L.mrc_mgraph_graph.argtypes = [vp, C.c_int]
     L.mrc_mgraph_solve_numeric.argtypes = [vp] + sharded_tail
     L.mrc_shard_fold.argtypes = [C.c_int, pd, pd, pd, pi, pi, pu8]
+    L.mrc_graph_build.argtypes = [C.c_int64, C.c_int64, vp, vp, C.c_int, pd, pd, C.c_int, C.c_int, C.POINTER(vp), p64, p64, p64]
+    L.mrc_graph_fetch_arrays.argtypes = [vp, p32, p32, pd, pd, p32, pu8]
+    L.mrc_cycle_weights.argtypes = [vp, C.c_int64, p32, pd, pd, p32, p32]
     L.mrc_scenarios_certify.argtypes = [vp, C.c_int64, p64, pd, pd, pd, C.c_double, C.c_double, C.c_int, p32, p64]
     for name in EXPORTS:
         if name == "mrc_mgraph_graph":
@@ -191,6 +195,49 @@ class DeviceGraph:
                                                 _ptr(arrs[1], C.c_int32), _ptr(arrs[2], C.c_double),
                                                 _ptr(arrs[3], C.c_double), C.byref(h)))
         return cls._wrap(h, n, m, comm.device)
+
+    @classmethod
+    def build(cls, n: int, U, V, Cw, Tw, remove_dominated: bool = True, device: int = 0):
+        """mrc_graph_build: insertion-order host arrays in; preprocessing, stable sort by destination and CSR on the
+        device.  Returns (graph, dup_pairs, removed); graph.m = edges left."""
+        U = np.ascontiguousarray(U)
+        V = np.ascontiguousarray(V)
+        if U.dtype != V.dtype or U.dtype not in (np.int32, np.int64):
+            U, V = U.astype(np.int64), V.astype(np.int64)
+        Cw = np.ascontiguousarray(Cw, dtype=np.float64)
+        Tw = np.ascontiguousarray(Tw, dtype=np.float64)
+        h = C.c_void_p()
+        mo, dups, rem = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().mrc_graph_build(int(n), len(U), U.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), U.dtype.itemsize,
+                                    _ptr(Cw, C.c_double), _ptr(Tw, C.c_double), int(bool(remove_dominated)), int(device),
+                                    C.byref(h), C.byref(mo), C.byref(dups), C.byref(rem)))
+        g = cls._wrap(h, n, mo.value, device)
+        g.m_input = len(U)
+        return g, dups.value, rem.value
+
+    def fetch_arrays(self, order: bool = False, keep: bool = False):
+        """(src int32, dst int32, cost, time[, order int32][, keep uint8]) of the destination-sorted arrays."""
+        src, dst = np.empty(self.m, np.int32), np.empty(self.m, np.int32)
+        cost, time = np.empty(self.m, np.float64), np.empty(self.m, np.float64)
+        o = np.empty(self.m, np.int32) if order else None
+        k = np.empty(getattr(self, "m_input", self.m), np.uint8) if keep else None
+        check(lib().mrc_graph_fetch_arrays(self._h, _ptr(src, C.c_int32), _ptr(dst, C.c_int32), _ptr(cost, C.c_double),
+                                           _ptr(time, C.c_double), _ptr(o, C.c_int32), _ptr(k, C.c_uint8)))
+        return tuple(x for x in (src, dst, cost, time, o, k) if x is not None)
+
+    def fetch_keep(self):
+        k = np.empty(getattr(self, "m_input", self.m), np.uint8)
+        check(lib().mrc_graph_fetch_arrays(self._h, None, None, None, None, None, _ptr(k, C.c_uint8)))
+        return k.astype(bool)
+
+    def cycle_weights(self, closed_cycle):
+        """mrc_cycle_weights: (sum_cost, sum_time, missing_hop or -1, hop edge indices)."""
+        cyc = np.ascontiguousarray(closed_cycle, dtype=np.int32)
+        L = max(len(cyc) - 1, 0)
+        sc, st, miss = C.c_double(), C.c_double(), C.c_int32(-1)
+        he = np.full(L, -1, np.int32)
+        check(lib().mrc_cycle_weights(self._h, L, _ptr(cyc, C.c_int32), C.byref(sc), C.byref(st), C.byref(miss), _ptr(he, C.c_int32)))
+        return sc.value, st.value, miss.value, he
 
     def close(self):
         if self._h is not None:

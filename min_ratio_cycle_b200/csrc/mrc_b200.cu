@@ -12,6 +12,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mrc_kernels.cuh"
@@ -100,6 +101,10 @@ struct mrc_graph {
     int lookahead = 1;           // option "lookahead": the next burst is enqueued before the previous burst's status is read
     void *d_cdist = nullptr; ull *d_cpred = nullptr; int *d_cjump = nullptr;   // compact column (compact survivor)
     void *d_base = nullptr;      // [n] potentials of the base probe of mrc_scenarios_certify
+    int *d_order = nullptr;      // mrc_graph_build: index among the preprocessed insertion-order edges of sorted edge i
+    int *d_starts = nullptr;     // [n+1] CSR by destination (built on first use by mrc_cycle_weights if the graph came sorted)
+    unsigned char *d_keep = nullptr;   // mrc_graph_build: 1 = input edge survived _remove_dominated_edges
+    ll m_input = 0;
     mrc_stats stats;
 };
 
@@ -174,7 +179,7 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
         void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
                         g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
                         g->d_keys, g->d_verr, g->d_out_off, g->d_out_edge,
-                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges, g->d_cdist, g->d_cpred, g->d_cjump, g->d_base};
+                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges, g->d_cdist, g->d_cpred, g->d_cjump, g->d_base, g->d_order, g->d_starts, g->d_keep};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
         cudaStreamSynchronize(g->stream);
     }
@@ -182,6 +187,23 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
+    return MRC_OK;
+}
+
+// launch geometry: persistent grids sized to whole waves of the 148 SMs
+static int graph_geometry(mrc_graph *g, const DeviceInfo *di) {
+    const ll n = g->n, m = g->m;
+    for (int KT : {1, 2, 4, 8})
+        for (int ex = 0; ex < 2; ex++) {
+            const int i = kt_index(KT);
+            if (di->occ_relax[i][ex] < 1 || di->occ_check[i] < 1) return set_err(MRC_ERR_CUDA, "kernel K=%d does not fit on an SM", KT);
+            const int rows = KT == 8 ? RelaxTune<8>::rows : RelaxTune<1>::rows;
+            const ll chunks = (m + 32 * rows - 1) / (32 * rows);   // one chunk per warp step
+            const ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
+            g->relax_blocks[i][ex] = (int)std::min<ll>(need, (ll)di->occ_relax[i][ex] * g->sms);
+            const ll needc = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
+            g->check_blocks[i] = (int)std::min<ll>(needc, (ll)di->occ_check[i] * g->sms);
+        }
     return MRC_OK;
 }
 
@@ -227,18 +249,7 @@ static int graph_new(int64_t n, int64_t m, int device, bool with_int, mrc_graph 
         CUDA_TRY(cudaMallocHost(&g->h_status, sizeof(DevStatus)));
         DALLOC(g->d_keys, 16);
         DALLOC(g->d_verr, 4);
-        // launch geometry: persistent grids sized to whole waves of the 148 SMs
-        for (int KT : {1, 2, 4, 8})
-            for (int ex = 0; ex < 2; ex++) {
-                const int i = kt_index(KT);
-                if (di->occ_relax[i][ex] < 1 || di->occ_check[i] < 1) return set_err(MRC_ERR_CUDA, "kernel K=%d does not fit on an SM", KT);
-                const int rows = KT == 8 ? RelaxTune<8>::rows : RelaxTune<1>::rows;
-                const ll chunks = (m + 32 * rows - 1) / (32 * rows);   // one chunk per warp step
-                const ll need = std::max<ll>(1, (chunks + MRC_RELAX_THREADS / 32 - 1) / (MRC_RELAX_THREADS / 32));
-                g->relax_blocks[i][ex] = (int)std::min<ll>(need, (ll)di->occ_relax[i][ex] * g->sms);
-                const ll needc = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
-                g->check_blocks[i] = (int)std::min<ll>(needc, (ll)di->occ_check[i] * g->sms);
-            }
+        MRC_TRY(graph_geometry(g, di));
         if (const char *env = getenv("MRC_B200_SPARSE")) g->sparse = atoi(env) != 0;   // default of option "sparse"
         if (const char *env = getenv("MRC_B200_SPARSE_DIV")) g->sparse_div = std::max(1, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_BPS")) g->sparse_bps = std::max(1, atoi(env));
@@ -312,6 +323,227 @@ extern "C" int mrc_graph_create(int64_t n, int64_t m, const int32_t *src, const 
     }();
     if (rc) { mrc_graph_destroy(g); return rc; }
     *out = g;
+    return MRC_OK;
+}
+
+// ---- host -> device upload of pageable arrays ---------------------------------------------------------------------
+// A plain cudaMemcpyAsync from pageable memory is staged by the driver through its own pinned buffer on ONE thread
+// (~10 GB/s here).  Four host threads each narrow / copy their quarter of the array into pinned chunks of their own and
+// queue the DMA of a chunk while filling the next: the copy runs at several memcpy streams' worth of bandwidth, and the
+// int64 -> int32 narrowing of vertex ids costs no pass of its own.
+struct UploadPool {
+    std::mutex mu;
+    static constexpr int T = 4, NBUF = 2;
+    static constexpr size_t CHUNK = 4u << 20;
+    void *buf[T][NBUF] = {};
+    bool ready = false;
+};
+static UploadPool g_upload;
+static int upload_array(int device, void *d_dst, const void *h_src, size_t count, int src_bytes, int dst_bytes) {
+    std::lock_guard<std::mutex> lock(g_upload.mu);
+    CUDA_TRY(cudaSetDevice(device));
+    if (!g_upload.ready) {
+        for (int t = 0; t < UploadPool::T; t++)
+            for (int b = 0; b < UploadPool::NBUF; b++) CUDA_TRY(cudaMallocHost(&g_upload.buf[t][b], UploadPool::CHUNK));
+        g_upload.ready = true;
+    }
+    const size_t per_chunk = UploadPool::CHUNK / (size_t)dst_bytes;
+    std::vector<int> rcs(UploadPool::T, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < UploadPool::T; t++)
+        th.emplace_back([&, t]() {
+            if (cudaSetDevice(device) != cudaSuccess) { rcs[t] = 1; return; }
+            cudaStream_t st;
+            cudaEvent_t ev[UploadPool::NBUF];
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { rcs[t] = 1; return; }
+            for (auto &e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            const size_t lo = count * t / UploadPool::T, hi = count * (t + 1) / UploadPool::T;
+            int b = 0;
+            bool used[UploadPool::NBUF] = {};
+            for (size_t i = lo; i < hi; i += per_chunk, b ^= 1) {
+                const size_t cnt = std::min(per_chunk, hi - i);
+                if (used[b]) cudaEventSynchronize(ev[b]);
+                if (src_bytes == dst_bytes) memcpy(g_upload.buf[t][b], (const char *)h_src + i * src_bytes, cnt * src_bytes);
+                else {   // int64 -> int32 (values were range-checked by the caller or are checked on the device)
+                    const int64_t *s = (const int64_t *)h_src + i;
+                    int32_t *d = (int32_t *)g_upload.buf[t][b];
+                    for (size_t j = 0; j < cnt; j++) d[j] = (int32_t)s[j];
+                }
+                if (cudaMemcpyAsync((char *)d_dst + i * dst_bytes, g_upload.buf[t][b], cnt * dst_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) rcs[t] = 1;
+                cudaEventRecord(ev[b], st);
+                used[b] = true;
+            }
+            if (cudaStreamSynchronize(st) != cudaSuccess) rcs[t] = 1;
+            for (auto &e : ev) cudaEventDestroy(e);
+            cudaStreamDestroy(st);
+        });
+    for (auto &x : th) x.join();
+    for (int r : rcs) if (r) return set_err(MRC_ERR_CUDA, "host-to-device upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return MRC_OK;
+}
+
+__global__ void range_check_kernel(const int *src, const int *dst, const double *time, ll n, ll m, int *err) {
+    int bad = 0;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (ll)gridDim.x * blockDim.x) {
+        if ((unsigned)src[e] >= (unsigned)n || (unsigned)dst[e] >= (unsigned)n) bad |= 1;
+        if (!(time[e] > 0.0)) bad |= 4;
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicOr(err, bad);
+}
+
+/*
+ * _preprocess_graph + _build_arrays_if_needed + upload in ONE step (solver.py:450-575): host arrays in INSERTION order
+ * (vertex ids int32 or int64), everything else on the device -- range checks, removal of dominated parallel edges,
+ * stable sort by destination, CSR offsets -- and the sorted arrays stay where the probes need them (no device -> host ->
+ * device round trip of 240 MB at m = 10^7).  The reference-order host mirrors (_U, _V, _C, _T, order) can be fetched
+ * later with mrc_graph_fetch_arrays.  Numeric graphs only.
+ */
+extern "C" int mrc_graph_build(int64_t n, int64_t m, const void *src, const void *dst, int index_bytes, const double *cost,
+                               const double *time, int remove_dominated, int device, mrc_graph **out, int64_t *m_out,
+                               int64_t *dup_pairs, int64_t *removed) {
+    if (!out) return set_err(MRC_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!src || !dst || !cost || !time) return set_err(MRC_ERR_ARG, "edge arrays are NULL");
+    if (index_bytes != 4 && index_bytes != 8) return set_err(MRC_ERR_ARG, "index_bytes must be 4 or 8");
+    mrc_graph *g = nullptr;
+    MRC_TRY(graph_new(n, m, device, false, &g));
+    int *d_s = nullptr, *d_d = nullptr;
+    double *d_c = nullptr, *d_t = nullptr;
+    int rc = [&]() -> int {
+        const size_t M = (size_t)m;
+        DALLOC(d_s, M * 4); DALLOC(d_d, M * 4); DALLOC(d_c, M * 8); DALLOC(d_t, M * 8);
+        DALLOC(g->d_order, M * 4); DALLOC(g->d_starts, ((size_t)n + 1) * 4); DALLOC(g->d_keep, M);
+        CUDA_TRY(cudaStreamSynchronize(g->stream));   // allocations are stream-ordered; the upload threads use their own streams
+        MRC_TRY(upload_array(device, d_s, src, M, index_bytes, 4));
+        MRC_TRY(upload_array(device, d_d, dst, M, index_bytes, 4));
+        MRC_TRY(upload_array(device, d_c, cost, M, 8, 8));
+        MRC_TRY(upload_array(device, d_t, time, M, 8, 8));
+        g->stats.h2d_bytes += (int64_t)m * 24;
+        CUDA_TRY(cudaMemsetAsync(g->d_verr, 0, 4, g->stream));
+        range_check_kernel<<<(int)std::min<ll>((m + 255) / 256, (ll)g->sms * 8), 256, 0, g->stream>>>(d_s, d_d, d_t, n, m, g->d_verr);
+        CUDA_TRY(cudaGetLastError());
+        int verr = 0;
+        CUDA_TRY(cudaMemcpyAsync(&verr, g->d_verr, 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        if (verr & 1) return set_err(MRC_ERR_ARG, "an edge has an endpoint outside [0,n)");
+        if (verr & 4) return set_err(MRC_ERR_ARG, "edge time must be strictly positive");
+        int64_t mk = m, dups = 0, rem = 0;
+        MRC_TRY(mrc_build_sorted_device(g->stream, n, m, d_s, d_d, d_c, d_t, remove_dominated, g->d_src, g->d_dst, g->d_cost,
+                                        g->d_time, g->d_order, g->d_starts, g->d_keep, &mk, &dups, &rem));
+        g->m_input = m;
+        g->m = mk;
+        const DeviceInfo *di = nullptr;
+        MRC_TRY(device_info(device, &di));
+        MRC_TRY(graph_geometry(g, di));
+        g->stats.other_launches += 12;
+        if (m_out) *m_out = mk;
+        if (dup_pairs) *dup_pairs = dups;
+        if (removed) *removed = rem;
+        return MRC_OK;
+    }();
+    for (void *q : {(void *)d_s, (void *)d_d, (void *)d_c, (void *)d_t}) if (q) cudaFreeAsync(q, g->stream);
+    if (rc) { mrc_graph_destroy(g); return rc; }
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    *out = g;
+    return MRC_OK;
+}
+
+/* Destination-sorted arrays of a graph back on the host (any pointer may be NULL): the reference's _U/_V/_C/_T
+ * (solver.py:488-491) for callers that read them; order[i] (mrc_graph_build only) = insertion index, among the edges that
+ * survived preprocessing, of sorted edge i; keep[j] (mrc_graph_build only, length = number of INPUT edges) = 1 where
+ * input edge j survived _remove_dominated_edges. */
+extern "C" int mrc_graph_fetch_arrays(mrc_graph *g, int32_t *src, int32_t *dst, double *cost, double *time, int32_t *order,
+                                      uint8_t *keep) {
+    if (!g) return set_err(MRC_ERR_ARG, "graph is NULL");
+    if ((order && !g->d_order) || (keep && !g->d_keep)) return set_err(MRC_ERR_ARG, "order / keep exist only for graphs made by mrc_graph_build");
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t M = (size_t)g->m;
+    if (src) CUDA_TRY(cudaMemcpyAsync(src, g->d_src, M * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (dst) CUDA_TRY(cudaMemcpyAsync(dst, g->d_dst, M * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (cost) CUDA_TRY(cudaMemcpyAsync(cost, g->d_cost, M * 8, cudaMemcpyDeviceToHost, g->stream));
+    if (time) CUDA_TRY(cudaMemcpyAsync(time, g->d_time, M * 8, cudaMemcpyDeviceToHost, g->stream));
+    if (order) CUDA_TRY(cudaMemcpyAsync(order, g->d_order, M * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (keep) CUDA_TRY(cudaMemcpyAsync(keep, g->d_keep, (size_t)g->m_input, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    g->stats.d2h_bytes += (int64_t)M * ((src ? 4 : 0) + (dst ? 4 : 0) + (cost ? 8 : 0) + (time ? 8 : 0) + (order ? 4 : 0));
+    return MRC_OK;
+}
+
+// per hop u -> v of a cycle: among the edges u -> v (segment of v in the destination-sorted arrays) the first one with
+// the smallest cost/time (solver.py:1309-1313); edge index or -1.  One warp per hop.
+__global__ void hop_edges_kernel(const int *cyc, ll L, const int *starts, const int *src, const double *cost, const double *time,
+                                 int *hop_edge, double *hop_c, double *hop_t) {
+    const int lane = threadIdx.x & 31;
+    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll i = warp; i < L; i += nw) {
+        const int u = cyc[i], v = cyc[i + 1];
+        const int lo = starts[v], hi = starts[v + 1];
+        double best = __longlong_as_double(0x7ff0000000000000ll);
+        int be = 0x7fffffff;
+        for (int e = lo + lane; e < hi; e += 32)
+            if (src[e] == u) {
+                const double r = __ddiv_rn(cost[e], time[e]);
+                if (r < best || (r == best && e < be)) { best = r; be = e; }
+            }
+        for (int o = 16; o; o >>= 1) {
+            const double rb = __shfl_xor_sync(0xffffffffu, best, o);
+            const int eb = __shfl_xor_sync(0xffffffffu, be, o);
+            if (eb != 0x7fffffff && (be == 0x7fffffff || rb < best || (rb == best && eb < be))) { best = rb; be = eb; }
+        }
+        if (lane == 0) {
+            hop_edge[i] = be == 0x7fffffff ? -1 : be;
+            hop_c[i] = be == 0x7fffffff ? 0.0 : cost[be];
+            hop_t[i] = be == 0x7fffffff ? 0.0 : time[be];
+        }
+    }
+}
+
+/* _compute_cycle_weights_float + _verify_cycle_exists (solver.py:1296-1327, :1563-1582) on the resident arrays:
+ * closed cycle of L hops (L + 1 vertices) in, per hop the edge the reference's rule picks; sums accumulated in cycle
+ * order from 0.0 like the reference.  *missing_hop = index of the first hop without an edge, or -1. */
+extern "C" int mrc_cycle_weights(mrc_graph *g, int64_t L, const int32_t *closed_cycle, double *sum_cost, double *sum_time,
+                                 int32_t *missing_hop, int32_t *hop_edges) {
+    if (!g || L < 0 || (L && !closed_cycle)) return set_err(MRC_ERR_ARG, "bad cycle arguments");
+    if (missing_hop) *missing_hop = -1;
+    if (sum_cost) *sum_cost = 0.0;
+    if (sum_time) *sum_time = 0.0;
+    if (L == 0) return MRC_OK;
+    for (ll i = 0; i <= L; i++)
+        if (closed_cycle[i] < 0 || closed_cycle[i] >= g->n) return set_err(MRC_ERR_ARG, "cycle vertex out of range");
+    CUDA_TRY(cudaSetDevice(g->device));
+    if (!g->d_starts) {
+        DALLOC(g->d_starts, ((size_t)g->n + 1) * 4);
+        in_offsets_kernel<<<(int)std::min<ll>((g->n + 256) / 256, (ll)g->sms * 8), 256, 0, g->stream>>>(g->d_dst, g->m, g->n, g->d_starts);
+        CUDA_TRY(cudaGetLastError());
+    }
+    int *d_cyc = nullptr, *d_he = nullptr;
+    double *d_hc = nullptr, *d_ht = nullptr;
+    std::vector<int> he((size_t)L);
+    std::vector<double> hc((size_t)L), ht((size_t)L);
+    int rc = [&]() -> int {
+        DALLOC(d_cyc, ((size_t)L + 1) * 4); DALLOC(d_he, (size_t)L * 4); DALLOC(d_hc, (size_t)L * 8); DALLOC(d_ht, (size_t)L * 8);
+        CUDA_TRY(cudaMemcpyAsync(d_cyc, closed_cycle, ((size_t)L + 1) * 4, cudaMemcpyHostToDevice, g->stream));
+        hop_edges_kernel<<<(int)std::min<ll>((L * 32 + 255) / 256, 1024), 256, 0, g->stream>>>(d_cyc, L, g->d_starts, g->d_src, g->d_cost,
+                                                                                            g->d_time, d_he, d_hc, d_ht);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(he.data(), d_he, (size_t)L * 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(hc.data(), d_hc, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(ht.data(), d_ht, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        return MRC_OK;
+    }();
+    for (void *q : {(void *)d_cyc, (void *)d_he, (void *)d_hc, (void *)d_ht}) if (q) cudaFreeAsync(q, g->stream);
+    if (rc) return rc;
+    g->stats.other_launches++;
+    double sc = 0.0, st = 0.0;
+    for (ll i = 0; i < L; i++) {
+        if (he[i] < 0) { if (missing_hop && *missing_hop < 0) *missing_hop = (int32_t)i; continue; }
+        sc += hc[i]; st += ht[i];
+        }
+    if (hop_edges) for (ll i = 0; i < L; i++) hop_edges[i] = he[i];
+    if (sum_cost) *sum_cost = sc;
+    if (sum_time) *sum_time = st;
     return MRC_OK;
 }
 

@@ -110,3 +110,80 @@ int mrc_build_out_csr(cudaStream_t st, int64_t n, int64_t m, const int32_t *d_sr
     *d_off_out = d_off; *d_edge_out = d_edge;
     return MRC_OK;
 }
+
+/*
+ * The whole of _preprocess_graph + _build_arrays_if_needed (solver.py:450-575) on device-resident insertion-order arrays:
+ * dominated parallel edges removed (optional), survivors stable-sorted by destination, CSR offsets.  Outputs go to
+ * caller-owned device buffers of m elements (o_starts: n + 1).  o_keep (may be NULL): one byte per INPUT edge, 1 = kept.
+ * o_order[i] = index among the SURVIVORS (insertion order) of sorted edge i.  *m_out = number of survivors.
+ */
+int mrc_build_sorted_device(cudaStream_t st, int64_t n, int64_t m, const int32_t *d_src, const int32_t *d_dst, const double *d_c,
+                            const double *d_t, int remove_dominated, int32_t *o_src, int32_t *o_dst, double *o_c, double *o_t,
+                            int32_t *o_order, int32_t *o_starts, unsigned char *o_keep, int64_t *m_out, int64_t *dups_out,
+                            int64_t *removed_out) {
+    const size_t M = (size_t)m;
+    int *d_idx = nullptr, *d_idx2 = nullptr, *d_kept = nullptr, *d_key32 = nullptr, *d_wide = nullptr, *d_rank = nullptr, *d_nsel = nullptr;
+    ull *d_k = nullptr, *d_k2 = nullptr, *d_cnt = nullptr;
+    unsigned char *d_keep = nullptr;
+    void *d_tmp = nullptr;
+    int rc = [&]() -> int {
+        const int blocks = (int)std::min<ll>((m + 255) / 256, 148 * 16);
+        int bits = 1;
+        while (((ll)1 << bits) < n) bits++;
+        CUDA_TRY(cudaMallocAsync((void **)&d_idx, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_idx2, M * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_kept, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_key32, M * 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_k, M * 8, st)); CUDA_TRY(cudaMallocAsync((void **)&d_k2, M * 8, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_cnt, 16, st)); CUDA_TRY(cudaMallocAsync((void **)&d_nsel, 4, st));
+        CUDA_TRY(cudaMallocAsync((void **)&d_keep, M, st));
+        size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, d_k, d_k2, d_idx, d_idx2, (int)m, 0, 32 + bits, st));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t2, d_key32, o_dst, d_kept, o_order, (int)m, 0, bits, st));
+        CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, t3, d_idx, d_keep, d_kept, d_nsel, (int)m, st));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, t4, d_idx, d_idx2, (int)m, st));
+        const size_t tmp_bytes = std::max(std::max(t1, t2), std::max(t3, t4));
+        CUDA_TRY(cudaMallocAsync(&d_tmp, tmp_bytes, st));
+        build_iota_kernel<<<blocks, 256, 0, st>>>(d_idx, m);
+        // ---- repeated (u,v) pairs and, among them, dominated edges
+        ull counts[2] = {0, 0};
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 16, st));
+        build_pair_keys_kernel<<<blocks, 256, 0, st>>>(d_src, d_dst, d_k, m);
+        size_t tb = tmp_bytes;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_k, d_k2, d_idx, d_idx2, (int)m, 0, 32 + bits, st));
+        build_dominated_kernel<<<blocks, 256, 0, st>>>(d_k2, d_idx2, d_c, d_t, m, d_keep, d_cnt);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(counts, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const ll removed = remove_dominated ? (ll)counts[1] : 0;
+        ll mk = m;
+        const int *kept = d_idx;                    // identity: nothing removed
+        if (removed > 0) {
+            tb = tmp_bytes;
+            CUDA_TRY(cub::DeviceSelect::Flagged(d_tmp, tb, d_idx, d_keep, d_kept, d_nsel, (int)m, st));   // stable: insertion order kept
+            kept = d_kept;
+            mk = m - removed;
+            // rank among the survivors of every input edge
+            CUDA_TRY(cudaMallocAsync((void **)&d_wide, M * 4, st)); CUDA_TRY(cudaMallocAsync((void **)&d_rank, M * 4, st));
+            build_widen_flags_kernel<<<blocks, 256, 0, st>>>(d_keep, d_wide, m);
+            tb = tmp_bytes;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_wide, d_rank, (int)m, st));
+        } else if (!remove_dominated) {
+            CUDA_TRY(cudaMemsetAsync(d_keep, 1, M, st));
+        }
+        // ---- stable sort of the survivors by destination + gathers
+        build_gather_dst_kernel<<<blocks, 256, 0, st>>>(kept, d_dst, d_key32, mk);
+        tb = tmp_bytes;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_key32, o_dst, kept, o_order, (int)mk, 0, bits, st));
+        build_gather_kernel<<<blocks, 256, 0, st>>>(o_order, d_src, d_c, d_t, o_src, o_c, o_t, mk);
+        if (removed > 0) build_renumber_kernel<<<blocks, 256, 0, st>>>(o_order, d_rank, mk);
+        build_in_offsets_kernel<<<(int)std::min<ll>((n + 256) / 256, 148 * 16), 256, 0, st>>>(o_dst, mk, n, o_starts);
+        CUDA_TRY(cudaGetLastError());
+        if (o_keep) CUDA_TRY(cudaMemcpyAsync(o_keep, d_keep, M, cudaMemcpyDeviceToDevice, st));
+        *m_out = mk;
+        if (dups_out) *dups_out = (int64_t)counts[0];
+        if (removed_out) *removed_out = removed;
+        return MRC_OK;
+    }();
+    void *ptrs[] = {d_idx, d_idx2, d_kept, d_key32, d_wide, d_rank, d_nsel, d_k, d_k2, d_cnt, d_keep, d_tmp};
+    for (void *q : ptrs) if (q) cudaFreeAsync(q, st);
+    return rc;
+}

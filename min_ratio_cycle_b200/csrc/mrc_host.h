@@ -36,3 +36,8 @@ static inline int set_err(int code, const char *fmt, ...) {
 
 // mrc_build.cu: out-edge (by source) index of a device-resident destination-sorted graph
 int mrc_build_out_csr(cudaStream_t st, int64_t n, int64_t m, const int32_t *d_src, int32_t **d_off_out, int32_t **d_edge_out);
+// mrc_build.cu: _preprocess_graph + _build_arrays_if_needed on device-resident insertion-order arrays
+int mrc_build_sorted_device(cudaStream_t st, int64_t n, int64_t m, const int32_t *d_src, const int32_t *d_dst, const double *d_c,
+                            const double *d_t, int remove_dominated, int32_t *o_src, int32_t *o_dst, double *o_c, double *o_t,
+                            int32_t *o_order, int32_t *o_starts, unsigned char *o_keep, int64_t *m_out, int64_t *dups_out,
+                            int64_t *removed_out);

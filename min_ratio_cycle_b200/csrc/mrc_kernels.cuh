@@ -930,3 +930,15 @@ __global__ void unpatch_edges_kernel(double *cost, double *time, const ll *idx, 
     const ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < k) { cost[idx[i]] = old_c[i]; time[idx[i]] = old_t[i]; }
 }
+
+// starts[v] = first position of the destination-sorted arrays whose destination is >= v, v in [0, n] (CSR by destination)
+__global__ void in_offsets_kernel(const int *sorted_dst, ll m, ll n, int *starts) {
+    for (ll v = (ll)blockIdx.x * blockDim.x + threadIdx.x; v <= n; v += (ll)gridDim.x * blockDim.x) {
+        ll lo = 0, hi = m;
+        while (lo < hi) {
+            const ll mid = (lo + hi) >> 1;
+            if (sorted_dst[mid] < (int)v) lo = mid + 1; else hi = mid;
+        }
+        starts[v] = (int)lo;
+    }
+}

@@ -166,8 +166,26 @@ def _is_integral(x) -> bool:
     return isinstance(x, (int, Fraction)) or (isinstance(x, float) and x.is_integer())
 
 
+def _mirror(name):
+    """Host mirror of a device-resident array (the reference's private `_U`, `_V`, ... that tools read): after the
+    device-side build (mrc_graph_build) it is fetched from the device on first read instead of on every build."""
+    slot = "_m" + name
+
+    def get(self):
+        if getattr(self, slot, None) is None and getattr(self, "_mirrors_pending", False):
+            self._materialize_mirrors()
+        return getattr(self, slot, None)
+
+    def put(self, value):
+        setattr(self, slot, value)
+    return property(get, put)
+
+
 class MinRatioCycleSolver:
     """Minimum cost-to-time ratio cycle; lambda search and Bellman-Ford run on the GPU."""
+
+    _U, _V, _C, _T = _mirror("_U"), _mirror("_V"), _mirror("_C"), _mirror("_T")
+    _starts, _counts, _order = _mirror("_starts"), _mirror("_counts"), _mirror("_order")
 
     def __init__(self, n_vertices: int, config: SolverConfig | None = None):
         if not isinstance(n_vertices, int) or n_vertices <= 0:
@@ -181,6 +199,7 @@ class MinRatioCycleSolver:
         self._hop_cache: dict = {}
         self._setup_logging()
         self._arrays_built = False
+        self._mirrors_pending = False
         self._U = self._V = self._C = self._T = self._Ci = self._Ti = None
         self._starts = self._counts = self._order = None
         self._all_int = True
@@ -211,6 +230,59 @@ class MinRatioCycleSolver:
         self._arrays_built = False
         self._presorted = None
         self._no_repeated_pairs = False
+        self._mirrors_pending = False
+
+    def _materialize_mirrors(self) -> None:
+        """_U/_V/_C/_T (int64 / f64, destination-sorted), _order, _starts, _counts from the device-resident arrays."""
+        self._mirrors_pending = False
+        so, do, co, to, order = self._dev.fetch_arrays(order=True)
+        self._U, self._V, self._C, self._T = so.astype(np.int64), do.astype(np.int64), co, to
+        self._order = order.astype(np.int64)
+        self._counts = np.bincount(self._V, minlength=self.n)
+        self._starts = np.zeros(self.n, dtype=np.int64)
+        if self.n > 1:
+            np.cumsum(self._counts[:-1], out=self._starts[1:])
+        self._hop_cache = {}
+
+    def _device_build(self, remove_dominated: bool) -> bool:
+        """
+        Large numeric graph given as ONE bulk block: _preprocess_graph + _build_arrays_if_needed + upload as one library
+        call (mrc_graph_build) -- dominated-edge removal, stable sort by destination and CSR on the device, the sorted
+        arrays stay there; the host mirrors are fetched only if somebody reads them.  Returns False when not applicable.
+        """
+        if (self._arrays_built or self._edges or len(self._bulk) != 1 or self._all_int
+                or len(self._bulk[0][0]) < _DEVICE_BUILD_MIN_EDGES or len(self.config.gpu_devices or []) > 1):
+            return False
+        t0 = _time.time()
+        U, V, Cw, Tw = self._bulk[0]
+        if self._dev is not None:
+            self._dev.close()
+        self._close_multi()
+        try:
+            self._dev, dups, removed = N.DeviceGraph.build(self.n, U, V, Cw, Tw, remove_dominated=remove_dominated,
+                                                           device=self.config.gpu_device)
+        except N.NativeError as exc:
+            if exc.code == N.ERR_ARG and "endpoint" in exc.message:
+                raise ValueError("u and v must be valid vertex indices") from exc
+            if exc.code == N.ERR_ARG and "time" in exc.message:
+                raise ValueError("Edge transit time must be strictly positive") from exc
+            raise
+        if removed:
+            keep = self._dev.fetch_keep()                      # the reference drops the edges from its list for good
+            self._bulk = [tuple(a[keep] for a in self._bulk[0])]
+            self.logger.info("Preprocessing removed %d dominated edges", removed)
+        self._no_repeated_pairs = dups == 0 or remove_dominated
+        for name in ("_U", "_V", "_C", "_T", "_starts", "_counts", "_order"):
+            setattr(self, name, None)
+        self._Ci = self._Ti = None
+        self._hop_cache = {}
+        self._mirrors_pending = True
+        self._is_sparse = self._dev.m / (self.n * self.n) < self.config.sparse_threshold
+        self._dev.set_option("sparse", 1 if self.config.gpu_sparse else 0)
+        self._arrays_built = True
+        if self._metrics:
+            self._metrics.preprocessing_time = _time.time() - t0
+        return True
 
     def _num_edges(self) -> int:
         return len(self._edges) + sum(len(b[0]) for b in self._bulk)
@@ -261,19 +333,39 @@ class MinRatioCycleSolver:
             raise ValueError("edge arrays must have equal length")
         if len(U) == 0:
             return
-        if U.min() < 0 or V.min() < 0 or U.max() >= self.n or V.max() >= self.n:
-            raise ValueError("u and v must be valid vertex indices")
-        if not np.all(Tw > 0):
-            raise ValueError("Edge transit time must be strictly positive")
-        if self._all_int and not (np.all(Cw == np.trunc(Cw)) and np.all(Tw == np.trunc(Tw))):
-            self._all_int = False
+        large = len(U) >= _DEVICE_BUILD_MIN_EDGES
+        if self._all_int:
+            head = slice(0, 4096)          # a float graph shows in the first few values: no full pass needed
+            if not (np.all(Cw[head] == np.trunc(Cw[head])) and np.all(Tw[head] == np.trunc(Tw[head]))):
+                self._all_int = False
+            elif not (np.all(Cw == np.trunc(Cw)) and np.all(Tw == np.trunc(Tw))):
+                self._all_int = False
+        if not large or self._all_int:
+            if U.min() < 0 or V.min() < 0 or U.max() >= self.n or V.max() >= self.n:
+                raise ValueError("u and v must be valid vertex indices")
+            if not np.all(Tw > 0):
+                raise ValueError("Edge transit time must be strictly positive")
+            U, V, Cw, Tw = U.copy(), V.copy(), Cw.copy(), Tw.copy()   # later changes to the caller's arrays must not reach the graph
+        # else: a large numeric block is range-checked on the device when the arrays are built (same ValueErrors, raised
+        # by solve()); it is borrowed, not copied -- 320 MB at 10^7 edges -- so the caller must not modify it until then
         self._bulk.append((U, V, Cw, Tw))
         self._invalidate()
 
     def remove_edge(self, u: int, v: int) -> bool:
+        """First edge u -> v in insertion order (:312-325), whether it came through add_edge or add_edges_arrays."""
         for i, e in enumerate(self._edges):
             if e.u == u and e.v == v:
                 del self._edges[i]
+                self._invalidate()
+                return True
+        for bi, (U, V, Cw, Tw) in enumerate(self._bulk):
+            hit = np.flatnonzero((U == u) & (V == v))
+            if hit.size:
+                k = np.ones(len(U), dtype=bool)
+                k[hit[0]] = False
+                self._bulk[bi] = (U[k], V[k], Cw[k], Tw[k])
+                if len(self._bulk[bi][0]) == 0:
+                    del self._bulk[bi]
                 self._invalidate()
                 return True
         return False
@@ -288,7 +380,7 @@ class MinRatioCycleSolver:
         if self._num_edges() == 0:
             return {"error": "No edges in graph"}
         self._build_arrays_if_needed()
-        n, m = self.n, len(self._U)
+        n, m = self.n, self._dev.m
         density = m / (n * n)
         # the degree / weight statistics come from the device-resident arrays (mrc_graph_properties): solve() stores
         # this dictionary in result.metrics on every call and the eight NumPy sweeps cost 160 ms at m = 10^7
@@ -352,6 +444,8 @@ class MinRatioCycleSolver:
         if self._num_edges() == 0:
             self.logger.warning("No edges to build arrays from")
             return
+        if self._presorted is None and self._device_build(remove_dominated=False):
+            return
         if self._presorted is not None:
             so, do, co, to, order = self._presorted            # device sort already done by _preprocess_graph
             self._presorted = None
@@ -414,6 +508,8 @@ class MinRatioCycleSolver:
         if not self.config.enable_preprocessing:
             return
         if self._no_repeated_pairs:          # census already done for this edge set: nothing can be dominated
+            return
+        if self._device_build(remove_dominated=True):
             return
         before = self._num_edges()
         if before >= _DEVICE_BUILD_MIN_EDGES and not self._arrays_built:
@@ -662,6 +758,11 @@ class MinRatioCycleSolver:
         SURVEY 0.8 -- deliberately not reproduced).
         """
         self._build_arrays_if_needed()
+        if self._mirrors_pending:          # mrc_cycle_weights: same hop rule and summation order on the resident arrays
+            sc, st, missing, _ = self._dev.cycle_weights(list(cycle) + [cycle[0]])
+            if missing >= 0:
+                raise RuntimeError(f"Edge {cycle[missing]} -> {cycle[(missing + 1) % len(cycle)]} not found in cycle")
+            return sc, st
         sc = st = 0.0
         L = len(cycle)
         for i in range(L):
@@ -676,6 +777,10 @@ class MinRatioCycleSolver:
 
     # ------------------------------------------------------------------ validation (:1495-1582)
     def _verify_cycle_exists(self, cycle):
+        if self._mirrors_pending:
+            he = self._dev.cycle_weights(cycle)[3]
+            issues = [f"Missing edge {u} -> {v}" for (u, v), e in zip(zip(cycle[:-1], cycle[1:]), he) if e < 0]
+            return not issues, issues
         issues = [f"Missing edge {u} -> {v}" for u, v in zip(cycle[:-1], cycle[1:]) if self._hop_edges(u, v).size == 0]
         return not issues, issues
 
