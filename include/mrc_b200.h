@@ -87,6 +87,8 @@ typedef struct mrc_stats {
     int64_t relax_edge_slots;     /* sum over launches of m * (active candidates), whether or not an edge was skipped */
     int64_t sparse_passes;        /* worklist passes (relax_sparse_kernel: only out-edges of the vertices the previous pass lowered) */
     double sparse_ms;             /* CUDA-event time spent in them (not part of relax_ms) */
+    double gated_ms;              /* CUDA-event time of the launches of a burst that returned at once because their candidates had
+                                     converged (not part of relax_ms; relax_ms counts the launches that swept the edges) */
 } mrc_stats;
 
 int mrc_abi_version(void);

@@ -46,6 +46,7 @@ struct mrc_graph {
     int device = 0, sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evb[MRC_MAX_BURST + 1] = {};   // one per dense launch of a burst: launches gated out are not relaxation time
     ll n = 0, m = 0;
     int *d_src = nullptr, *d_dst = nullptr;
     double *d_cost = nullptr, *d_time = nullptr;
@@ -95,6 +96,8 @@ struct mrc_graph {
     int narrow = 1;              // option "narrow": late passes run the narrowest kernel covering the undecided candidates
     int compact = 1;             // option "compact": a probe narrowed to ONE live slot continues on a compact [n][1] copy of its column
     ll compact_min_edges = 2000000;   // ... on graphs where a sweep is bandwidth-bound (smaller ones are launch-bound)
+    int check_skip = 0;          // option "check_skip": a cycle check leaves out candidates whose lowering count is still collapsing
+                                 // (measured: -7..-13 % on instances with long certifying probes, +10 % and one more round on C3 seed 0: off)
     int cert_first = 1;          // option "cert_first": mrc_solve_numeric passes MRC_F_CERT_FIRST to the probes of rounds that hold a cycle
     int tick_max = 8;            // option "tick_max": longest tick (passes between two exchanges) of the sharded search
     int check_every = 0;         // option "check_every" (experiments): cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
@@ -185,6 +188,7 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
     }
     if (g->h_status) cudaFreeHost(g->h_status);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : g->evb) if (e) cudaEventDestroy(e);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
     return MRC_OK;
@@ -231,6 +235,7 @@ static int graph_new(int64_t n, int64_t m, int device, bool with_int, mrc_graph 
         g->sms = di->sms;
         CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
         for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
+        for (auto &e : g->evb) CUDA_TRY(cudaEventCreate(&e));
         const size_t m4 = ((size_t)m + 3) & ~(size_t)3;   // vector loads never read past the allocation
         DALLOC(g->d_src, m4 * 4); DALLOC(g->d_dst, m4 * 4);
         DALLOC(g->d_cost, m4 * 8); DALLOC(g->d_time, m4 * 8);
@@ -633,20 +638,42 @@ extern "C" int mrc_graph_patch_edges(mrc_graph *g, int64_t k, const int64_t *idx
     if (k == 0) return MRC_OK;
     for (ll i = 0; i < k; i++)
         if (idx[i] < 0 || idx[i] >= g->m) return set_err(MRC_ERR_ARG, "edge index out of range");
+    {   // an edge listed twice would race on its saved weight: mrc_graph_restore could not bring the original back
+        std::vector<int64_t> sorted(idx, idx + k);
+        std::sort(sorted.begin(), sorted.end());
+        if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) return set_err(MRC_ERR_ARG, "edge index listed twice in one patch");
+    }
     CUDA_TRY(cudaSetDevice(g->device));
     PatchRec p;
-    p.k = k;
-    double *d_dc, *d_dt;
-    DALLOC(p.d_idx, (size_t)k * 8); DALLOC(p.d_oldc, (size_t)k * 8); DALLOC(p.d_oldt, (size_t)k * 8);
-    DALLOC(d_dc, (size_t)k * 8); DALLOC(d_dt, (size_t)k * 8);
-    CUDA_TRY(cudaMemcpyAsync(p.d_idx, idx, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_dc, dcost, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_dt, dtime, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
-    patch_edges_kernel<<<(int)((k + 127) / 128), 128, 0, g->stream>>>(g->d_cost, g->d_time, p.d_idx, d_dc, d_dt, k,
-                                                                      p.d_oldc, p.d_oldt);
-    CUDA_TRY(cudaGetLastError());
-    cudaFreeAsync(d_dc, g->stream); cudaFreeAsync(d_dt, g->stream);
-    CUDA_TRY(cudaStreamSynchronize(g->stream));   // the host delta arrays may be reused by the caller
+    p.k = k; p.d_idx = nullptr; p.d_oldc = p.d_oldt = nullptr;
+    double *d_dc = nullptr, *d_dt = nullptr;
+    int bad = 0;
+    int rc = [&]() -> int {
+        DALLOC(p.d_idx, (size_t)k * 8); DALLOC(p.d_oldc, (size_t)k * 8); DALLOC(p.d_oldt, (size_t)k * 8);
+        DALLOC(d_dc, (size_t)k * 8); DALLOC(d_dt, (size_t)k * 8);
+        CUDA_TRY(cudaMemcpyAsync(p.d_idx, idx, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_dc, dcost, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_dt, dtime, (size_t)k * 8, cudaMemcpyHostToDevice, g->stream));
+        CUDA_TRY(cudaMemsetAsync(g->d_verr, 0, 4, g->stream));
+        patch_edges_kernel<<<(int)((k + 127) / 128), 128, 0, g->stream>>>(g->d_cost, g->d_time, p.d_idx, d_dc, d_dt, k,
+                                                                          p.d_oldc, p.d_oldt, g->d_verr);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&bad, g->d_verr, 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));   // the host delta arrays may be reused by the caller
+        if (bad) {   // every kernel of the path relies on time > 0 (ratio bounds, the sign test of a cycle): undo and refuse
+            unpatch_edges_kernel<<<(int)((k + 127) / 128), 128, 0, g->stream>>>(g->d_cost, g->d_time, p.d_idx, k, p.d_oldc, p.d_oldt);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(g->stream));
+            return set_err(MRC_ERR_ARG, "Edge transit time must be strictly positive after the perturbation");
+        }
+        return MRC_OK;
+    }();
+    if (d_dc) cudaFreeAsync(d_dc, g->stream);
+    if (d_dt) cudaFreeAsync(d_dt, g->stream);
+    if (rc) {
+        for (void *q : {(void *)p.d_idx, (void *)p.d_oldc, (void *)p.d_oldt}) if (q) cudaFreeAsync(q, g->stream);
+        return rc;
+    }
     g->patches.push_back(p);
     g->pot_valid = false;
     g->stats.other_launches++;
@@ -944,8 +971,11 @@ int ProbeRun::enqueue_burst(int cap) {
         dense_launches++;
         // launch i > 0 skips the candidates launch i-1 did not move (fixed point) and returns at once if that is all of them
         ra.gate = (i > 0 && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
+        ra.lowered = g->check_skip ? &g->d_status->lowered[i * MRC_KMAX] : nullptr;
+        CUDA_TRY(cudaEventRecord(g->evb[i], g->stream));
         MRC_TRY(launch_relax(g, KT, exact, ra, ck));
     }
+    if (!sparse_burst) CUDA_TRY(cudaEventRecord(g->evb[nb], g->stream));
     if (use_sparse && !sparse_burst) {
         // bm[1] may hold the membership bits of a worklist nobody consumed (a probe that ended on a verified cycle,
         // or a switch back to dense sweeps): the next worklist pass deduplicates through it, so it must be clean
@@ -959,6 +989,7 @@ int ProbeRun::enqueue_burst(int cap) {
     do_check = passes + nb >= next_check || passes + nb >= max_passes;
     if (do_check) {
         ca.gate = g->gate ? &g->d_status->changed[nb - 1] : nullptr;
+        ca.skip_nb = (g->check_skip && !sparse_burst && passes + nb < max_passes) ? nb : 0;
         if (ck >= 0) {   // the survivor's predecessor graph lives in the compact column: a 1-wide check, results in slot 0
             CheckArgs cc = ca;
             cc.pred = g->d_cpred; cc.dist = g->d_cdist; cc.jump = g->d_cjump; cc.cyc_edges = g->d_cyc_edges + (ll)ck * g->cyc_cap;
@@ -986,14 +1017,17 @@ int ProbeRun::collect() {
     if (nb <= 0) return MRC_OK;
     const ll n = g->n, m = g->m;
     float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]));
-    if (sparse_burst) g->stats.sparse_ms += ms; else g->stats.relax_ms += ms;
-    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
     const DevStatus &hs = *g->h_status;
     // launches / passes that did work: the first of the burst, and each one whose predecessor still moved something
     int ran = nb;
     if (g->gate || sparse_burst)
         for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
+    if (sparse_burst) { CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->stats.sparse_ms += ms; }
+    else {   // relaxation time = the launches that swept the edges; the gated-out tail of the burst (~3 us each) is idle time
+        CUDA_TRY(cudaEventElapsedTime(&ms, g->evb[0], g->evb[ran])); g->stats.relax_ms += ms;
+        if (ran < nb) { CUDA_TRY(cudaEventElapsedTime(&ms, g->evb[ran], g->evb[nb])); g->stats.gated_ms += ms; }
+    }
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
     if (sparse_burst) {
         g->stats.sparse_passes += ran;
         g->stats.other_launches += 1;
@@ -1366,6 +1400,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "compact_min_edges") g->compact_min_edges = std::max(0, value);
     else if (s == "lookahead") g->lookahead = value != 0;
     else if (s == "check_every") g->check_every = std::max(0, value);
+    else if (s == "check_skip") g->check_skip = value != 0;
     else if (s == "cert_first") g->cert_first = value != 0;
     else if (s == "tick_max") g->tick_max = std::max(1, std::min(value, MRC_MAX_BURST));
     else if (s == "gate") g->gate = value != 0;

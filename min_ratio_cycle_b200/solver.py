@@ -194,6 +194,7 @@ class MinRatioCycleSolver:
         self.config = config or SolverConfig()
         self._edges: list[Edge] = []
         self._bulk: list[tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = []
+        self._bulk_int: list[tuple[np.ndarray, np.ndarray] | None] = []   # exact int64 weights of a bulk block given as integers
         self._presorted = None
         self._no_repeated_pairs = False
         self._hop_cache: dict = {}
@@ -270,6 +271,7 @@ class MinRatioCycleSolver:
         if removed:
             keep = self._dev.fetch_keep()                      # the reference drops the edges from its list for good
             self._bulk = [tuple(a[keep] for a in self._bulk[0])]
+            self._bulk_int = [None]
             self.logger.info("Preprocessing removed %d dominated edges", removed)
         self._no_repeated_pairs = dups == 0 or remove_dominated
         for name in ("_U", "_V", "_C", "_T", "_starts", "_counts", "_order"):
@@ -327,6 +329,10 @@ class MinRatioCycleSolver:
         """
         U = np.ascontiguousarray(U, dtype=np.int64)
         V = np.ascontiguousarray(V, dtype=np.int64)
+        ints = None
+        if np.asarray(cost).dtype.kind in "iu" and np.asarray(time).dtype.kind in "iu":
+            # integer weights stay exact (the float64 view below rounds above 2^53; exact mode reads these, :493-498)
+            ints = (np.array(cost, dtype=np.int64), np.array(time, dtype=np.int64))
         Cw = np.ascontiguousarray(cost, dtype=np.float64)
         Tw = np.ascontiguousarray(time, dtype=np.float64)
         if not (len(U) == len(V) == len(Cw) == len(Tw)):
@@ -349,6 +355,7 @@ class MinRatioCycleSolver:
         # else: a large numeric block is range-checked on the device when the arrays are built (same ValueErrors, raised
         # by solve()); it is borrowed, not copied -- 320 MB at 10^7 edges -- so the caller must not modify it until then
         self._bulk.append((U, V, Cw, Tw))
+        self._bulk_int.append(ints)
         self._invalidate()
 
     def remove_edge(self, u: int, v: int) -> bool:
@@ -364,8 +371,11 @@ class MinRatioCycleSolver:
                 k = np.ones(len(U), dtype=bool)
                 k[hit[0]] = False
                 self._bulk[bi] = (U[k], V[k], Cw[k], Tw[k])
+                if self._bulk_int[bi] is not None:
+                    self._bulk_int[bi] = tuple(a[k] for a in self._bulk_int[bi])
                 if len(self._bulk[bi][0]) == 0:
                     del self._bulk[bi]
+                    del self._bulk_int[bi]
                 self._invalidate()
                 return True
         return False
@@ -373,6 +383,7 @@ class MinRatioCycleSolver:
     def clear_edges(self) -> None:
         self._edges.clear()
         self._bulk.clear()
+        self._bulk_int.clear()
         self._invalidate()
 
     # ------------------------------------------------------------------ graph analysis (:339-444)
@@ -471,8 +482,15 @@ class MinRatioCycleSolver:
         if self.n > 1:
             np.cumsum(self._counts[:-1], out=self._starts[1:])
         if self._all_int:
-            self._Ci = np.trunc(self._C).astype(np.int64)   # int(edge.cost), :493-498
-            self._Ti = np.trunc(self._T).astype(np.int64)
+            # int(edge.cost), int(edge.time) (:493-498) from the ORIGINAL values: a Python int or an integer array above
+            # 2^53 is not representable in the float64 arrays; above 2^63 this raises OverflowError like the reference
+            ci = [np.array([int(e.cost) for e in self._edges], dtype=np.int64)]
+            ti = [np.array([int(e.time) for e in self._edges], dtype=np.int64)]
+            for b, bi in zip(self._bulk, self._bulk_int):
+                ci.append(np.trunc(b[2]).astype(np.int64) if bi is None else bi[0])
+                ti.append(np.trunc(b[3]).astype(np.int64) if bi is None else bi[1])
+            self._Ci = np.concatenate(ci)[order]
+            self._Ti = np.concatenate(ti)[order]
         else:
             self._Ci = self._Ti = None
         self._is_sparse = len(self._U) / (self.n * self.n) < self.config.sparse_threshold
@@ -542,16 +560,21 @@ class MinRatioCycleSolver:
         m1 = len(self._edges)
         self._edges = [e for i, e in enumerate(self._edges) if not drop[i]]
         off = m1
-        kept = []
-        for b in self._bulk:
+        kept, kept_int = [], []
+        for b, bi in zip(self._bulk, self._bulk_int):
             k = ~drop[off: off + len(b[0])]
             off += len(b[0])
             if k.any():
                 kept.append(tuple(a[k] for a in b))
-        self._bulk = kept
+                kept_int.append(None if bi is None else tuple(a[k] for a in bi))
+        self._bulk, self._bulk_int = kept, kept_int
 
     # ------------------------------------------------------------------ solve (:581-679)
     def solve(self, mode: SolverMode | str = SolverMode.AUTO, target_ratio: float | None = None, **kwargs) -> SolverResult:
+        """solve() of the reference (:581-679): same ladder, errors and result conventions.  `mode` is validated and then
+        ignored unless SolverConfig.honor_mode (the reference always runs numeric, :622-627).  `target_ratio` is accepted
+        and ignored: the reference's early exit compares it with the cycle's sum_time (a bug, :1063-1071) and a search
+        that needs 5-10 probes has nothing to cut short."""
         if isinstance(mode, str):
             mode = SolverMode(mode)
         t_start = _time.time()
@@ -788,14 +811,16 @@ class MinRatioCycleSolver:
         if not result.success or not result.cycle:
             return result
         try:
-            if len(result.cycle) < 3 and not self.config.repair_cycles:
-                result.success, result.error_message = False, "Cycle too short"
-                return result
+            if len(result.cycle) < 3:
+                if not self.config.repair_cycles:
+                    result.success, result.error_message = False, "Cycle too short"
+                    return result
+                result = self._repair_short_cycle(result)
             ok, issues = self._verify_cycle_exists(result.cycle)
             if not ok:
-                result.success = False
-                result.error_message = (f"Could not repair cycle: {', '.join(issues)}" if self.config.repair_cycles
-                                        else f"Invalid cycle: {', '.join(issues)}")
+                if self.config.repair_cycles:
+                    return self._repair_missing_edges(result, issues)
+                result.success, result.error_message = False, f"Invalid cycle: {', '.join(issues)}"
                 return result
             c, t = self._compute_cycle_weights_float(result.cycle[:-1])
             tol = 1e-10 if isinstance(result.ratio, (int, Fraction)) else 1e-6
@@ -809,6 +834,30 @@ class MinRatioCycleSolver:
         except Exception as exc:
             result.success, result.error_message = False, f"Validation failed: {exc}"
             return result
+
+    def _has_edge(self, u: int, v: int) -> bool:
+        """:1622-1629, through the CSR segment of v instead of a scan of the edge list."""
+        self._build_arrays_if_needed()
+        return self._hop_edges(u, v).size > 0
+
+    def _repair_short_cycle(self, result: SolverResult) -> SolverResult:
+        """:1584-1608.  Only a closed 2-cycle [u, v, u] is ever extended (to u -> w -> v -> u through the first w that has
+        both edges); _validate_result calls this for cycles shorter than that (a self-loop [v, v]), which it leaves alone."""
+        if len(result.cycle) == 3 and result.cycle[0] == result.cycle[2]:
+            u, v = result.cycle[0], result.cycle[1]
+            for w in range(self.n):
+                if w != u and w != v and self._has_edge(u, w) and self._has_edge(w, v):
+                    new_cycle = [u, w, v, u]
+                    cost, time = self._compute_cycle_weights_float(new_cycle[:-1])
+                    result.cycle, result.sum_cost, result.sum_time, result.ratio = new_cycle, cost, time, cost / time
+                    return result
+        return result
+
+    def _repair_missing_edges(self, result: SolverResult, issues: list[str]) -> SolverResult:
+        """:1610-1620: no repair is attempted, the result is marked failed with the reference's message."""
+        result.success = False
+        result.error_message = f"Could not repair cycle: {', '.join(issues)}"
+        return result
 
     # ------------------------------------------------------------------ analytics (:1699-1759)
     def _certify_single_edge_scenarios(self, warm, pos, dc, dt, tol, slack):

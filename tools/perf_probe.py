@@ -11,6 +11,8 @@ for seed in seeds:
     o = np.argsort(V, kind="stable")
     g = N.DeviceGraph(n, U[o].astype(np.int32), V[o].astype(np.int32), C[o], T[o])
     lo, hi = g.bounds()
+    for kv in filter(None, os.environ.get("OPTS", "").split(",")):
+        k, v = kv.split("="); g.set_option(k, int(v)); tag = tag + " " + kv if kv not in tag else tag
     g.set_option("sparse", 0)
     base = g.solve_numeric(lo, hi, K=1)
     r = base["ratio"]
