@@ -87,8 +87,6 @@ typedef struct mrc_stats {
     int64_t relax_edge_slots;     /* sum over launches of m * (active candidates), whether or not an edge was skipped */
     int64_t sparse_passes;        /* worklist passes (relax_sparse_kernel: only out-edges of the vertices the previous pass lowered) */
     double sparse_ms;             /* CUDA-event time spent in them (not part of relax_ms) */
-    double gated_ms;              /* CUDA-event time of the launches of a burst that returned at once because their candidates had
-                                     converged (not part of relax_ms; relax_ms counts the launches that swept the edges) */
 } mrc_stats;
 
 int mrc_abi_version(void);
@@ -179,25 +177,28 @@ int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_cycle, int m
 /* Measurement aid (bench/profiling only): `passes` relaxation launches for K lambdas from dist == 0, no
  * cycle checks, each launch timed with CUDA events on the library's stream. */
 int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *ms_per_pass);
-/* Tuning knobs: "alternate" (sweep direction flips every pass, 0/1), "burst_init", "burst_max" (passes per
- * host round trip), "tma" (bit mask over K in {1,2,4,8}: TMA-staged edge stream), "frontier" (0/1: launches
- * from "frontier_from" on skip edges whose source vertex was not lowered by the previous launch), "stop_on_neg"
- * (minimum K from which mrc_solve_numeric passes MRC_F_STOP_ON_NEG to its probes; 0 = never, the default),
- * "narrow" (0/1, default 1: once some of the K candidates of a probe are decided, the remaining passes run the
- * narrowest kernel -- 1, 2 or 4 candidates wide -- that covers the undecided slots of the dist/pred layout),
- * "gate" (0/1, default 1: a relaxation launch returns at once when the previous launch of its burst moved none of
- * its candidates, so bursts can be long without wasting passes after convergence), "sparse" (0/1, default 0 or
- * the environment variable MRC_B200_SPARSE; the Python facade switches it on: once fewer than n / "sparse_div" (default 32) vertices were lowered by the last pass of a burst, the next bursts
- * run as worklist passes over the out-edges of just those vertices -- same fixed point, same verdicts; graphs
- * below "sparse_min_edges" (default 1.5 M) keep sweeping; "sparse_look": dense bursts are at most this long while
- * the worklist waits to take over, 0 = chosen by graph size),
- * "async" (0/1, default 0 or the environment variable MRC_B200_ASYNC: mrc_solve_numeric with K >= 2 refills a
- * candidate slot the moment its candidate is decided instead of waiting for the round's slowest one; fewer sweeps,
- * costlier ones -- measured slower on large graphs, see profiles/r01e_policy.txt), "prune_above" (0/1, default 1:
- * with MRC_F_MONOTONE_PRUNE and candidates in increasing order a cycle check stops working on the candidates
- * above the lowest one whose predecessor graph holds a cycle), "patience" (0/1:
- * mrc_solve_numeric passes MRC_F_PATIENCE to its probes).
- * A graph handle is not thread-safe: one probe / solve at a time per mrc_graph. */
+/* Tuning knobs (defaults in brackets; measurements: profiles/):
+ *   "burst_init" [2], "burst_max" [16]  passes per host round trip (bursts of 2, 4, 8, 16, 16, ...)
+ *   "gate" [1]        a relaxation launch skips the candidates the previous launch of its burst did not move and returns at
+ *                     once when that is all of them, so bursts can be long without wasting passes after convergence
+ *   "narrow" [1]      once some of the K candidates of a probe are decided, the remaining passes run the narrowest kernel
+ *                     (1, 2 or 4 candidates wide) that covers the undecided slots of the dist/pred layout
+ *   "compact" [1], "compact_min_edges" [2 M]  a probe narrowed to ONE live candidate continues on a compact [n][1] copy of
+ *                     its dist/pred column (8 MB of contiguous doubles instead of every K-th double of 8K MB)
+ *   "sparse" [0; env MRC_B200_SPARSE; the Python facade switches it on], "sparse_div" [32], "sparse_min_edges" [1.5 M],
+ *   "sparse_look" [0 = by graph size]  once fewer than n / sparse_div vertices were lowered by the last pass of a burst, the
+ *                     next bursts run as worklist passes over the out-edges of just those vertices (same fixed point, same
+ *                     verdicts); smaller graphs keep sweeping; dense bursts are at most sparse_look long while the worklist
+ *                     waits to take over
+ *   "prune_above" [1] with MRC_F_MONOTONE_PRUNE and candidates in increasing order a cycle check stops working on the
+ *                     candidates above the lowest one whose predecessor graph holds a cycle
+ *   "cert_first" [1]  mrc_solve_numeric passes MRC_F_CERT_FIRST to the probes of rounds that already hold a cycle
+ *   "stop_on_neg" [0] minimum K from which mrc_solve_numeric passes MRC_F_STOP_ON_NEG; "patience" [0]: MRC_F_PATIENCE
+ *   "check_every" [0] experiments: cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
+ *   "tick_max" [8]    longest tick (passes between two exchanges) of mrc_solve_numeric_sharded
+ *   "sparse_poison"   test hook
+ * A graph handle is not thread-safe: one probe / solve at a time per mrc_graph (different handles, also on different
+ * devices, may be used from different threads). */
 int mrc_set_option(mrc_graph *g, const char *name, int value);
 
 /* Pure host helpers shared by mrc_solve_numeric and the multi-GPU driver (one process per GPU, the

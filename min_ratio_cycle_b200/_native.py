@@ -54,7 +54,7 @@ class Stats(C.Structure):
         ("probes", C.c_int64), ("rounds", C.c_int64), ("other_launches", C.c_int64),
         ("relax_ms", C.c_double), ("check_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("false_cycles_cut", C.c_int64), ("relax_edge_slots", C.c_int64),
-        ("sparse_passes", C.c_int64), ("sparse_ms", C.c_double), ("gated_ms", C.c_double),
+        ("sparse_passes", C.c_int64), ("sparse_ms", C.c_double)
     ]
 
     def as_dict(self):

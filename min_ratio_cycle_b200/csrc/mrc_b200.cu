@@ -46,7 +46,6 @@ struct mrc_graph {
     int device = 0, sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t evb[MRC_MAX_BURST + 1] = {};   // one per dense launch of a burst: launches gated out are not relaxation time
     ll n = 0, m = 0;
     int *d_src = nullptr, *d_dst = nullptr;
     double *d_cost = nullptr, *d_time = nullptr;
@@ -96,8 +95,7 @@ struct mrc_graph {
     int narrow = 1;              // option "narrow": late passes run the narrowest kernel covering the undecided candidates
     int compact = 1;             // option "compact": a probe narrowed to ONE live slot continues on a compact [n][1] copy of its column
     ll compact_min_edges = 2000000;   // ... on graphs where a sweep is bandwidth-bound (smaller ones are launch-bound)
-    int check_skip = 0;          // option "check_skip": a cycle check leaves out candidates whose lowering count is still collapsing
-                                 // (measured: -7..-13 % on instances with long certifying probes, +10 % and one more round on C3 seed 0: off)
+    int pdl = 1;                 // option "pdl": sweep i > 0 of a burst is launched with programmatic stream serialisation (queued while sweep i-1 drains)
     int cert_first = 1;          // option "cert_first": mrc_solve_numeric passes MRC_F_CERT_FIRST to the probes of rounds that hold a cycle
     int tick_max = 8;            // option "tick_max": longest tick (passes between two exchanges) of the sharded search
     int check_every = 0;         // option "check_every" (experiments): cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
@@ -188,7 +186,6 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
     }
     if (g->h_status) cudaFreeHost(g->h_status);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
-    for (auto &e : g->evb) if (e) cudaEventDestroy(e);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
     return MRC_OK;
@@ -235,7 +232,6 @@ static int graph_new(int64_t n, int64_t m, int device, bool with_int, mrc_graph 
         g->sms = di->sms;
         CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
         for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
-        for (auto &e : g->evb) CUDA_TRY(cudaEventCreate(&e));
         const size_t m4 = ((size_t)m + 3) & ~(size_t)3;   // vector loads never read past the allocation
         DALLOC(g->d_src, m4 * 4); DALLOC(g->d_dst, m4 * 4);
         DALLOC(g->d_cost, m4 * 8); DALLOC(g->d_time, m4 * 8);
@@ -734,6 +730,17 @@ static void compact_args(const mrc_graph *g, int k, const RelaxArgs &ra_full, Re
 static int launch_relax_args(mrc_graph *g, int kc, bool exact, const RelaxArgs &ra) {
     void *args[] = {(void *)&ra};
     const int blocks = g->relax_blocks[kt_index(kc)][exact ? 1 : 0];
+    if (g->pdl && ra.gate) {   // a sweep that follows another sweep of its burst: queue it while the previous one drains
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(MRC_RELAX_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = g->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, relax_fn_of(kc, exact, ra.scen != 0), args));
+        return MRC_OK;
+    }
     CUDA_TRY(cudaLaunchKernel(relax_fn_of(kc, exact, ra.scen != 0), dim3(blocks), dim3(MRC_RELAX_THREADS), args, 0, g->stream));
     return MRC_OK;
 }
@@ -971,11 +978,8 @@ int ProbeRun::enqueue_burst(int cap) {
         dense_launches++;
         // launch i > 0 skips the candidates launch i-1 did not move (fixed point) and returns at once if that is all of them
         ra.gate = (i > 0 && g->gate) ? &g->d_status->changed[i - 1] : nullptr;
-        ra.lowered = g->check_skip ? &g->d_status->lowered[i * MRC_KMAX] : nullptr;
-        CUDA_TRY(cudaEventRecord(g->evb[i], g->stream));
         MRC_TRY(launch_relax(g, KT, exact, ra, ck));
     }
-    if (!sparse_burst) CUDA_TRY(cudaEventRecord(g->evb[nb], g->stream));
     if (use_sparse && !sparse_burst) {
         // bm[1] may hold the membership bits of a worklist nobody consumed (a probe that ended on a verified cycle,
         // or a switch back to dense sweeps): the next worklist pass deduplicates through it, so it must be clean
@@ -989,7 +993,6 @@ int ProbeRun::enqueue_burst(int cap) {
     do_check = passes + nb >= next_check || passes + nb >= max_passes;
     if (do_check) {
         ca.gate = g->gate ? &g->d_status->changed[nb - 1] : nullptr;
-        ca.skip_nb = (g->check_skip && !sparse_burst && passes + nb < max_passes) ? nb : 0;
         if (ck >= 0) {   // the survivor's predecessor graph lives in the compact column: a 1-wide check, results in slot 0
             CheckArgs cc = ca;
             cc.pred = g->d_cpred; cc.dist = g->d_cdist; cc.jump = g->d_cjump; cc.cyc_edges = g->d_cyc_edges + (ll)ck * g->cyc_cap;
@@ -1022,11 +1025,10 @@ int ProbeRun::collect() {
     int ran = nb;
     if (g->gate || sparse_burst)
         for (ran = 1; ran < nb && (hs.changed[ran - 1] & active); ran++) {}
-    if (sparse_burst) { CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->stats.sparse_ms += ms; }
-    else {   // relaxation time = the launches that swept the edges; the gated-out tail of the burst (~3 us each) is idle time
-        CUDA_TRY(cudaEventElapsedTime(&ms, g->evb[0], g->evb[ran])); g->stats.relax_ms += ms;
-        if (ran < nb) { CUDA_TRY(cudaEventElapsedTime(&ms, g->evb[ran], g->evb[nb])); g->stats.gated_ms += ms; }
-    }
+    // one event pair per burst (an event between every two launches was measured: it breaks the back-to-back issue of the
+    // kernels and costs ~15 us per launch): the few gated-out launches of a burst (~4 us each) count as relaxation time
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]));
+    if (sparse_burst) g->stats.sparse_ms += ms; else g->stats.relax_ms += ms;
     CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->stats.check_ms += ms;
     if (sparse_burst) {
         g->stats.sparse_passes += ran;
@@ -1400,7 +1402,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "compact_min_edges") g->compact_min_edges = std::max(0, value);
     else if (s == "lookahead") g->lookahead = value != 0;
     else if (s == "check_every") g->check_every = std::max(0, value);
-    else if (s == "check_skip") g->check_skip = value != 0;
+    else if (s == "pdl") g->pdl = value != 0;
     else if (s == "cert_first") g->cert_first = value != 0;
     else if (s == "tick_max") g->tick_max = std::max(1, std::min(value, MRC_MAX_BURST));
     else if (s == "gate") g->gate = value != 0;

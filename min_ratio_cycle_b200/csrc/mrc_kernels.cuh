@@ -62,7 +62,6 @@ struct RelaxArgs {
     // Candidates a cycle check has already decided on the device (DevStatus::decided, bit per slot of the layout):
     // bursts enqueued before the host has read that check's result skip them.
     const unsigned *decided;
-    unsigned *lowered;   // [KT] counters of this launch: successful lowerings per candidate slot of the layout (NULL = not counted)
     unsigned *act_out;   // one bit per vertex, "dist[v] was lowered for some candidate" (seed of a worklist); NULL = not tracked
     ull *examined;       // worklist passes: edges actually relaxed
     ll n;
@@ -82,7 +81,6 @@ struct CycleOut {
 struct DevStatus {
     unsigned changed[MRC_MAX_BURST];
     ull examined;                              // worklist passes: edges relaxed (cleared with `changed`)
-    unsigned lowered[MRC_MAX_BURST * MRC_KMAX];   // dense launch i of the burst lowered dist this many times for candidate k (cleared with `changed`)
     unsigned cnt[MRC_MAX_ROUNDS * MRC_KMAX];   // live vertices per doubling round and candidate
     int minlive[MRC_MAX_ROUNDS * MRC_KMAX];    // smallest live vertex per doubling round and candidate
     unsigned cyc_mask, rounds_run, pend, cuts;
@@ -126,9 +124,6 @@ struct CheckArgs {
     int prune_above;        // candidates are in increasing lambda order and the caller prunes by monotonicity: once the
                             // lowest candidate with a cycle is known, the ones above it are not examined further
     int k0;                 // first slot of the layout this (possibly narrowed) launch serves: shifts the bits of `decided`
-    int skip_nb;            // > 1: the burst before this check ran that many dense launches; a candidate whose last launch lowered
-                            // fewer than 80 % of what the one before it lowered is still collapsing towards its fixed point (a
-                            // relaxation that winds around a negative cycle keeps its count) and is not examined by this check
     int samples;            // cycle sampling: warps per candidate that each walk one cycle of the predecessor graph (0 = off)
     double lam[MRC_KMAX];
     ll a[MRC_KMAX], b[MRC_KMAX];
@@ -253,7 +248,7 @@ __device__ __forceinline__ bool mrc_pick_winner(bool imp, ll cand, const RowRuns
 // Control flow never waits for an atomic's return value before all atomics of the row are in flight.
 template <int K, typename T, bool SCEN>
 __device__ __forceinline__ void relax_row(const RelaxArgs &p, unsigned act, bool valid, int lane, unsigned e, int u, int v,
-                                          T c, T t, unsigned &chg, unsigned *s_low) {
+                                          T c, T t, unsigned &chg, unsigned *act_out) {
     // K = 8 is processed as two halves of 4 candidates (two 256-bit gathers from the same 64-B group, one after
     // the other), so its register footprint stays that of K = 4.
     constexpr int H = K > 4 ? 4 : K;
@@ -294,19 +289,13 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, unsigned act, bool
             if ((wins >> k) & 1u) old[k] = mrc_atomic_min(dist + (size_t)v * p.ks + h + k, cand[k]);
         bool lowered = false;
 #pragma unroll
-        for (int k = 0; k < H; k++) {
-            const bool ok = ((wins >> k) & 1u) && mrc_lowered(old[k], cand[k]);
-            if (ok) {
+        for (int k = 0; k < H; k++)
+            if (((wins >> k) & 1u) && mrc_lowered(old[k], cand[k])) {
                 __stcg(p.pred + (size_t)v * p.ks + h + k, ((ull)(unsigned)u << 32) | e);
                 chg |= 1u << (h + k);
                 lowered = true;
             }
-            if (p.lowered) {   // warp-uniform (kernel argument); slow path only: the warp is converged here
-                const unsigned okm = __ballot_sync(MRC_FULL, ok);
-                if (okm && lane == 0) atomicAdd(&s_low[h + k], (unsigned)__popc(okm));
-            }
-        }
-        if (lowered && p.act_out) atomicOr(p.act_out + (v >> 5), 1u << (v & 31));
+        if (lowered && act_out) atomicOr(act_out + (v >> 5), 1u << (v & 31));
     }
 }
 
@@ -339,18 +328,12 @@ template <int K> struct RelaxTune {
     // at K = 8 (two halves) the extra registers cost more than the overlap wins (101 -> 120 us)
     static constexpr bool prefetch = MRC_TUNE_PF;
 };
+// One sweep over the edge stream for the candidates in `act`; ORs "candidate k lowered something" into *changed.
 template <int K, bool EXACT, bool SCEN>
-__global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) relax_kernel(const __grid_constant__ RelaxArgs p) {
+__device__ __forceinline__ void relax_sweep(const RelaxArgs &p, unsigned act, unsigned *changed, unsigned *act_out) {
     typedef typename WeightT<EXACT>::type W;
     const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
     const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
-    unsigned act = p.active;
-    if (p.decided) act &= ~(__ldcg(p.decided) >> p.k0);
-    if (p.gate) act &= __ldcg(p.gate) >> p.k0;
-    if (!act) return;
-    __shared__ unsigned s_low[MRC_KMAX];   // lowerings of this CTA per candidate (slow path of relax_row)
-    if (threadIdx.x < MRC_KMAX) s_low[threadIdx.x] = 0;
-    __syncthreads();
     unsigned chg = 0;
     const int lane = threadIdx.x & 31;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -365,7 +348,7 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
             const unsigned e = c * CH + 32 * j + lane;
             const bool ok = e < m;
             relax_row<K, W, SCEN>(p, act, ok, lane, e, ok ? p.src[e] : 0, ok ? p.dst[e] : 0, ok ? cost[e] : W(0),
-                                  ok ? time[e] : W(0), chg, s_low);
+                                  ok ? time[e] : W(0), chg, act_out);
         }
     };
     if constexpr (!RelaxTune<K>::prefetch) {
@@ -382,7 +365,7 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
             }
 #pragma unroll
             for (int j = 0; j < ROWS; j++)
-                relax_row<K, W, SCEN>(p, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg, s_low);
+                relax_row<K, W, SCEN>(p, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg, act_out);
         }
     } else {
         int s[ROWS], d[ROWS], s2[ROWS], d2[ROWS];
@@ -412,7 +395,7 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
             const unsigned e0 = c * CH + lane;
 #pragma unroll
             for (int j = 0; j < ROWS; j++)
-                relax_row<K, W, SCEN>(p, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg, s_low);
+                relax_row<K, W, SCEN>(p, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg, act_out);
 #pragma unroll
             for (int j = 0; j < ROWS; j++) { s[j] = s2[j]; d[j] = d2[j]; cs[j] = cs2[j]; tm[j] = tm2[j]; }
             c = nx;
@@ -420,11 +403,22 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
     }
     // changed flag: warp vote, one atomic per warp at most
     chg = __reduce_or_sync(MRC_FULL, chg);
-    if (lane == 0 && chg) atomicOr(p.changed, chg << p.k0);
-    if (p.lowered) {
-        __syncthreads();
-        if (threadIdx.x < K && s_low[threadIdx.x]) atomicAdd(p.lowered + p.k0 + threadIdx.x, s_low[threadIdx.x]);
-    }
+    if (lane == 0 && chg) atomicOr(changed, chg << p.k0);
+}
+
+template <int K, bool EXACT, bool SCEN>
+__global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) relax_kernel(const __grid_constant__ RelaxArgs p) {
+    // Programmatic dependent launch (sm_90+): the sweeps of a burst are launched with programmatic stream serialisation, so
+    // this grid is already queued on the device while the previous sweep drains; it must not read what that sweep wrote
+    // before griddepcontrol.wait returns (full completion + flush of the prerequisite grid), and it lets ITS successor be
+    // queued right away.  Without the launch attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    unsigned act = p.active;
+    if (p.decided) act &= ~(__ldcg(p.decided) >> p.k0);
+    if (p.gate) act &= __ldcg(p.gate) >> p.k0;
+    if (!act) return;
+    relax_sweep<K, EXACT, SCEN>(p, act, p.changed, p.act_out);
 }
 
 // dist[v][0..ks) = base[v] for every vertex: a probe that starts from the converged potentials of a neighbouring
@@ -577,14 +571,7 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         st->out[threadIdx.x].len = 0;
     }
     if (tid0 == 0) { st->cyc_mask = 0; st->pend = 0; st->cuts = 0; }
-    unsigned active = p.gate ? (p.active & (__ldcg(p.gate) >> p.k0)) : p.active;
-    if (p.skip_nb > 1) {   // grid-uniform: every thread reads the same counters
-        for (int k = 0; k < K; k++) {
-            const unsigned a = __ldcg(&st->lowered[(p.skip_nb - 2) * MRC_KMAX + p.k0 + k]);
-            const unsigned b = __ldcg(&st->lowered[(p.skip_nb - 1) * MRC_KMAX + p.k0 + k]);
-            if ((ull)b * 5 < (ull)a * 4) active &= ~(1u << k);
-        }
-    }
+    const unsigned active = p.gate ? (p.active & (__ldcg(p.gate) >> p.k0)) : p.active;
     if (!active) return;   // grid-uniform
     // jump = grandparent (two predecessor steps straight from pred, which nobody writes during this
     // phase): saves the separate init sweep, its grid sync and the src[] gather of an edge-only pred
