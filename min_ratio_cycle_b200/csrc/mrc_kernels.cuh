@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                     // tail is longer still, the point where the capped lap stopped is itself past the tail; only
                     // if even that fails Brent's cycle finding (one pointer step per iteration) runs from there.
                     int y = rep;
-                    for (int t = 0; t < 96; t++) {
+                    for (int t = 0; t < 96; t++) {   // (16 hops were measured: the capped laps of the fallback cost more, check 65 -> 80-93 us)
                         const int j = __ldcg(p.jump + (ll)y * K + k);
                         if (j < 0) break;
                         y = j;
