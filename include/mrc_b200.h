@@ -194,7 +194,10 @@ int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *m
  *                     candidates above the lowest one whose predecessor graph holds a cycle
  *   "cert_first" [1]  mrc_solve_numeric passes MRC_F_CERT_FIRST to the probes of rounds that already hold a cycle
  *   "stop_on_neg" [0] minimum K from which mrc_solve_numeric passes MRC_F_STOP_ON_NEG; "patience" [0]: MRC_F_PATIENCE
- *   "check_every" [0] experiments: cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
+ *   "check_growth" [50]  cycle checks after 2 passes and then every max(4, 50 % of the passes so far): 2, 6, 10, 15, 22, 33, 49, ...
+ *                     (0: the doubling schedule 2, 6, 14, 30, ...).  A negative probe ends at the first check after its cycle closed;
+ *                     with doubling a cycle that closes at pass 36 is noticed at 62
+ *   "check_every" [0] experiments: cycle checks every so many passes after the first
  *   "tick_max" [8]    longest tick (passes between two exchanges) of mrc_solve_numeric_sharded
  *   "sparse_poison"   test hook
  * A graph handle is not thread-safe: one probe / solve at a time per mrc_graph (different handles, also on different

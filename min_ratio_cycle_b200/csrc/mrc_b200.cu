@@ -98,6 +98,7 @@ struct mrc_graph {
     int pdl = 1;                 // option "pdl": sweep i > 0 of a burst is launched with programmatic stream serialisation (queued while sweep i-1 drains)
     int cert_first = 1;          // option "cert_first": mrc_solve_numeric passes MRC_F_CERT_FIRST to the probes of rounds that hold a cycle
     int tick_max = 8;            // option "tick_max": longest tick (passes between two exchanges) of the sharded search
+    int check_growth = 50;       // option "check_growth" (0 = the doubling schedule 2, 6, 14, 30, ...): see ProbeRun::enqueue_burst
     int check_every = 0;         // option "check_every" (experiments): cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
     int lookahead = 1;           // option "lookahead": the next burst is enqueued before the previous burst's status is read
     void *d_cdist = nullptr; ull *d_cpred = nullptr; int *d_cjump = nullptr;   // compact column (compact survivor)
@@ -910,7 +911,7 @@ int ProbeRun::begin(mrc_graph *g_, bool exact_, int K_, const double *lam_, cons
     max_passes = n;   // n-1 passes + the detection pass
     passes = 0;
     burst = g->burst_init;
-    next_check = g->burst_init;   // cycle checks after 2, 6, 14, 30, ... passes; convergence flags every burst
+    next_check = g->burst_init;   // cycle checks after 2, 6, 10, 15, 22, 33, 49, ... passes ("check_growth"); convergence flags every burst
     g->stats.probes += K;
     any_neg = false;
     new_verdicts = 0;
@@ -1004,7 +1005,10 @@ int ProbeRun::enqueue_burst(int cap) {
             ca.active = active; ca.k0 = 0;
             MRC_TRY(launch_check(g, KT, ca));
         }
-        next_check = g->check_every > 0 ? next_check + g->check_every : 2 * next_check + 2;
+        // cycle checks after 2, 6, 14, 30, ... passes, or ("check_growth" > 0) every max(4, growth % of the passes so far): a
+        // negative probe is noticed at the first check after its cycle closed
+        next_check = g->check_every > 0 ? next_check + g->check_every
+                     : g->check_growth > 0 ? next_check + std::max<ll>(4, next_check * g->check_growth / 100) : 2 * next_check + 2;
     }
     CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
     return MRC_OK;
@@ -1402,6 +1406,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "compact_min_edges") g->compact_min_edges = std::max(0, value);
     else if (s == "lookahead") g->lookahead = value != 0;
     else if (s == "check_every") g->check_every = std::max(0, value);
+    else if (s == "check_growth") g->check_growth = std::max(0, value);
     else if (s == "pdl") g->pdl = value != 0;
     else if (s == "cert_first") g->cert_first = value != 0;
     else if (s == "tick_max") g->tick_max = std::max(1, std::min(value, MRC_MAX_BURST));
