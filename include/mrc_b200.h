@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MRC_ABI_VERSION 3   /* 2: mrc_stats grew (sparse_passes, sparse_ms); 3: mrc_comm_*, sharded solve, options pruned */
+#define MRC_ABI_VERSION 4   /* 2: mrc_stats grew (sparse_passes, sparse_ms); 3: mrc_comm_*, sharded solve, options pruned; 4: persistent probe kernel (mrc_stats grew) */
 #define MRC_KMAX 8 /* candidate lambdas evaluated by one relaxation launch */
 
 /* status codes */
@@ -87,6 +87,15 @@ typedef struct mrc_stats {
     int64_t relax_edge_slots;     /* sum over launches of m * (active candidates), whether or not an edge was skipped */
     int64_t sparse_passes;        /* worklist passes (relax_sparse_kernel: only out-edges of the vertices the previous pass lowered) */
     double sparse_ms;             /* CUDA-event time spent in them (not part of relax_ms) */
+    int64_t kernel_launches;      /* CUDA kernel launches of this library on the graph's stream (a persistent probe is ONE launch however many
+                                     sweeps it runs; relax_launches / check_launches / sparse_passes keep counting sweeps, checks and passes) */
+    int64_t probe_launches;       /* persistent probe kernels (csrc/mrc_probe.cuh) */
+    double probe_ms;              /* device time inside them (globaltimer): sweeps + checks + worklist passes + grid syncs */
+    int64_t crowded_sweeps;       /* persistent probes: of relax_launches, the first two sweeps of each probe (every vertex is lowered) */
+    double crowded_ms;            /* ... and their share of relax_ms */
+    double check_doubling_ms;     /* inside check_ms (device globaltimer): predecessor-graph pointer doubling ... */
+    double check_extract_ms;      /* ... and cycle extraction + verification */
+    int64_t check_rounds;         /* pointer-doubling rounds over all checks */
 } mrc_stats;
 
 int mrc_abi_version(void);

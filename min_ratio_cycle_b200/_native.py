@@ -54,7 +54,10 @@ class Stats(C.Structure):
         ("probes", C.c_int64), ("rounds", C.c_int64), ("other_launches", C.c_int64),
         ("relax_ms", C.c_double), ("check_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("false_cycles_cut", C.c_int64), ("relax_edge_slots", C.c_int64),
-        ("sparse_passes", C.c_int64), ("sparse_ms", C.c_double)
+        ("sparse_passes", C.c_int64), ("sparse_ms", C.c_double),
+        ("kernel_launches", C.c_int64), ("probe_launches", C.c_int64), ("probe_ms", C.c_double),
+        ("crowded_sweeps", C.c_int64), ("crowded_ms", C.c_double),
+        ("check_doubling_ms", C.c_double), ("check_extract_ms", C.c_double), ("check_rounds", C.c_int64),
     ]
 
     def as_dict(self):

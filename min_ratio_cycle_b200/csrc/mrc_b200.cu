@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "mrc_kernels.cuh"
+#include "mrc_probe.cuh"
 #define MRC_MAX_DEVICES 64
 #define MRC_SPARSE_MIN_EDGES 1500000   /* below this a dense sweep is launch-bound (~10 us) and a worklist pass does not pay */
 #include "mrc_search.h"
@@ -100,7 +101,16 @@ struct mrc_graph {
     int tick_max = 8;            // option "tick_max": longest tick (passes between two exchanges) of the sharded search
     int check_growth = 50;       // option "check_growth" (0 = the doubling schedule 2, 6, 14, 30, ...): see ProbeRun::enqueue_burst
     int check_every = 0;         // option "check_every" (experiments): cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
-    int lookahead = 1;           // option "lookahead": the next burst is enqueued before the previous burst's status is read
+    int qstart = 1;              // option "qstart": the first round of a search without a known cycle places its candidates at low quantiles of the
+                                 // edge-ratio distribution (see plan_first_round) instead of uniformly over [min c/t - 1, max c/t + 1]
+    ll qstart_min_edges = 20000; // ... on graphs of at least this many edges (smaller ones keep the reference's midpoints)
+    std::vector<double> qsample; // sorted sample of cost/time over the edges (first use)
+    int persist = 2;             // option "persist" (env MRC_B200_PERSIST): a probe is ONE cooperative launch (mrc_probe.cuh) instead of bursts + host
+                                 // round trips.  0 never, 1 whenever the kernel exists (K <= 4), 2 (default) for single-candidate probes: measured at C3
+                                 // (profiles/r02_persist.txt) the K = 1 searches gain 10-30 %, the K = 4 ones lose the register double buffer of the
+                                 // crowded first sweeps (165 instead of 116 us) and come out even or behind
+    int probe_blocks[MRC_PW][2] = {{0, 0}, {0, 0}, {0, 0}};
+    ProbeDev *d_probe = nullptr, *h_probe = nullptr;
     void *d_cdist = nullptr; ull *d_cpred = nullptr; int *d_cjump = nullptr;   // compact column (compact survivor)
     void *d_base = nullptr;      // [n] potentials of the base probe of mrc_scenarios_certify
     int *d_order = nullptr;      // mrc_graph_build: index among the preprocessed insertion-order edges of sorted edge i
@@ -136,6 +146,13 @@ static const void *relax_fn_of(int KT, bool exact, bool scen = false) {
         default: return relax_fn<8>(exact, scen);
     }
 }
+static const void *probe_fn_of(int KT, bool exact) {
+    switch (KT) {
+        case 1: return exact ? (const void *)probe_kernel<1, true> : (const void *)probe_kernel<1, false>;
+        case 2: return exact ? (const void *)probe_kernel<2, true> : (const void *)probe_kernel<2, false>;
+        default: return exact ? (const void *)probe_kernel<4, true> : (const void *)probe_kernel<4, false>;
+    }
+}
 static const void *check_fn_of(int KT) {
     switch (KT) {
         case 1: return (const void *)cycle_check_kernel<1>;
@@ -151,9 +168,10 @@ struct DeviceInfo {
     std::once_flag once;
     int rc = MRC_OK;
     std::string err;
-    int sms = 0, occ_relax[4][2], occ_check[4];
+    int sms = 0, occ_relax[4][2], occ_check[4], occ_probe[MRC_PW][2];
 };
 static DeviceInfo g_devinfo[MRC_MAX_DEVICES];
+static std::mutex g_probe_mu[MRC_MAX_DEVICES];
 static int device_info_fill(int device, DeviceInfo &d) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device));
     for (int KT : {1, 2, 4, 8})
@@ -161,6 +179,7 @@ static int device_info_fill(int device, DeviceInfo &d) {
             const int i = kt_index(KT);
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_relax[i][ex], relax_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
             if (ex == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_check[i], check_fn_of(KT), 256, 0));
+            if (i < MRC_PW) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_probe[i][ex], probe_fn_of(KT, ex), MRC_RELAX_THREADS, 0));
         }
     return MRC_OK;
 }
@@ -181,11 +200,12 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
         void *ptrs[] = {g->d_src, g->d_dst, g->d_cost, g->d_time, g->d_icost, g->d_itime, g->d_dist, g->d_pred, g->d_jump,
                         g->d_cyc_edges, g->d_status, g->d_g_src, g->d_g_c, g->d_g_t, g->d_g_ic, g->d_g_it, g->d_mask,
                         g->d_keys, g->d_verr, g->d_out_off, g->d_out_edge,
-                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges, g->d_cdist, g->d_cpred, g->d_cjump, g->d_base, g->d_order, g->d_starts, g->d_keep};
+                        g->d_wl[0], g->d_wl[1], g->d_bm[0], g->d_bm[1], g->d_best_edges, g->d_probe, g->d_cdist, g->d_cpred, g->d_cjump, g->d_base, g->d_order, g->d_starts, g->d_keep};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
         cudaStreamSynchronize(g->stream);
     }
     if (g->h_status) cudaFreeHost(g->h_status);
+    if (g->h_probe) cudaFreeHost(g->h_probe);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
@@ -205,6 +225,12 @@ static int graph_geometry(mrc_graph *g, const DeviceInfo *di) {
             g->relax_blocks[i][ex] = (int)std::min<ll>(need, (ll)di->occ_relax[i][ex] * g->sms);
             const ll needc = std::max<ll>(MRC_KMAX, (n * KT + 255) / 256);
             g->check_blocks[i] = (int)std::min<ll>(needc, (ll)di->occ_check[i] * g->sms);
+            if (i < MRC_PW) {
+                if (di->occ_probe[i][ex] < 1) return set_err(MRC_ERR_CUDA, "probe kernel K=%d does not fit on an SM", KT);
+                // one grid serves the sweeps (a chunk per warp step) and the check (n * KT entries, one CTA per candidate)
+                const ll want = std::max<ll>(std::max<ll>(need, (n * KT + 255) / 256), MRC_KMAX);
+                g->probe_blocks[i][ex] = (int)std::min<ll>(want, (ll)di->occ_probe[i][ex] * g->sms);
+            }
         }
     return MRC_OK;
 }
@@ -249,6 +275,8 @@ static int graph_new(int64_t n, int64_t m, int device, bool with_int, mrc_graph 
         DALLOC(g->d_status, sizeof(DevStatus));
         CUDA_TRY(cudaMemsetAsync(g->d_status, 0, sizeof(DevStatus), g->stream));
         CUDA_TRY(cudaMallocHost(&g->h_status, sizeof(DevStatus)));
+        DALLOC(g->d_probe, sizeof(ProbeDev));
+        CUDA_TRY(cudaMallocHost(&g->h_probe, sizeof(ProbeDev)));
         DALLOC(g->d_keys, 16);
         DALLOC(g->d_verr, 4);
         MRC_TRY(graph_geometry(g, di));
@@ -258,7 +286,7 @@ static int graph_new(int64_t n, int64_t m, int device, bool with_int, mrc_graph 
         if (const char *env = getenv("MRC_B200_SPARSE_LOOK")) g->sparse_look = std::max(0, atoi(env));
         if (const char *env = getenv("MRC_B200_SPARSE_MIN_EDGES")) g->sparse_min_edges = atoll(env);   // parity suite: 0
         if (const char *env = getenv("MRC_B200_COMPACT_MIN_EDGES")) g->compact_min_edges = atoll(env);   // parity suite: 0
-        if (const char *env = getenv("MRC_B200_LOOKAHEAD")) g->lookahead = atoi(env) != 0;
+        if (const char *env = getenv("MRC_B200_PERSIST")) g->persist = std::max(0, std::min(2, atoi(env)));
         return MRC_OK;
     }();
     if (rc) { mrc_graph_destroy(g); return rc; }
@@ -275,7 +303,7 @@ static int graph_validate(mrc_graph *g) {
     int verr = 0;
     CUDA_TRY(cudaMemcpyAsync(&verr, g->d_verr, 4, cudaMemcpyDeviceToHost, g->stream));
     CUDA_TRY(cudaStreamSynchronize(g->stream));
-    g->stats.other_launches++;
+    { g->stats.other_launches++; g->stats.kernel_launches++; }
     if (verr & 1) return set_err(MRC_ERR_ARG, "an edge has an endpoint outside [0,n)");
     if (verr & 2) return set_err(MRC_ERR_ARG, "edges are not destination-sorted");
     if (verr & 4) return set_err(MRC_ERR_ARG, "edge time must be strictly positive");
@@ -438,7 +466,7 @@ extern "C" int mrc_graph_build(int64_t n, int64_t m, const void *src, const void
         const DeviceInfo *di = nullptr;
         MRC_TRY(device_info(device, &di));
         MRC_TRY(graph_geometry(g, di));
-        g->stats.other_launches += 12;
+        { g->stats.other_launches += 12; g->stats.kernel_launches += 12; }
         if (m_out) *m_out = mk;
         if (dup_pairs) *dup_pairs = dups;
         if (removed) *removed = rem;
@@ -537,7 +565,7 @@ extern "C" int mrc_cycle_weights(mrc_graph *g, int64_t L, const int32_t *closed_
     }();
     for (void *q : {(void *)d_cyc, (void *)d_he, (void *)d_hc, (void *)d_ht}) if (q) cudaFreeAsync(q, g->stream);
     if (rc) return rc;
-    g->stats.other_launches++;
+    { g->stats.other_launches++; g->stats.kernel_launches++; }
     double sc = 0.0, st = 0.0;
     for (ll i = 0; i < L; i++) {
         if (he[i] < 0) { if (missing_hop && *missing_hop < 0) *missing_hop = (int32_t)i; continue; }
@@ -584,7 +612,7 @@ extern "C" int mrc_numeric_bounds(mrc_graph *g, double *lo, double *hi) {
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(keys, g->d_keys, 16, cudaMemcpyDeviceToHost, g->stream));
     CUDA_TRY(cudaStreamSynchronize(g->stream));
-    g->stats.other_launches++;
+    { g->stats.other_launches++; g->stats.kernel_launches++; }
     *lo = key_to_f64(keys[0]) - 1.0;   // solver.py:1022-1023
     *hi = key_to_f64(keys[1]) + 1.0;
     return MRC_OK;
@@ -620,7 +648,7 @@ extern "C" int mrc_graph_properties(mrc_graph *g, double *out) {
     CUDA_TRY(cudaMemcpyAsync(cnt, d_deg + 2 * n, sizeof cnt, cudaMemcpyDeviceToHost, g->stream));
     cudaFreeAsync(d_deg, g->stream); cudaFreeAsync(d_acc, g->stream);
     CUDA_TRY(cudaStreamSynchronize(g->stream));
-    g->stats.other_launches += 3;
+    { g->stats.other_launches += 3; g->stats.kernel_launches += 3; }
     for (int i = 0; i < 5; i++) out[i] = (double)cnt[i];
     out[5] = key_to_f64(h.keys[0]); out[6] = key_to_f64(h.keys[1]);
     out[7] = h.acc[0] / (double)m; out[8] = sqrt(h.acc[2] / (double)m);
@@ -673,7 +701,7 @@ extern "C" int mrc_graph_patch_edges(mrc_graph *g, int64_t k, const int64_t *idx
     }
     g->patches.push_back(p);
     g->pot_valid = false;
-    g->stats.other_launches++;
+    { g->stats.other_launches++; g->stats.kernel_launches++; }
     g->stats.h2d_bytes += k * 24;
     return MRC_OK;
 }
@@ -687,7 +715,7 @@ extern "C" int mrc_graph_restore(mrc_graph *g) {
                                                                               p.d_oldc, p.d_oldt);
         CUDA_TRY(cudaGetLastError());
         cudaFreeAsync(p.d_idx, g->stream); cudaFreeAsync(p.d_oldc, g->stream); cudaFreeAsync(p.d_oldt, g->stream);
-        g->stats.other_launches++;
+        { g->stats.other_launches++; g->stats.kernel_launches++; }
     }
     return MRC_OK;
 }
@@ -730,6 +758,7 @@ static void compact_args(const mrc_graph *g, int k, const RelaxArgs &ra_full, Re
 }
 static int launch_relax_args(mrc_graph *g, int kc, bool exact, const RelaxArgs &ra) {
     void *args[] = {(void *)&ra};
+    g->stats.kernel_launches++;
     const int blocks = g->relax_blocks[kt_index(kc)][exact ? 1 : 0];
     if (g->pdl && ra.gate) {   // a sweep that follows another sweep of its burst: queue it while the previous one drains
         cudaLaunchConfig_t cfg;
@@ -754,6 +783,7 @@ static int launch_relax(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_fu
 static int launch_check(mrc_graph *g, int KT, const CheckArgs &ca) {
     const int blocks = g->check_blocks[kt_index(KT)];
     void *args[] = {(void *)&ca};
+    g->stats.kernel_launches++;
     CUDA_TRY(cudaLaunchCooperativeKernel(check_fn_of(KT), dim3(blocks), dim3(256), args, 0, g->stream));
     return MRC_OK;
 }
@@ -775,7 +805,7 @@ static int ensure_sparse(mrc_graph *g) {
         if (occ < 1) return set_err(MRC_ERR_CUDA, "sparse relaxation kernel does not fit on an SM");
         g->sparse_blocks[ex] = std::min(occ, g->sparse_bps) * g->sms;
     }
-    g->stats.other_launches += 3;
+    { g->stats.other_launches += 3; g->stats.kernel_launches += 3; }
     g->sparse_ready = true;
     return MRC_OK;
 }
@@ -789,6 +819,7 @@ static int launch_sparse(mrc_graph *g, int KT, bool exact, const RelaxArgs &ra_f
     sa.bm[0] = g->d_bm[0]; sa.bm[1] = g->d_bm[1]; sa.wl[0] = g->d_wl[0]; sa.wl[1] = g->d_wl[1];
     sa.st = g->d_status; sa.first = first; sa.cidx = cidx; sa.npasses = npasses;
     void *args[] = {(void *)&sa};
+    g->stats.kernel_launches++;
     const void *fn = exact ? (const void *)relax_sparse_kernel<true> : (const void *)relax_sparse_kernel<false>;
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(g->sparse_blocks[exact ? 1 : 0]), dim3(256), args, 0, g->stream));
     return MRC_OK;
@@ -836,6 +867,7 @@ struct ProbeRun {
     int sp_in = 0, sp_ci = 0, look0 = 0, look = 0;
     int ck = -1;   // slot served from the compact column, or -1
     const void *warm_from = nullptr;   // [n] potentials every candidate starts from instead of zero (set before begin())
+    bool device_init = false;          // the persistent probe kernel initialises dist / pred itself (set before begin())
     // the burst in flight
     int nb = 0, dense_launches = 0;
     bool sparse_burst = false, do_check = false;
@@ -899,14 +931,17 @@ int ProbeRun::begin(mrc_graph *g_, bool exact_, int K_, const double *lam_, cons
     }
     { int r = 1; while (((ll)1 << r) < n + 1) r++; ca.rounds = std::min(r + 1, MRC_MAX_ROUNDS); }
 
-    if (warm_from) {
+    if (device_init) {
+    } else if (warm_from) {
         broadcast_column_kernel<<<std::min<int>((int)((n * KT + 255) / 256), 8 * g->sms), 256, 0, g->stream>>>(
             (const ull *)warm_from, (ull *)g->d_dist, KT, n);
         CUDA_TRY(cudaGetLastError());
-        g->stats.other_launches++;
+        { g->stats.other_launches++; g->stats.kernel_launches++; }
     } else CUDA_TRY(cudaMemsetAsync(g->d_dist, 0, (size_t)n * KT * 8, g->stream));   // dist = 0 (:1148 / :829)
-    CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)n * KT * 8, g->stream));   // pred = none (:1154)
-    CUDA_TRY(cudaMemsetAsync(&g->d_status->decided, 0, sizeof(unsigned), g->stream));
+    if (!device_init) {
+        CUDA_TRY(cudaMemsetAsync(g->d_pred, 0xff, (size_t)n * KT * 8, g->stream));   // pred = none (:1154)
+        CUDA_TRY(cudaMemsetAsync(&g->d_status->decided, 0, sizeof(unsigned), g->stream));
+    }
     active = (1u << K) - 1u;
     max_passes = n;   // n-1 passes + the detection pass
     passes = 0;
@@ -954,7 +989,7 @@ int ProbeRun::enqueue_burst(int cap) {
         column_copy_kernel<<<std::min<int>((int)((n + 255) / 256), 8 * g->sms), 256, 0, g->stream>>>(
             (const ull *)g->d_dist + ck, g->d_pred + ck, KT, (ull *)g->d_cdist, g->d_cpred, 1, n);
         CUDA_TRY(cudaGetLastError());
-        g->stats.other_launches++;
+        { g->stats.other_launches++; g->stats.kernel_launches++; }
     }
     CUDA_TRY(cudaMemsetAsync(g->d_status, 0, offsetof(DevStatus, cnt), g->stream));   // changed[] + examined
     CUDA_TRY(cudaEventRecord(g->ev[0], g->stream));
@@ -1042,6 +1077,7 @@ int ProbeRun::collect() {
     } else {
         g->stats.relax_launches += ran;
         g->stats.other_launches += nb - ran + (use_sparse ? 1 : 0);
+        g->stats.kernel_launches += use_sparse ? 1 : 0;   // the compaction (sweeps and check are counted where they are launched)
         if (use_sparse) {
             const ll scaled = (ll)hs.act_cnt[0] * g->sparse_div;   // size of the worklist compacted from the last sweep
             if (scaled < n) { sparse_mode = true; sp_in = 0; sp_ci = 0; }
@@ -1062,7 +1098,11 @@ int ProbeRun::collect() {
         else g->stats.relax_edge_visits += slots * m;
         g->stats.relax_edge_slots += slots * m;
     }
-    if (do_check) { g->stats.check_launches++; g->stats.false_cycles_cut += hs.cuts; }
+    if (do_check) {
+        g->stats.check_launches++; g->stats.false_cycles_cut += hs.cuts;
+        g->stats.check_doubling_ms += 1e-6 * (double)hs.ns_check[0]; g->stats.check_extract_ms += 1e-6 * (double)hs.ns_check[1];
+        g->stats.check_rounds += (int64_t)hs.check_rounds;
+    }
     g->stats.d2h_bytes += sizeof(DevStatus);
     for (int k = 0; k < K; k++) {
         if (!((active >> k) & 1u)) continue;
@@ -1132,8 +1172,74 @@ void ProbeRun::finish() {
     g->last_exact = exact; g->last_K = K;
 }
 
+/*
+ * The same probe as ONE cooperative launch (mrc_probe.cuh): the pass loop, the check schedule, narrowing, the compact
+ * survivor, the switch to worklist passes and pruning by monotonicity run on the device; the host launches, waits once
+ * and reads one result block.
+ */
+static int run_probe_persist(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
+                             unsigned flags, ProbeOut *res, const void *warm = nullptr) {
+    ProbeRun pr;
+    pr.device_init = true;
+    MRC_TRY(pr.begin(g, exact, K, lam, a, b, slack, flags, res));
+    const int KT = pr.KT;
+    if (pr.may_compact) MRC_TRY(ensure_compact(g));
+    ProbeArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.r = pr.ra;
+    pa.r.ks = KT; pa.r.k0 = 0; pa.r.active = (1u << K) - 1u;
+    pa.r.changed = nullptr; pa.r.gate = nullptr; pa.r.decided = nullptr; pa.r.act_out = nullptr;
+    pa.c = pr.ca;
+    pa.c.active = pa.r.active; pa.c.k0 = 0; pa.c.gate = nullptr;
+    pa.K = K; pa.flags = flags; pa.asc = pr.ca.prune_above; pa.max_passes = pr.max_passes;
+    pa.first_check = g->burst_init; pa.check_growth = g->check_growth; pa.check_every = g->check_every;
+    pa.may_compact = pr.may_compact ? 1 : 0;
+    pa.cdist = g->d_cdist; pa.cpred = g->d_cpred; pa.cjump = g->d_cjump;
+    pa.use_sparse = pr.use_sparse ? 1 : 0; pa.sparse_div = g->sparse_div; pa.look0 = g->sparse_look > 0 ? g->sparse_look : 2;
+    pa.out_off = g->d_out_off; pa.out_edge = g->d_out_edge;
+    pa.bm[0] = g->d_bm[0]; pa.bm[1] = g->d_bm[1]; pa.wl[0] = g->d_wl[0]; pa.wl[1] = g->d_wl[1];
+    pa.bm_words = (int)(g->bm_bytes / 4);
+    pa.warm = warm;
+    pa.out = g->d_probe;
+    const int blocks = g->probe_blocks[kt_index(KT)][exact ? 1 : 0];
+    {   // one probe per device at a time: its arguments live in the device's constant memory (c_probe)
+        std::lock_guard<std::mutex> lock(g_probe_mu[g->device]);
+        CUDA_TRY(cudaMemcpyToSymbolAsync(c_probe, &pa, sizeof pa, 0, cudaMemcpyHostToDevice, g->stream));
+        CUDA_TRY(cudaLaunchCooperativeKernel(probe_fn_of(KT, exact), dim3(blocks), dim3(MRC_RELAX_THREADS), nullptr, 0, g->stream));
+        CUDA_TRY(cudaMemcpyAsync(g->h_probe, g->d_probe, sizeof(ProbeDev), cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+    }
+    g->bm1_dirty = g->bm1_dirty || pr.use_sparse;
+    const ProbeDev &o = *g->h_probe;
+    for (int k = 0; k < K; k++) {
+        ProbeOut &r = res[k];
+        r.verdict = o.verdict[k]; r.passes = o.passes[k];
+        if (r.verdict == MRC_V_NEG || r.verdict == MRC_V_TIE) {
+            const CycleOut &c = o.cyc[k];
+            r.len = c.len; r.minv = c.minv; r.start = c.pad; r.sumc = c.sumc; r.sumt = c.sumt; r.isumc = c.isumc; r.isumt = c.isumt;
+        }
+    }
+    mrc_stats &st = g->stats;
+    for (int i = 0; i < MRC_PW; i++) { st.relax_launches += o.n_sweep[i]; st.relax_ms += 1e-6 * (double)o.ns_sweep[i]; }
+    st.crowded_sweeps += o.n_crowded; st.crowded_ms += 1e-6 * (double)o.ns_crowded;
+    st.sparse_passes += o.n_sparse; st.sparse_ms += 1e-6 * (double)o.ns_sparse;
+    st.check_launches += o.n_check; st.check_ms += 1e-6 * (double)o.ns_check;
+    st.false_cycles_cut += o.cuts;
+    st.check_doubling_ms += 1e-6 * (double)o.ns_chk_phase[0]; st.check_extract_ms += 1e-6 * (double)o.ns_chk_phase[1]; st.check_rounds += (int64_t)o.check_rounds;
+    st.relax_edge_slots += (int64_t)o.slots * g->m;
+    st.relax_edge_visits += (int64_t)o.slots * g->m + (int64_t)o.sparse_visits;
+    st.probe_launches += 1; st.probe_ms += 1e-6 * (double)o.ns_total;
+    st.kernel_launches += 1;
+    st.d2h_bytes += sizeof(ProbeDev);
+    pr.finish();
+    return MRC_OK;
+}
+
 static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
                      unsigned flags, ProbeOut *res) {
+    if (g && (g->persist == 1 ? K <= 4 : g->persist == 2 ? K == 1 : false) && K >= 1 && !g->scen_on &&
+        !(flags & (MRC_F_STOP_ON_NEG | MRC_F_PATIENCE)))
+        return run_probe_persist(g, exact, K, lam, a, b, slack, flags, res);
     ProbeRun pr;
     MRC_TRY(pr.begin(g, exact, K, lam, a, b, slack, flags, res));
     while (pr.active) {
@@ -1181,7 +1287,7 @@ static int fetch_cycle(mrc_graph *g, bool exact, int k, const ProbeOut &o, std::
         CUDA_TRY(cudaMemcpyAsync(ht.data(), g->d_g_t, (size_t)L * 8, cudaMemcpyDeviceToHost, g->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(g->stream));
-    g->stats.other_launches++;
+    { g->stats.other_launches++; g->stats.kernel_launches++; }
     g->stats.d2h_bytes += L * 20;
     // The device recorded the BACKWARD walk from `start`: b_0 = start, b_{j+1} = src(e_j), b_L = start, edge e_j
     // runs b_{j+1} -> b_j.  Forward cycle: f_i = b_{L-i}, forward edge i = e_{L-1-i}.  Rotate it so that it starts
@@ -1404,7 +1510,9 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "narrow") g->narrow = value != 0;
     else if (s == "compact") g->compact = value != 0;
     else if (s == "compact_min_edges") g->compact_min_edges = std::max(0, value);
-    else if (s == "lookahead") g->lookahead = value != 0;
+    else if (s == "persist") g->persist = std::max(0, std::min(2, value));
+    else if (s == "qstart") g->qstart = value != 0;
+    else if (s == "qstart_min_edges") g->qstart_min_edges = std::max(0, value);
     else if (s == "check_every") g->check_every = std::max(0, value);
     else if (s == "check_growth") g->check_growth = std::max(0, value);
     else if (s == "pdl") g->pdl = value != 0;
@@ -1431,6 +1539,56 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
 }
 
 // ------------------------------------------------------------------------------- numeric lambda search
+// Where the first round looks.  The reference starts from [min c/t - 1, max c/t + 1] (solver.py:1019-1023) and halves it;
+// uniform candidates over that bracket spend the first rounds far from lambda*: the minimum cycle ratio is a weighted mean of
+// edge ratios and, with many cycles to choose from, sits in the low tail of their distribution (C3: the 2.5 % quantile of
+// c/t, while the bracket's midpoint is near the 60 % quantile).  So the first round's candidates are low QUANTILES of a
+// sample of the edge ratios -- uniform in probability mass, not in value.  Any lambda in (lo, hi) is a legitimate candidate;
+// the rounds after the first are the usual ones (mrc_plan), so a graph whose optimum is not in the tail loses one round.
+__global__ void ratio_sample_kernel(const double *cost, const double *time, ll m, int S, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S) {
+        const ll e = (ll)(((double)i + 0.5) * (double)m / (double)S);
+        out[i] = __ddiv_rn(cost[e], time[e]);
+    }
+}
+static int ensure_qsample(mrc_graph *g) {
+    if (!g->qsample.empty()) return MRC_OK;
+    const int S = (int)std::min<ll>(g->m, 2048);
+    double *d = nullptr;
+    DALLOC(d, (size_t)S * 8);
+    std::vector<double> h((size_t)S);
+    ratio_sample_kernel<<<(S + 255) / 256, 256, 0, g->stream>>>(g->d_cost, g->d_time, g->m, S, d);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h.data(), d, (size_t)S * 8, cudaMemcpyDeviceToHost, g->stream));
+    cudaFreeAsync(d, g->stream);
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    { g->stats.other_launches++; g->stats.kernel_launches++; }
+    g->stats.d2h_bytes += (int64_t)S * 8;
+    std::sort(h.begin(), h.end());
+    g->qsample.swap(h);
+    return MRC_OK;
+}
+// quantile levels of a first round of K candidates: a geometric ladder from q_lo to q_hi (K = 4: 1 %, 2.9 %, 8.5 %, 25 %)
+static void first_round_levels(int K, double *q) {
+    if (K == 1) { q[0] = 0.05; return; }
+    const double q_lo = K == 2 ? 0.02 : K <= 4 ? 0.01 : K <= 8 ? 0.005 : 0.002, q_hi = K == 2 ? 0.10 : K <= 4 ? 0.25 : 0.5;
+    for (int j = 0; j < K; j++) q[j] = q_lo * std::pow(q_hi / q_lo, (double)j / (double)(K - 1));
+}
+// K candidates for the first round of a search over (lo, hi) without a known cycle; false = use the uniform plan
+static bool plan_first_round(mrc_graph *g, double lo, double hi, int K, double *lam) {
+    if (!g->qstart || g->m < g->qstart_min_edges || K < 1) return false;
+    if (ensure_qsample(g) != MRC_OK) return false;
+    std::vector<double> q((size_t)K);
+    first_round_levels(K, q.data());
+    const size_t S = g->qsample.size();
+    for (int j = 0; j < K; j++) {
+        lam[j] = g->qsample[std::min(S - 1, (size_t)(q[j] * (double)(S - 1)))];
+        if (!(lam[j] > lo && lam[j] < hi) || (j > 0 && !(lam[j] > lam[j - 1]))) return false;   // ties / outside the bracket
+    }
+    return true;
+}
+
 extern "C" int mrc_plan_candidates(double lo, double hi, int have_cycle, double tol, int K_total, double *lam_out) {
     if (!lam_out || K_total < 1) return set_err(MRC_ERR_ARG, "bad plan arguments");
     mrc_plan(lo, hi, have_cycle, tol, K_total, lam_out);
@@ -1469,7 +1627,7 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
         }
         iters++;
         g->stats.rounds++;
-        MRC_TRY(mrc_plan_candidates(lo, hi, have_cycle, tol, K, lam));
+        if (!(i == 0 && !have_cycle && plan_first_round(g, lo, hi, K, lam))) MRC_TRY(mrc_plan_candidates(lo, hi, have_cycle, tol, K, lam));
         // Option "stop_on_neg": intermediate rounds only need a better cycle, so a round may end at the first
         // check (from pass 6 on) that verified one, leaving the slow non-negative candidates undecided; the round in
         // which nothing is negative still runs to convergence and proves the lower end.
@@ -1560,7 +1718,7 @@ static int tight_mask_device(mrc_graph *g, ll a, ll b, bool *ok) {
     tight_mask_kernel<<<blocks, 256, 0, g->stream>>>(g->d_src, g->d_dst, g->d_icost, g->d_itime, (const ll *)g->d_dist,
                                                      a, b, g->m, g->d_mask);
     CUDA_TRY(cudaGetLastError());
-    g->stats.other_launches++;
+    { g->stats.other_launches++; g->stats.kernel_launches++; }
     return MRC_OK;
 }
 

@@ -332,7 +332,8 @@ static int shard_solve_rank(mrc_comm *c, mrc_graph *g, double lo, double hi, int
         if (!running && !exhausted) {
             if (rounds >= max_iter) exhausted = true;
             else {
-                mrc_plan(lo, hi, have_cycle, tol, KT_all, plan.data());
+                if (!(rounds == 0 && !have_cycle && plan_first_round(g, lo, hi, KT_all, plan.data())))   // same sample, same plan on every replica
+                    mrc_plan(lo, hi, have_cycle, tol, KT_all, plan.data());
                 const double *mine = plan.data() + (size_t)me * K;
                 int Kp = K;
                 // With a cycle in hand the plan's last candidate is its certifier -- the one probe that can end the
@@ -379,6 +380,7 @@ static int shard_solve_rank(mrc_comm *c, mrc_graph *g, double lo, double hi, int
         CUDA_TRY(cudaStreamSynchronize(g->stream));
         ticks++;
         g->stats.other_launches += running ? 1 : 0;
+        g->stats.kernel_launches += running ? 1 : 0;
         g->stats.d2h_bytes += (int64_t)per * 8 * W;
         if (running) MRC_TRY(pr.collect());
         // keep my host copy of the records in step with what the device sent (decided candidates stay decided)

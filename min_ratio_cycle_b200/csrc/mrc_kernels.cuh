@@ -81,6 +81,8 @@ struct CycleOut {
 struct DevStatus {
     unsigned changed[MRC_MAX_BURST];
     ull examined;                              // worklist passes: edges relaxed (cleared with `changed`)
+    ull ns_check[2];                           // cycle check, globaltimer of thread 0: jump init + pointer doubling, extraction (cleared with `changed`)
+    ull check_rounds;                          // ... doubling rounds run
     unsigned cnt[MRC_MAX_ROUNDS * MRC_KMAX];   // live vertices per doubling round and candidate
     int minlive[MRC_MAX_ROUNDS * MRC_KMAX];    // smallest live vertex per doubling round and candidate
     unsigned cyc_mask, rounds_run, pend, cuts;
@@ -166,11 +168,38 @@ template <> struct DistVec<4> {
 // (:1161).  dist <= 0 always (starts at +0.0, only decreases), so for negative doubles
 // "smaller value" == "larger bit pattern": atomicMax on the raw bits is a 64-bit atomic min.
 // exact: w = b*icost - a*itime in int64 (solver.py:799-800), strict < without slack (:833).
-__device__ __forceinline__ double mrc_cand(const RelaxArgs &p, int k, double du, double c, double t) {
-    return __dadd_rn(du, __dsub_rn(c, __dmul_rn(p.lam[k], t)));
+// Where a sweep finds its candidates and its dist / pred columns.  ParamView: straight from the kernel parameters
+// (constant-bank operands, no registers) -- every launch whose host picked the columns.  RegView<K>: a narrower set of
+// columns picked ON THE DEVICE by the persistent probe kernel (mrc_probe.cuh); its few lambdas live in registers.
+struct ParamView {
+    const RelaxArgs &p;
+    __device__ __forceinline__ double lam(int k) const { return p.lam[k]; }
+    __device__ __forceinline__ ll a(int k) const { return p.a[k]; }
+    __device__ __forceinline__ ll b(int k) const { return p.b[k]; }
+    __device__ __forceinline__ void *dist() const { return p.dist; }
+    __device__ __forceinline__ ull *pred() const { return p.pred; }
+    __device__ __forceinline__ int ks() const { return p.ks; }
+    __device__ __forceinline__ int k0() const { return p.k0; }
+};
+template <int K> struct RegView {
+    double lam_[K];
+    ll a_[K], b_[K];
+    void *dist_;
+    ull *pred_;
+    int ks_, k0_;
+    __device__ __forceinline__ double lam(int k) const { return lam_[k]; }
+    __device__ __forceinline__ ll a(int k) const { return a_[k]; }
+    __device__ __forceinline__ ll b(int k) const { return b_[k]; }
+    __device__ __forceinline__ void *dist() const { return dist_; }
+    __device__ __forceinline__ ull *pred() const { return pred_; }
+    __device__ __forceinline__ int ks() const { return ks_; }
+    __device__ __forceinline__ int k0() const { return k0_; }
+};
+template <typename V> __device__ __forceinline__ double mrc_cand(const V &vw, int k, double du, double c, double t) {
+    return __dadd_rn(du, __dsub_rn(c, __dmul_rn(vw.lam(k), t)));
 }
-__device__ __forceinline__ ll mrc_cand(const RelaxArgs &p, int k, ll du, ll c, ll t) {
-    return du + (p.b[k] * c - p.a[k] * t);
+template <typename V> __device__ __forceinline__ ll mrc_cand(const V &vw, int k, ll du, ll c, ll t) {
+    return du + (vw.b(k) * c - vw.a(k) * t);
 }
 // scenario batching: candidate k re-solves the graph with ONE edge perturbed (sensitivity_analysis, solver.py:1716-1721)
 __device__ __forceinline__ void mrc_scenario_patch(const RelaxArgs &p, int k, int e, double &c, double &t) {
@@ -246,28 +275,29 @@ __device__ __forceinline__ bool mrc_pick_winner(bool imp, ll cand, const RowRuns
 // The row is warp-synchronous: every lane calls it (valid == false for lanes past the end).  Steady state (nothing
 // improves, almost every row after the first passes): two gathers, 4 flops + one compare per candidate, ONE vote.
 // Control flow never waits for an atomic's return value before all atomics of the row are in flight.
-template <int K, typename T, bool SCEN>
-__device__ __forceinline__ void relax_row(const RelaxArgs &p, unsigned act, bool valid, int lane, unsigned e, int u, int v,
+template <int K, typename T, bool SCEN, typename V>
+__device__ __forceinline__ void relax_row(const RelaxArgs &p, const V &vw, unsigned act, bool valid, int lane, unsigned e, int u, int v,
                                           T c, T t, unsigned &chg, unsigned *act_out) {
     // K = 8 is processed as two halves of 4 candidates (two 256-bit gathers from the same 64-B group, one after
     // the other), so its register footprint stays that of K = 4.
     constexpr int H = K > 4 ? 4 : K;
-    T *dist = static_cast<T *>(p.dist);
+    T *dist = static_cast<T *>(vw.dist());
+    const int ks = vw.ks();
 #pragma unroll
     for (int h = 0; h < K; h += H) {
         const unsigned acth = (act >> h) & ((1u << H) - 1u);
         if (!acth) continue;   // warp-uniform: nothing active in this half
         T du[H], dv[H], cand[H];
         if (valid) {
-            DistVec<H>::load(du, dist + (size_t)u * p.ks + h);
-            DistVec<H>::load(dv, dist + (size_t)v * p.ks + h);
+            DistVec<H>::load(du, dist + (size_t)u * ks + h);
+            DistVec<H>::load(dv, dist + (size_t)v * ks + h);
         }
         bool imp[H], any = false;
 #pragma unroll
         for (int k = 0; k < H; k++) {
             T ck = c, tk = t;
             if (SCEN) mrc_scenario_patch(p, h + k, (int)e, ck, tk);
-            cand[k] = mrc_cand(p, h + k, du[k], ck, tk);
+            cand[k] = mrc_cand(vw, h + k, du[k], ck, tk);
             imp[k] = valid && ((acth >> k) & 1u) && mrc_improves(p, cand[k], dv[k]);
             any |= imp[k];
         }
@@ -286,12 +316,12 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, unsigned act, bool
         T old[H];
 #pragma unroll
         for (int k = 0; k < H; k++)
-            if ((wins >> k) & 1u) old[k] = mrc_atomic_min(dist + (size_t)v * p.ks + h + k, cand[k]);
+            if ((wins >> k) & 1u) old[k] = mrc_atomic_min(dist + (size_t)v * ks + h + k, cand[k]);
         bool lowered = false;
 #pragma unroll
         for (int k = 0; k < H; k++)
             if (((wins >> k) & 1u) && mrc_lowered(old[k], cand[k])) {
-                __stcg(p.pred + (size_t)v * p.ks + h + k, ((ull)(unsigned)u << 32) | e);
+                __stcg(vw.pred() + (size_t)v * ks + h + k, ((ull)(unsigned)u << 32) | e);
                 chg |= 1u << (h + k);
                 lowered = true;
             }
@@ -327,10 +357,19 @@ template <int K> struct RelaxTune {
     // resolution (B200, C3: K=1 -8 % per steady pass; K=4 pass 1 157 -> 116 us, pass 2 103 -> 80, steady 60 -> 58);
     // at K = 8 (two halves) the extra registers cost more than the overlap wins (101 -> 120 us)
     static constexpr bool prefetch = MRC_TUNE_PF;
+    // MRC_TUNE_L2PF (experiments): without the register double buffer, one prefetch.global.L2 per warp step pulls the lines
+    // of the warp's next chunk into L2 (12 lines of 128 B, one per lane) -- costs no registers
+#ifndef MRC_TUNE_L2PF
+#define MRC_TUNE_L2PF 0
+#endif
+    static constexpr int l2pf = MRC_TUNE_L2PF;   // chunks ahead (0 = off)
 };
 // One sweep over the edge stream for the candidates in `act`; ORs "candidate k lowered something" into *changed.
-template <int K, bool EXACT, bool SCEN>
-__device__ __forceinline__ void relax_sweep(const RelaxArgs &p, unsigned act, unsigned *changed, unsigned *act_out) {
+// PF: 1 = register double buffer of the edge stream (the stand-alone kernels, K <= 4), 0 = none, 2 = none + one
+// prefetch.global.L2 per warp step for the lines of the warp's next chunk (the persistent probe kernel, whose sweeps are
+// called through the ABI and cannot afford the 12 registers of the double buffer)
+template <int K, bool EXACT, bool SCEN, typename V, int PF = (RelaxTune<K>::prefetch ? 1 : (RelaxTune<K>::l2pf > 0 ? 2 : 0))>
+__device__ __forceinline__ void relax_sweep(const RelaxArgs &p, const V &vw, unsigned act, unsigned *changed, unsigned *act_out) {
     typedef typename WeightT<EXACT>::type W;
     const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
     const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
@@ -347,13 +386,24 @@ __device__ __forceinline__ void relax_sweep(const RelaxArgs &p, unsigned act, un
         for (int j = 0; j < ROWS; j++) {
             const unsigned e = c * CH + 32 * j + lane;
             const bool ok = e < m;
-            relax_row<K, W, SCEN>(p, act, ok, lane, e, ok ? p.src[e] : 0, ok ? p.dst[e] : 0, ok ? cost[e] : W(0),
+            relax_row<K, W, SCEN>(p, vw, act, ok, lane, e, ok ? p.src[e] : 0, ok ? p.dst[e] : 0, ok ? cost[e] : W(0),
                                   ok ? time[e] : W(0), chg, act_out);
         }
     };
-    if constexpr (!RelaxTune<K>::prefetch) {
+    if constexpr (PF != 1) {
         for (unsigned c = warp; c < nchunks; c += nwarps) {
             if (c >= nfull) { tail(c); break; }
+            if constexpr (PF == 2) {
+                const unsigned nx = c + (RelaxTune<K>::l2pf > 0 ? RelaxTune<K>::l2pf : 1) * nwarps;
+                constexpr int L4 = CH * 4 / 128, L8 = CH * 8 / 128;   // lines of a chunk per int / f64 array
+                if (nx < nfull && lane < 2 * L4 + 2 * L8) {
+                    const char *a = lane < L4            ? (const char *)(p.src + (size_t)nx * CH) + lane * 128
+                                    : lane < 2 * L4      ? (const char *)(p.dst + (size_t)nx * CH) + (lane - L4) * 128
+                                    : lane < 2 * L4 + L8 ? (const char *)(cost + (size_t)nx * CH) + (lane - 2 * L4) * 128
+                                                         : (const char *)(time + (size_t)nx * CH) + (lane - 2 * L4 - L8) * 128;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                }
+            }
             const unsigned e0 = c * CH + lane;
             int s[ROWS], d[ROWS];
             W cs[ROWS], tm[ROWS];
@@ -365,7 +415,7 @@ __device__ __forceinline__ void relax_sweep(const RelaxArgs &p, unsigned act, un
             }
 #pragma unroll
             for (int j = 0; j < ROWS; j++)
-                relax_row<K, W, SCEN>(p, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg, act_out);
+                relax_row<K, W, SCEN>(p, vw, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg, act_out);
         }
     } else {
         int s[ROWS], d[ROWS], s2[ROWS], d2[ROWS];
@@ -395,7 +445,7 @@ __device__ __forceinline__ void relax_sweep(const RelaxArgs &p, unsigned act, un
             const unsigned e0 = c * CH + lane;
 #pragma unroll
             for (int j = 0; j < ROWS; j++)
-                relax_row<K, W, SCEN>(p, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg, act_out);
+                relax_row<K, W, SCEN>(p, vw, act, true, lane, e0 + 32 * j, s[j], d[j], cs[j], tm[j], chg, act_out);
 #pragma unroll
             for (int j = 0; j < ROWS; j++) { s[j] = s2[j]; d[j] = d2[j]; cs[j] = cs2[j]; tm[j] = tm2[j]; }
             c = nx;
@@ -403,7 +453,7 @@ __device__ __forceinline__ void relax_sweep(const RelaxArgs &p, unsigned act, un
     }
     // changed flag: warp vote, one atomic per warp at most
     chg = __reduce_or_sync(MRC_FULL, chg);
-    if (lane == 0 && chg) atomicOr(changed, chg << p.k0);
+    if (lane == 0 && chg) atomicOr(changed, chg << vw.k0());
 }
 
 template <int K, bool EXACT, bool SCEN>
@@ -418,7 +468,7 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, RelaxTune<K>::minblocks) re
     if (p.decided) act &= ~(__ldcg(p.decided) >> p.k0);
     if (p.gate) act &= __ldcg(p.gate) >> p.k0;
     if (!act) return;
-    relax_sweep<K, EXACT, SCEN>(p, act, p.changed, p.act_out);
+    relax_sweep<K, EXACT, SCEN>(p, ParamView{p}, act, p.changed, p.act_out);
 }
 
 // dist[v][0..ks) = base[v] for every vertex: a probe that starts from the converged potentials of a neighbouring
@@ -476,64 +526,77 @@ __global__ void compact_active_kernel(const unsigned *bm, int words, int *wl, De
     }
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(256) relax_sparse_kernel(const __grid_constant__ SparseArgs a) {
+// One worklist pass: the out-edges of the `cin` vertices of wl_in; vertices it lowers are appended to wl_out (counted in
+// st->act_cnt[co], deduplicated through bm_out).  Called by every thread of a cooperative grid; the caller grid-syncs.
+template <bool EXACT, typename V>
+__device__ __forceinline__ void sparse_pass_device(const RelaxArgs &p, const V &vw, int kc, unsigned active, const int *out_off,
+                                                   const int *out_edge, const int *wl_in, int *wl_out, unsigned *bm_in,
+                                                   unsigned *bm_out, DevStatus *st, unsigned cin, int co, unsigned *changed) {
     typedef typename WeightT<EXACT>::type W;
-    cg::grid_group grid = cg::this_grid();
-    const RelaxArgs &p = a.r;
     const W *cost = EXACT ? reinterpret_cast<const W *>(p.icost) : reinterpret_cast<const W *>(p.cost);
     const W *time = EXACT ? reinterpret_cast<const W *>(p.itime) : reinterpret_cast<const W *>(p.time);
-    W *dist = static_cast<W *>(p.dist);
-    DevStatus *st = a.st;
+    W *dist = static_cast<W *>(vw.dist());
+    ull *pred = vw.pred();
+    const int ks = vw.ks();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = tid & 7;                                   // 8 lanes share one worklist vertex
     const int grp = tid >> 3, ngrp = (gridDim.x * blockDim.x) >> 3;
+    unsigned chg = 0, seen = 0;
+    for (unsigned i = grp; i < cin; i += ngrp) {
+        const int u = __ldcg(wl_in + i);
+        if (sub == 0) atomicAnd(bm_in + (u >> 5), ~(1u << (u & 31)));   // leave the bitmap clean for its next use
+        W du[MRC_KMAX];
+#pragma unroll
+        for (int k = 0; k < MRC_KMAX; k++)
+            du[k] = (k < kc && ((active >> k) & 1u)) ? __ldcg(dist + (size_t)u * ks + k) : W(0);
+        const int beg = __ldg(out_off + u), end = __ldg(out_off + u + 1);
+        for (int j = beg + sub; j < end; j += 8) {
+            const int e = __ldg(out_edge + j);
+            const int v = __ldg(p.dst + e);
+            const W c = __ldg(cost + e), t = __ldg(time + e);
+            seen++;
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < MRC_KMAX; k++) {
+                if (k >= kc || !((active >> k) & 1u)) continue;
+                W ck = c, tk = t;
+                mrc_scenario_patch(p, k, e, ck, tk);
+                const W cand = mrc_cand(vw, k, du[k], ck, tk);
+                const W dv = __ldcg(dist + (size_t)v * ks + k);
+                if (mrc_improves(p, cand, dv) && mrc_atomic_lower(dist + (size_t)v * ks + k, cand)) {
+                    __stcg(pred + (size_t)v * ks + k, ((ull)(unsigned)u << 32) | (unsigned)e);
+                    chg |= 1u << k;
+                    any = true;
+                }
+            }
+            if (any) {
+                const unsigned bit = 1u << (v & 31);
+                if (!(atomicOr(bm_out + (v >> 5), bit) & bit)) wl_out[atomicAdd(&st->act_cnt[co], 1u)] = v;
+            }
+        }
+    }
+    chg = __reduce_or_sync(0xffffffffu, chg);
+    seen = __reduce_add_sync(0xffffffffu, seen);
+    if ((threadIdx.x & 31) == 0) {
+        if (chg) atomicOr(changed, chg << vw.k0());
+        if (seen) atomicAdd(p.examined, (ull)seen);
+    }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256) relax_sparse_kernel(const __grid_constant__ SparseArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const RelaxArgs &p = a.r;
+    DevStatus *st = a.st;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     int in = a.first, ci = a.cidx;
     for (int pass = 0; pass < a.npasses; pass++) {
         const int out = in ^ 1, co = ci == 2 ? 0 : ci + 1, cz = co == 2 ? 0 : co + 1;
         const unsigned cin = __ldcg(&st->act_cnt[ci]);          // final since the previous grid sync
         if (cin == 0) break;                                    // grid-uniform: fixed point
         if (tid == 0) st->act_cnt[cz] = 0;                      // next pass appends there; last read one pass ago
-        unsigned chg = 0, seen = 0;
-        for (unsigned i = grp; i < cin; i += ngrp) {
-            const int u = __ldcg(a.wl[in] + i);
-            if (sub == 0) atomicAnd(a.bm[in] + (u >> 5), ~(1u << (u & 31)));   // leave the bitmap clean for its next use
-            W du[MRC_KMAX];
-#pragma unroll
-            for (int k = 0; k < MRC_KMAX; k++)
-                du[k] = (k < a.kc && ((p.active >> k) & 1u)) ? __ldcg(dist + (size_t)u * p.ks + k) : W(0);
-            const int beg = __ldg(a.out_off + u), end = __ldg(a.out_off + u + 1);
-            for (int j = beg + sub; j < end; j += 8) {
-                const int e = __ldg(a.out_edge + j);
-                const int v = __ldg(p.dst + e);
-                const W c = __ldg(cost + e), t = __ldg(time + e);
-                seen++;
-                bool any = false;
-#pragma unroll
-                for (int k = 0; k < MRC_KMAX; k++) {
-                    if (k >= a.kc || !((p.active >> k) & 1u)) continue;
-                    W ck = c, tk = t;
-                    mrc_scenario_patch(p, k, e, ck, tk);
-                    const W cand = mrc_cand(p, k, du[k], ck, tk);
-                    const W dv = __ldcg(dist + (size_t)v * p.ks + k);
-                    if (mrc_improves(p, cand, dv) && mrc_atomic_lower(dist + (size_t)v * p.ks + k, cand)) {
-                        __stcg(p.pred + (size_t)v * p.ks + k, ((ull)(unsigned)u << 32) | (unsigned)e);
-                        chg |= 1u << k;
-                        any = true;
-                    }
-                }
-                if (any) {
-                    const unsigned bit = 1u << (v & 31);
-                    if (!(atomicOr(a.bm[out] + (v >> 5), bit) & bit)) a.wl[out][atomicAdd(&st->act_cnt[co], 1u)] = v;
-                }
-            }
-        }
-        chg = __reduce_or_sync(0xffffffffu, chg);
-        seen = __reduce_add_sync(0xffffffffu, seen);
-        if ((threadIdx.x & 31) == 0) {
-            if (chg) atomicOr(p.changed + pass, chg << p.k0);
-            if (seen) atomicAdd(p.examined, (ull)seen);
-        }
+        sparse_pass_device<EXACT>(p, ParamView{p}, a.kc, p.active, a.out_off, a.out_edge, a.wl[in], a.wl[out], a.bm[in], a.bm[out],
+                                  st, cin, co, p.changed + pass);
         grid.sync();
         in = out; ci = co;
     }
@@ -555,9 +618,167 @@ __global__ void __launch_bounds__(256) relax_sparse_kernel(const __grid_constant
 #define MRC_MAX_EXTRACT 6
 #define MRC_CYC_NEG 1
 #define MRC_CYC_TIE 2
-template <int K>
-__global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant__ CheckArgs p) {
-    cg::grid_group grid = cg::this_grid();
+// ---- pieces of the check
+template <int K, typename CV> __device__ __forceinline__ int cycle_step(const CV &cv, int k, int y) {
+    return y < 0 ? -1 : (int)(__ldcg(cv.pred() + (ll)y * K + k) >> 32);
+}
+// one lap over pred from y, recording the edge list; returns the vertex it stopped at
+template <int K, typename CV> __device__ __forceinline__ int cycle_lap(const CheckArgs &p, const CV &cv, int k, int y, ll cap, ll &len) {
+    int cur = y;
+    ll i = 0;
+    do {
+        const ull pe = __ldcg(cv.pred() + (ll)cur * K + k);
+        if (i < p.cap) cv.cyc_edges()[(ll)k * p.cap + i] = (int)(unsigned)pe;
+        cur = (int)(pe >> 32);
+        i++;
+    } while (cur != y && cur >= 0 && i < cap);
+    len = i;
+    return cur;
+}
+// The whole CTA: sums, smallest vertex and max |dist| over the recorded lap of candidate k (x = vertex the lap started from,
+// -1 = none), then thread 0 tests it against lambda: negative -> reported in st->out[k] (+ decided bit); rounding artefact ->
+// TIE; otherwise the cycle is false: pred of its smallest vertex is reset and its vertices are marked dead
+// in jump.  Returns (thread 0) whether candidate k is settled for this check.
+template <int K, typename CV>
+__device__ __forceinline__ bool cycle_verify_block(const CheckArgs &p, const CV &cv, int k, int x, int len, bool mark_jump) {
+    __shared__ double s_d[3][8];
+    __shared__ ll s_l[2][8];
+    __shared__ int s_m[8];
+    DevStatus *st = p.st;
+    bool settled = true;   // nothing left to examine for k unless a false cycle is cut below
+    if (x < 0) return settled;   // block-uniform: no representative left, or the chain broke while we walked
+    double sc = 0.0, stt = 0.0, mabs = 0.0;
+    ll isc = 0, ist = 0;
+    int minv = 0x7fffffff;
+    __threadfence_block();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        const int e = __ldcg(cv.cyc_edges() + (ll)k * p.cap + i);
+        const int u = __ldg(p.src + e);
+        minv = u < minv ? u : minv;
+        if (p.exact) { isc += __ldg(p.icost + e); ist += __ldg(p.itime + e); }
+        else {
+            double ce = __ldg(p.cost + e), te = __ldg(p.time + e);
+            cv.scenario_patch(k, e, ce, te);
+            sc += ce; stt += te;
+            mabs = fmax(mabs, fabs(__ldcg(static_cast<const double *>(cv.dist()) + (ll)u * K + k)));
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        sc += __shfl_down_sync(0xffffffffu, sc, o); stt += __shfl_down_sync(0xffffffffu, stt, o);
+        mabs = fmax(mabs, __shfl_down_sync(0xffffffffu, mabs, o));
+        isc += __shfl_down_sync(0xffffffffu, isc, o); ist += __shfl_down_sync(0xffffffffu, ist, o);
+        const int mo = __shfl_down_sync(0xffffffffu, minv, o);
+        minv = mo < minv ? mo : minv;
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_d[0][w] = sc; s_d[1][w] = stt; s_d[2][w] = mabs; s_l[0][w] = isc; s_l[1][w] = ist; s_m[w] = minv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sc = 0.0; stt = 0.0; mabs = 0.0; isc = 0; ist = 0; minv = 0x7fffffff;
+        for (int j = 0; j < (int)(blockDim.x >> 5); j++) {
+            sc += s_d[0][j]; stt += s_d[1][j]; mabs = fmax(mabs, s_d[2][j]);
+            isc += s_l[0][j]; ist += s_l[1][j]; minv = s_m[j] < minv ? s_m[j] : minv;
+        }
+        int kind = 0;
+        if (p.exact) {
+            if ((__int128)cv.b(k) * isc - (__int128)cv.a(k) * ist < 0) kind = MRC_CYC_NEG;
+        } else if (stt > 0) {
+            // r < lambda: negative.  r >= lambda but (r - lambda)*T inside the rounding noise of the
+            // walk (len * eps * max|dist|, x8): a rounding artefact that would relax forever -> TIE.
+            const double rr = sc / stt;
+            if (rr < cv.lam(k)) kind = MRC_CYC_NEG;
+            else if ((rr - cv.lam(k)) * stt <= 8.0 * (double)len * 2.220446049250313e-16 * mabs) kind = MRC_CYC_TIE;
+        }
+        if (kind) {
+            CycleOut o;
+            o.found = kind; o.len = len; o.minv = minv; o.pad = x;   // pad = vertex the recorded walk starts from
+            o.sumc = sc; o.sumt = stt; o.maxabs = mabs; o.isumc = isc; o.isumt = ist;
+            st->out[k] = o;
+            atomicOr(&st->decided, 1u << (k + cv.k0()));   // relaxation launches already enqueued skip this candidate
+        } else {
+            // false cycle: cut it for good (and mark its vertices dead for this launch of the doubling check)
+            if (mark_jump) {
+                int cur = minv;
+                ll g = 0;
+                do {
+                    const int nxt = cycle_step<K>(cv, k, cur);
+                    __stcg(cv.jump() + (ll)cur * K + k, -2);
+                    cur = nxt;
+                    g++;
+                } while (cur != minv && cur >= 0 && g <= p.n);
+            }
+            __stcg(cv.pred() + (ll)minv * K + k, ~0ull);
+            atomicAdd(&st->cuts, 1u);
+            settled = false;
+        }
+    }
+    __syncthreads();   // the shared arrays may be reused by the caller's next candidate
+    return settled;
+}
+
+// Body of the check: every thread of a cooperative grid calls it (grid-uniform control flow); returns the mask of candidates
+// whose predecessor graph held a cycle (results in st->out[], st->cyc_mask).  Shared by cycle_check_kernel and the
+// persistent probe kernel (mrc_probe.cuh).
+// Where a check finds its predecessor graph and its candidates: CheckParamView = the kernel parameters (host picked the
+// columns), CheckRegView = the compact survivor column picked on the device by the persistent probe kernel.
+struct CheckParamView {
+    const CheckArgs &p;
+    __device__ __forceinline__ ull *pred() const { return p.pred; }
+    __device__ __forceinline__ const void *dist() const { return p.dist; }
+    __device__ __forceinline__ int *jump() const { return p.jump; }
+    __device__ __forceinline__ int *cyc_edges() const { return p.cyc_edges; }
+    __device__ __forceinline__ unsigned active() const { return p.active; }
+    __device__ __forceinline__ const unsigned *gate() const { return p.gate; }
+    __device__ __forceinline__ int k0() const { return p.k0; }
+    __device__ __forceinline__ int prune_above() const { return p.prune_above; }
+    __device__ __forceinline__ double lam(int k) const { return p.lam[k]; }
+    __device__ __forceinline__ ll a(int k) const { return p.a[k]; }
+    __device__ __forceinline__ ll b(int k) const { return p.b[k]; }
+    __device__ __forceinline__ void scenario_patch(int k, int e, double &ce, double &te) const {
+        if (p.scen && e == p.pe[k]) { ce = __dadd_rn(ce, p.pdc[k]); te = __dadd_rn(te, p.pdt[k]); }
+    }
+};
+struct CheckActiveView {   // the kernel parameters, but only the candidates in active_ (a mask read or kept on the device)
+    const CheckArgs &p;
+    unsigned active_;
+    __device__ __forceinline__ ull *pred() const { return p.pred; }
+    __device__ __forceinline__ const void *dist() const { return p.dist; }
+    __device__ __forceinline__ int *jump() const { return p.jump; }
+    __device__ __forceinline__ int *cyc_edges() const { return p.cyc_edges; }
+    __device__ __forceinline__ unsigned active() const { return active_; }
+    __device__ __forceinline__ const unsigned *gate() const { return nullptr; }
+    __device__ __forceinline__ int k0() const { return p.k0; }
+    __device__ __forceinline__ int prune_above() const { return p.prune_above; }
+    __device__ __forceinline__ double lam(int k) const { return p.lam[k]; }
+    __device__ __forceinline__ ll a(int k) const { return p.a[k]; }
+    __device__ __forceinline__ ll b(int k) const { return p.b[k]; }
+    __device__ __forceinline__ void scenario_patch(int k, int e, double &ce, double &te) const {
+        if (p.scen && e == p.pe[k]) { ce = __dadd_rn(ce, p.pdc[k]); te = __dadd_rn(te, p.pdt[k]); }
+    }
+};
+struct CheckRegView {   // one candidate (K = 1), results in slot 0
+    ull *pred_;
+    const void *dist_;
+    int *jump_, *cyc_edges_;
+    unsigned active_;
+    int k0_, prune_;
+    double lam_;
+    ll a_, b_;
+    __device__ __forceinline__ ull *pred() const { return pred_; }
+    __device__ __forceinline__ const void *dist() const { return dist_; }
+    __device__ __forceinline__ int *jump() const { return jump_; }
+    __device__ __forceinline__ int *cyc_edges() const { return cyc_edges_; }
+    __device__ __forceinline__ unsigned active() const { return active_; }
+    __device__ __forceinline__ const unsigned *gate() const { return nullptr; }
+    __device__ __forceinline__ int k0() const { return k0_; }
+    __device__ __forceinline__ int prune_above() const { return prune_; }
+    __device__ __forceinline__ double lam(int) const { return lam_; }
+    __device__ __forceinline__ ll a(int) const { return a_; }
+    __device__ __forceinline__ ll b(int) const { return b_; }
+    __device__ __forceinline__ void scenario_patch(int, int, double &, double &) const {}
+};
+template <int K, typename CV>
+__device__ __forceinline__ unsigned cycle_check_device(const CheckArgs &p, const CV &cv, cg::grid_group &grid) {
     const ll total = p.n * K;
     const ll tid0 = (ll)blockIdx.x * blockDim.x + threadIdx.x;
     const ll stride = (ll)gridDim.x * blockDim.x;
@@ -566,22 +787,24 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < MRC_MAX_ROUNDS * MRC_KMAX; i += blockDim.x) { st->cnt[i] = 0; st->minlive[i] = 0x7fffffff; }
     if (blockIdx.x == 0 && threadIdx.x < MRC_KMAX * MRC_MAX_EXTRACT) st->rep[threadIdx.x] = 0x7fffffff;
-    if (blockIdx.x == 0 && threadIdx.x < MRC_KMAX) {
+    const unsigned active = cv.gate() ? (cv.active() & (__ldcg(cv.gate()) >> cv.k0())) : cv.active();
+    if (blockIdx.x == 0 && threadIdx.x < K && ((active >> threadIdx.x) & 1u)) {
         st->out[threadIdx.x].found = 0;
         st->out[threadIdx.x].len = 0;
     }
     if (tid0 == 0) { st->cyc_mask = 0; st->pend = 0; st->cuts = 0; }
-    const unsigned active = p.gate ? (p.active & (__ldcg(p.gate) >> p.k0)) : p.active;
-    if (!active) return;   // grid-uniform
+    ull t_phase = 0;
+    if (tid0 == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_phase));
+    if (!active) return 0u;   // grid-uniform
     // jump = grandparent (two predecessor steps straight from pred, which nobody writes during this
     // phase): saves the separate init sweep, its grid sync and the src[] gather of an edge-only pred
     for (ll i = tid0; i < total; i += stride) {
         const int k = (int)(i % K);
         if (!((active >> k) & 1u)) continue;   // jump of a decided candidate is never read
         int j = -1;
-        const int u = (int)(__ldcg(p.pred + i) >> 32);
-        if (u >= 0) j = (int)(__ldcg(p.pred + (ll)u * K + k) >> 32);
-        __stcg(p.jump + i, j);
+        const int u = (int)(__ldcg(cv.pred() + i) >> 32);
+        if (u >= 0) j = (int)(__ldcg(cv.pred() + (ll)u * K + k) >> 32);
+        __stcg(cv.jump() + i, j);
     }
     grid.sync();
 
@@ -599,12 +822,12 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         for (ll i = tid0; i < total; i += stride) {
             const int k = (int)(i % K);
             if (!((alive_mask >> k) & 1u)) continue;
-            const int j = __ldcg(p.jump + i);
+            const int j = __ldcg(cv.jump() + i);
             if (j >= 0) {
                 int jj = j;
                 if ((moving >> k) & 1u) {
-                    jj = __ldcg(p.jump + (ll)j * K + k);
-                    __stcg(p.jump + i, jj);
+                    jj = __ldcg(cv.jump() + (ll)j * K + k);
+                    __stcg(cv.jump() + i, jj);
                 }
                 if (jj >= 0) {
                     const int v = (int)(i / K);
@@ -633,7 +856,7 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
             if (c) na |= 1u << k;
             if (c && c < cp && ((moving >> k) & 1u)) nm |= 1u << k;
         }
-        if (p.prune_above) {
+        if (cv.prune_above()) {
             // a candidate that is alive but no longer moving holds a cycle; a cycle negative at lambda_k is negative
             // at every larger lambda, so the (deeper, junk-cycle) predecessor graphs above it need no more rounds
 #pragma unroll
@@ -643,8 +866,14 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         alive_mask = na;
         moving = nm;
     }
-    if (tid0 == 0) { st->rounds_run = (unsigned)r; st->pend = alive_mask; }
-    if (alive_mask == 0) return;
+    if (tid0 == 0) {
+        st->rounds_run = (unsigned)r; st->pend = alive_mask;
+        ull t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        st->ns_check[0] += t - t_phase; st->check_rounds += (ull)r;
+        t_phase = t;
+    }
+    if (alive_mask == 0) return 0u;
 
     unsigned pending = alive_mask;   // candidates whose predecessor graph still holds an unexamined cycle
     const int r_last = r - 1;   // at least one doubling round ran
@@ -656,8 +885,8 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         for (ll i = tid0; i < total; i += stride) {
             const int k = (int)(i % K);
             if (!((pending >> k) & 1u)) continue;
-            const int j = __ldcg(p.jump + i);
-            if (j >= 0 && __ldcg(p.jump + (ll)j * K + k) != -2) {
+            const int j = __ldcg(cv.jump() + i);
+            if (j >= 0 && __ldcg(cv.jump() + (ll)j * K + k) != -2) {
                 const int v = (int)(i / K);
 #pragma unroll
                 for (int kk = 0; kk < K; kk++)
@@ -675,23 +904,6 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
         if (blockIdx.x < K && ((pending >> blockIdx.x) & 1u)) {   // block-uniform: block k serves candidate k
             const int k = blockIdx.x;
             __shared__ int s_x, s_len;
-            __shared__ double s_d[3][8];
-            __shared__ ll s_l[2][8];
-            __shared__ int s_m[8];
-            auto step = [&](int y) { return y < 0 ? -1 : (int)(__ldcg(p.pred + (ll)y * K + k) >> 32); };
-            // one lap over pred from y, recording the edge list; returns the vertex it stopped at
-            auto lap = [&](int y, ll cap, ll &len) {
-                int cur = y;
-                ll i = 0;
-                do {
-                    const ull pe = __ldcg(p.pred + (ll)cur * K + k);
-                    if (i < p.cap) p.cyc_edges[(ll)k * p.cap + i] = (int)(unsigned)pe;
-                    cur = (int)(pe >> 32);
-                    i++;
-                } while (cur != y && cur >= 0 && i < cap);
-                len = i;
-                return cur;
-            };
             if (threadIdx.x == 0) {
                 const int rep = it == 0 ? __ldcg(&st->minlive[r_last * MRC_KMAX + k]) : __ldcg(&st->rep[it * MRC_KMAX + k]);
                 int x = -1;
@@ -704,25 +916,25 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                     // if even that fails Brent's cycle finding (one pointer step per iteration) runs from there.
                     int y = rep;
                     for (int t = 0; t < 96; t++) {   // (16 hops were measured: the capped laps of the fallback cost more, check 65 -> 80-93 us)
-                        const int j = __ldcg(p.jump + (ll)y * K + k);
+                        const int j = __ldcg(cv.jump() + (ll)y * K + k);
                         if (j < 0) break;
                         y = j;
                     }
-                    int cur = lap(y, 2048, len);
+                    int cur = cycle_lap<K>(p, cv, k, y, 2048, len);
                     if (cur == y) x = y;
                     else if (cur >= 0) {
                         y = cur;
-                        cur = lap(y, 4096, len);
+                        cur = cycle_lap<K>(p, cv, k, y, 4096, len);
                         if (cur == y) x = y;
                         else if (cur >= 0) {
-                            int hare = step(cur), tort = cur;
+                            int hare = cycle_step<K>(cv, k, cur), tort = cur;
                             ll power = 1, lam_ = 1;
                             for (ll g = 0; hare >= 0 && hare != tort && g <= 3 * p.n; g++) {
                                 if (power == lam_) { tort = hare; power <<= 1; lam_ = 0; }
-                                hare = step(hare);
+                                hare = cycle_step<K>(cv, k, hare);
                                 lam_++;
                             }
-                            if (hare >= 0 && hare == tort && lap(hare, p.n + 1, len) == hare) x = hare;
+                            if (hare >= 0 && hare == tort && cycle_lap<K>(p, cv, k, hare, p.n + 1, len) == hare) x = hare;
                         }
                     }
                 }
@@ -730,85 +942,25 @@ __global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant_
                 s_len = x >= 0 ? (int)len : 0;
             }
             __syncthreads();
-            const int x = s_x, len = s_len;
-            if (x >= 0) {   // block-uniform
-                // sums, smallest vertex and max |dist| of the recorded lap, by the whole block
-                double sc = 0.0, stt = 0.0, mabs = 0.0;
-                ll isc = 0, ist = 0;
-                int minv = 0x7fffffff;
-                __threadfence_block();
-                for (int i = threadIdx.x; i < len; i += blockDim.x) {
-                    const int e = __ldcg(p.cyc_edges + (ll)k * p.cap + i);
-                    const int u = __ldg(p.src + e);
-                    minv = u < minv ? u : minv;
-                    if (p.exact) { isc += __ldg(p.icost + e); ist += __ldg(p.itime + e); }
-                    else {
-                        double ce = __ldg(p.cost + e), te = __ldg(p.time + e);
-                        if (p.scen && e == p.pe[k]) { ce = __dadd_rn(ce, p.pdc[k]); te = __dadd_rn(te, p.pdt[k]); }
-                        sc += ce; stt += te;
-                        mabs = fmax(mabs, fabs(__ldcg(static_cast<const double *>(p.dist) + (ll)u * K + k)));
-                    }
-                }
-                for (int o = 16; o; o >>= 1) {
-                    sc += __shfl_down_sync(0xffffffffu, sc, o); stt += __shfl_down_sync(0xffffffffu, stt, o);
-                    mabs = fmax(mabs, __shfl_down_sync(0xffffffffu, mabs, o));
-                    isc += __shfl_down_sync(0xffffffffu, isc, o); ist += __shfl_down_sync(0xffffffffu, ist, o);
-                    const int mo = __shfl_down_sync(0xffffffffu, minv, o);
-                    minv = mo < minv ? mo : minv;
-                }
-                const int w = threadIdx.x >> 5;
-                if ((threadIdx.x & 31) == 0) { s_d[0][w] = sc; s_d[1][w] = stt; s_d[2][w] = mabs; s_l[0][w] = isc; s_l[1][w] = ist; s_m[w] = minv; }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    sc = 0.0; stt = 0.0; mabs = 0.0; isc = 0; ist = 0; minv = 0x7fffffff;
-                    for (int j = 0; j < 8; j++) {
-                        sc += s_d[0][j]; stt += s_d[1][j]; mabs = fmax(mabs, s_d[2][j]);
-                        isc += s_l[0][j]; ist += s_l[1][j]; minv = s_m[j] < minv ? s_m[j] : minv;
-                    }
-                }
-                if (threadIdx.x == 0) {
-                    bool settled = true;   // nothing left to examine for k unless a false cycle is cut below
-                    int kind = 0;
-                    if (p.exact) {
-                        if ((__int128)p.b[k] * isc - (__int128)p.a[k] * ist < 0) kind = MRC_CYC_NEG;
-                    } else if (stt > 0) {
-                        // r < lambda: negative.  r >= lambda but (r - lambda)*T inside the rounding noise of the
-                        // walk (len * eps * max|dist|, x8): a rounding artefact that would relax forever -> TIE.
-                        const double rr = sc / stt;
-                        if (rr < p.lam[k]) kind = MRC_CYC_NEG;
-                        else if ((rr - p.lam[k]) * stt <= 8.0 * (double)len * 2.220446049250313e-16 * mabs) kind = MRC_CYC_TIE;
-                    }
-                    if (kind) {
-                        CycleOut o;
-                        o.found = kind; o.len = len; o.minv = minv; o.pad = x;   // pad = vertex the recorded walk starts from
-                        o.sumc = sc; o.sumt = stt; o.maxabs = mabs; o.isumc = isc; o.isumt = ist;
-                        st->out[k] = o;
-                        atomicOr(&st->decided, 1u << (k + p.k0));   // relaxation launches already enqueued skip this candidate
-                    } else {
-                        // false cycle: mark its vertices dead for this launch and cut it for good
-                        int cur = minv;
-                        ll g = 0;
-                        do {
-                            const int nxt = step(cur);
-                            __stcg(p.jump + (ll)cur * K + k, -2);
-                            cur = nxt;
-                            g++;
-                        } while (cur != minv && cur >= 0 && g <= p.n);
-                        __stcg(p.pred + (ll)minv * K + k, ~0ull);
-                        atomicAdd(&st->cuts, 1u);
-                        settled = false;
-                    }
-                    if (settled) atomicAnd(&st->pend, ~(1u << k));
-                }
-            } else if (threadIdx.x == 0) {
-                // no representative left, or the chain broke while we walked (cannot happen between launches)
-                atomicAnd(&st->pend, ~(1u << k));
-            }
+            const bool settled = cycle_verify_block<K>(p, cv, k, s_x, s_len, true);
+            if (threadIdx.x == 0 && settled) atomicAnd(&st->pend, ~(1u << k));
         }
         grid.sync();
         pending = __ldcg(&st->pend);
     }
-    if (tid0 == 0) st->cyc_mask = alive_mask;
+    if (tid0 == 0) {
+        st->cyc_mask = alive_mask;
+        ull t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        st->ns_check[1] += t - t_phase;
+    }
+    return alive_mask;
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) cycle_check_kernel(const __grid_constant__ CheckArgs p) {
+    cg::grid_group grid = cg::this_grid();
+    cycle_check_device<K>(p, CheckParamView{p}, grid);
 }
 
 // gather (src, cost, time) of a recorded cycle edge list for the host

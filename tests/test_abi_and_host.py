@@ -35,7 +35,7 @@ def test_header_symbols_exported(native):
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/mrc_b200.h but not exported"
     assert sorted(native.EXPORTS) == syms
-    assert L.mrc_abi_version() == 3
+    assert L.mrc_abi_version() == 4
 
 
 def test_status_codes_match_header(native):

@@ -20,7 +20,8 @@ for seed in seeds:
         for K in (1, 2, 4, 8):
             ms = g.bench_relax([r - 0.5 - 0.1 * k for k in range(K)], 30)
             print(f"[{tag}] relax K={K}: pass1 {ms[0]*1e3:6.1f} pass2 {ms[1]*1e3:6.1f} pass3 {ms[2]*1e3:6.1f} late(21-30) {ms[20:].mean()*1e3:6.1f} us", flush=True)
-    for K, sparse in (() if os.environ.get("ONLY_PASSES") else ((4, 0), (4, 1), (1, 0), (1, 1))):
+    modes = [tuple(int(x) for x in md.split(":")) for md in os.environ.get("MODES", "4:0,4:1,1:0,1:1").split(",")]
+    for K, sparse in (() if os.environ.get("ONLY_PASSES") else modes):
         g.set_option("sparse", sparse)
         for _ in range(2):
             g.solve_numeric(lo, hi, K=K)
@@ -34,5 +35,8 @@ for seed in seeds:
         assert abs(out["ratio"] - r) <= 1e-9 * max(1, abs(r)), (out["ratio"], r)
         print(f"[{tag}] seed {seed} K={K} sparse={sparse}: {dt*1e3:6.2f} ms/solve  rounds {out['iterations']}  relax {st['relax_launches']/reps:5.1f} x "
               f"{1e3*st['relax_ms']/max(st['relax_launches'],1):5.1f} us = {st['relax_ms']/reps:5.2f} ms  sparse {st['sparse_passes']/reps:5.1f} passes {st['sparse_ms']/reps:5.2f} ms  "
-              f"check {st['check_launches']/reps:4.1f} x {1e3*st['check_ms']/max(st['check_launches'],1):5.1f} us = {st['check_ms']/reps:5.2f} ms  cyc_len {len(out['cycle'])-1}", flush=True)
+              f"check {st['check_launches']/reps:4.1f} x {1e3*st['check_ms']/max(st['check_launches'],1):5.1f} us = {st['check_ms']/reps:5.2f} ms "
+              f"(doubling {st['check_doubling_ms']/reps:4.2f} in {st['check_rounds']/max(st['check_launches'],1):3.1f} rounds, extract {st['check_extract_ms']/reps:4.2f})  "
+              f"crowded {st['crowded_sweeps']/reps:3.1f} x {1e3*st['crowded_ms']/max(st['crowded_sweeps'],1):5.1f} us  probes {st['probe_launches']/reps:3.1f} {st['probe_ms']/reps:5.2f} ms  "
+              f"launches {st['kernel_launches']/reps:5.1f}  cyc_len {len(out['cycle'])-1}", flush=True)
     g.close()
