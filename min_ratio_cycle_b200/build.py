@@ -22,7 +22,7 @@ OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libmrc_b200.so")
 HEADER = os.path.join(ROOT, "include", "mrc_b200.h")
 UNITS = {   # source -> headers it depends on
-    "mrc_b200.cu": ["mrc_kernels.cuh", "mrc_batch.cuh", "mrc_search.h", "mrc_host.h", "mrc_comm.cuh"],
+    "mrc_b200.cu": ["mrc_kernels.cuh", "mrc_probe.cuh", "mrc_batch.cuh", "mrc_search.h", "mrc_host.h", "mrc_comm.cuh"],
     "mrc_build.cu": ["mrc_build.cuh", "mrc_host.h"],
 }
 SOURCES = [os.path.join(CSRC, s) for s in UNITS]

@@ -101,6 +101,11 @@ struct mrc_graph {
     int tick_max = 8;            // option "tick_max": longest tick (passes between two exchanges) of the sharded search
     int check_growth = 50;       // option "check_growth" (0 = the doubling schedule 2, 6, 14, 30, ...): see ProbeRun::enqueue_burst
     int check_every = 0;         // option "check_every" (experiments): cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
+    int dprobe = 1;              // option "dprobe": with several ranks, probes of a search that holds a cycle are DISTRIBUTED (every rank sweeps
+                                 // a slice of the edge stream, mrc_comm.cuh) instead of run by one rank while the others wait
+    int dprobe_group = 0;        // option "dprobe_group": sweeps of a distributed probe between two exchanges (0 = ranks / 2)
+    int slice_W = 0, slice_me = -1;   // distributed probe: cached slice of this rank (graph_slice)
+    ll slice_e[2] = {0, 0}, slice_v[2] = {0, 0};
     int qstart = 1;              // option "qstart": the first round of a search without a known cycle places its candidates at low quantiles of the
                                  // edge-ratio distribution (see plan_first_round) instead of uniformly over [min c/t - 1, max c/t + 1]
     ll qstart_min_edges = 20000; // ... on graphs of at least this many edges (smaller ones keep the reference's midpoints)
@@ -287,6 +292,8 @@ static int graph_new(int64_t n, int64_t m, int device, bool with_int, mrc_graph 
         if (const char *env = getenv("MRC_B200_SPARSE_MIN_EDGES")) g->sparse_min_edges = atoll(env);   // parity suite: 0
         if (const char *env = getenv("MRC_B200_COMPACT_MIN_EDGES")) g->compact_min_edges = atoll(env);   // parity suite: 0
         if (const char *env = getenv("MRC_B200_PERSIST")) g->persist = std::max(0, std::min(2, atoi(env)));
+        if (const char *env = getenv("MRC_B200_DPROBE")) g->dprobe = atoi(env) != 0;
+        if (const char *env = getenv("MRC_B200_DPROBE_GROUP")) g->dprobe_group = std::max(0, std::min(atoi(env), 64));
         return MRC_OK;
     }();
     if (rc) { mrc_graph_destroy(g); return rc; }
@@ -1172,19 +1179,10 @@ void ProbeRun::finish() {
     g->last_exact = exact; g->last_K = K;
 }
 
-/*
- * The same probe as ONE cooperative launch (mrc_probe.cuh): the pass loop, the check schedule, narrowing, the compact
- * survivor, the switch to worklist passes and pruning by monotonicity run on the device; the host launches, waits once
- * and reads one result block.
- */
-static int run_probe_persist(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
-                             unsigned flags, ProbeOut *res, const void *warm = nullptr) {
-    ProbeRun pr;
-    pr.device_init = true;
-    MRC_TRY(pr.begin(g, exact, K, lam, a, b, slack, flags, res));
-    const int KT = pr.KT;
+// arguments of a persistent probe from a ProbeRun whose begin() has run (with device_init set)
+static int probe_args(mrc_graph *g, ProbeRun &pr, unsigned flags, const void *warm, ProbeArgs &pa) {
+    const int K = pr.K, KT = pr.KT;
     if (pr.may_compact) MRC_TRY(ensure_compact(g));
-    ProbeArgs pa;
     memset(&pa, 0, sizeof pa);
     pa.r = pr.ra;
     pa.r.ks = KT; pa.r.k0 = 0; pa.r.active = (1u << K) - 1u;
@@ -1201,6 +1199,13 @@ static int run_probe_persist(mrc_graph *g, bool exact, int K, const double *lam,
     pa.bm_words = (int)(g->bm_bytes / 4);
     pa.warm = warm;
     pa.out = g->d_probe;
+    pa.dW = 1;
+    return MRC_OK;
+}
+// launch, wait, read the result block; verdicts and statistics of the probe
+static int probe_launch_collect(mrc_graph *g, ProbeRun &pr, const ProbeArgs &pa, ProbeOut *res) {
+    const int K = pr.K, KT = pr.KT;
+    const bool exact = pr.exact;
     const int blocks = g->probe_blocks[kt_index(KT)][exact ? 1 : 0];
     {   // one probe per device at a time: its arguments live in the device's constant memory (c_probe)
         std::lock_guard<std::mutex> lock(g_probe_mu[g->device]);
@@ -1226,13 +1231,28 @@ static int run_probe_persist(mrc_graph *g, bool exact, int K, const double *lam,
     st.check_launches += o.n_check; st.check_ms += 1e-6 * (double)o.ns_check;
     st.false_cycles_cut += o.cuts;
     st.check_doubling_ms += 1e-6 * (double)o.ns_chk_phase[0]; st.check_extract_ms += 1e-6 * (double)o.ns_chk_phase[1]; st.check_rounds += (int64_t)o.check_rounds;
-    st.relax_edge_slots += (int64_t)o.slots * g->m;
-    st.relax_edge_visits += (int64_t)o.slots * g->m + (int64_t)o.sparse_visits;
+    st.relax_edge_slots += (int64_t)o.slots * pa.r.m;
+    st.relax_edge_visits += (int64_t)o.slots * pa.r.m + (int64_t)o.sparse_visits;
     st.probe_launches += 1; st.probe_ms += 1e-6 * (double)o.ns_total;
     st.kernel_launches += 1;
     st.d2h_bytes += sizeof(ProbeDev);
     pr.finish();
     return MRC_OK;
+}
+
+/*
+ * The same probe as ONE cooperative launch (mrc_probe.cuh): the pass loop, the check schedule, narrowing, the compact
+ * survivor, the switch to worklist passes and pruning by monotonicity run on the device; the host launches, waits once
+ * and reads one result block.
+ */
+static int run_probe_persist(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
+                             unsigned flags, ProbeOut *res, const void *warm = nullptr) {
+    ProbeRun pr;
+    pr.device_init = true;
+    MRC_TRY(pr.begin(g, exact, K, lam, a, b, slack, flags, res));
+    ProbeArgs pa;
+    MRC_TRY(probe_args(g, pr, flags, warm, pa));
+    return probe_launch_collect(g, pr, pa, res);
 }
 
 static int run_probe(mrc_graph *g, bool exact, int K, const double *lam, const ll *a, const ll *b, double slack,
@@ -1512,6 +1532,8 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "compact_min_edges") g->compact_min_edges = std::max(0, value);
     else if (s == "persist") g->persist = std::max(0, std::min(2, value));
     else if (s == "qstart") g->qstart = value != 0;
+    else if (s == "dprobe") g->dprobe = value != 0;
+    else if (s == "dprobe_group") g->dprobe_group = std::max(0, std::min(value, 64));
     else if (s == "qstart_min_edges") g->qstart_min_edges = std::max(0, value);
     else if (s == "check_every") g->check_every = std::max(0, value);
     else if (s == "check_growth") g->check_growth = std::max(0, value);
@@ -1582,8 +1604,13 @@ static bool plan_first_round(mrc_graph *g, double lo, double hi, int K, double *
     std::vector<double> q((size_t)K);
     first_round_levels(K, q.data());
     const size_t S = g->qsample.size();
+    size_t prev = 0;
     for (int j = 0; j < K; j++) {
-        lam[j] = g->qsample[std::min(S - 1, (size_t)(q[j] * (double)(S - 1)))];
+        size_t idx = std::min(S - 1, (size_t)(q[j] * (double)(S - 1)));
+        if (j > 0 && idx <= prev) idx = prev + 1;   // a long ladder (many ranks) is denser than the sample at its low end
+        if (idx >= S) return false;
+        prev = idx;
+        lam[j] = g->qsample[idx];
         if (!(lam[j] > lo && lam[j] < hi) || (j > 0 && !(lam[j] > lam[j - 1]))) return false;   // ties / outside the bracket
     }
     return true;

@@ -10,6 +10,7 @@
 #include <nccl.h>
 
 #include <thread>
+#include <unistd.h>
 
 // ------------------------------------------------------------------------------------------------ NCCL at run time
 // libmrc_b200.so does not link NCCL: a process that already carries one (PyTorch's bundled copy has the same soname)
@@ -72,8 +73,31 @@ struct mrc_comm {
     double *d_send = nullptr, *d_recv = nullptr, *h_send = nullptr, *h_recv = nullptr;
     int *d_cyc = nullptr;            // broadcast buffer of the winning cycle
     size_t cyc_cap = 0;
+    // peer window of the distributed probe: replicas of dist / pred and a mailbox in plain cudaMalloc memory, mapped into
+    // every other rank (CUDA IPC between processes, peer access inside one process)
+    ll win_n = 0;                    // vertices the window was made for (0 = none yet)
+    bool win_ok = false;             // every rank mapped every peer
+    double *win_dist = nullptr;
+    ull *win_pred = nullptr, *win_mbox = nullptr;
+    void *win_peer[MRC_KMAX][3] = {};   // [rank] -> dist, pred, mbox of that rank (mine: the local pointers)
+    bool win_ipc[MRC_KMAX] = {};        // opened with cudaIpcOpenMemHandle (to be closed)
+    ull xseq = 1ull << 32;           // step number of the next distributed probe's first message
 };
 static size_t comm_rank_doubles() { return MRC_HDR + (size_t)MRC_KMAX * MRC_REC; }
+
+static void comm_window_free(mrc_comm *c) {
+    for (int r = 0; r < MRC_KMAX; r++) {
+        if (c->win_ipc[r]) for (int j = 0; j < 3; j++) if (c->win_peer[r][j]) cudaIpcCloseMemHandle(c->win_peer[r][j]);
+        c->win_ipc[r] = false;
+        for (int j = 0; j < 3; j++) c->win_peer[r][j] = nullptr;
+    }
+    if (c->win_dist) cudaFree(c->win_dist);
+    if (c->win_pred) cudaFree(c->win_pred);
+    if (c->win_mbox) cudaFree(c->win_mbox);
+    c->win_dist = nullptr; c->win_pred = nullptr; c->win_mbox = nullptr;
+    c->win_n = 0; c->win_ok = false;
+    cudaGetLastError();
+}
 
 static int comm_buffers(mrc_comm *c) {
     CUDA_TRY(cudaSetDevice(c->device));
@@ -104,6 +128,7 @@ extern "C" int mrc_comm_destroy(mrc_comm *c) {
     if (c->d_send) cudaFree(c->d_send);
     if (c->d_recv) cudaFree(c->d_recv);
     if (c->d_cyc) cudaFree(c->d_cyc);
+    comm_window_free(c);
     if (c->h_send) cudaFreeHost(c->h_send);
     if (c->h_recv) cudaFreeHost(c->h_recv);
     delete c;
@@ -222,6 +247,159 @@ extern "C" int mrc_graph_create_replicated(mrc_comm *c, int root, int64_t n, int
     return replicate_rank(c, root, n, m, src, dst, cost, time, out);
 }
 
+// ------------------------------------------------------------------------------------------------ distributed probe
+// Once the search holds a cycle, what is left is a chain of single-candidate probes (the certifier of the best cycle, again
+// after every better cycle): depth-bound, ~21 sweeps of the whole edge stream at C3, and more candidates in parallel do not
+// shorten it.  The ranks therefore run such a probe TOGETHER: rank r sweeps the in-edges of its slice of the vertices
+// (1/W of the stream), every value it lowers goes straight into the peers' replicas of dist over NVLink (an 8-byte atomic
+// min per peer; after the first passes a pass lowers a few thousand vertices), and one word per rank and pass through
+// mailboxes in peer memory tells everybody whether anybody moved.  No host, no NCCL inside the probe: it is one persistent
+// kernel per rank (probe_kernel<1>, mrc_probe.cuh).  NCCL carries only the IPC handles, once.
+struct WinHello {              // what a rank tells the others about its window (one all-gather)
+    long long pid;
+    int device, ok;
+    void *raw[3];
+    cudaIpcMemHandle_t h[3];
+};
+static_assert(sizeof(WinHello) <= (MRC_HDR + MRC_KMAX * MRC_REC) * 8, "WinHello must fit the per-rank exchange buffer");
+
+static int comm_allgather_bytes(mrc_comm *c, cudaStream_t st, const void *mine, void *all, size_t bytes) {
+    NcclApi *api;
+    MRC_TRY(nccl_api(&api));
+    const size_t per = comm_rank_doubles();
+    CUDA_TRY(cudaMemcpyAsync(c->d_send, mine, bytes, cudaMemcpyHostToDevice, st));
+    NCCL_TRY(api, api->AllGather(c->d_send, c->d_recv, per, ncclDouble, c->comm, st));
+    std::vector<char> tmp(per * 8 * (size_t)c->nranks);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), c->d_recv, tmp.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int r = 0; r < c->nranks; r++) memcpy((char *)all + (size_t)r * bytes, tmp.data() + (size_t)r * per * 8, bytes);
+    return MRC_OK;
+}
+
+// Collective over the ranks of c: (re)build the peer window for graphs of n vertices.  Failure to map a peer is not an
+// error of the search: the window is simply marked unusable on EVERY rank and the probes stay on one GPU.
+static int comm_window(mrc_comm *c, mrc_graph *g) {
+    const ll n = g->n;
+    if (c->win_n == n) return MRC_OK;
+    const int W = c->nranks, me = c->rank;
+    comm_window_free(c);
+    c->win_n = n;
+    if (W < 2 || W > MRC_KMAX) return MRC_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    WinHello mine;
+    memset(&mine, 0, sizeof mine);
+    mine.pid = (long long)getpid(); mine.device = c->device; mine.ok = 1;
+    const size_t mbox_bytes = (size_t)W * MRC_MBOX_SLOTS * 8;
+    if (cudaMalloc((void **)&c->win_dist, (size_t)n * 8) != cudaSuccess || cudaMalloc((void **)&c->win_pred, (size_t)n * 8) != cudaSuccess ||
+        cudaMalloc((void **)&c->win_mbox, mbox_bytes) != cudaSuccess) mine.ok = 0;
+    if (mine.ok) {
+        if (cudaMemset(c->win_mbox, 0, mbox_bytes) != cudaSuccess) mine.ok = 0;
+        mine.raw[0] = c->win_dist; mine.raw[1] = c->win_pred; mine.raw[2] = c->win_mbox;
+        for (int j = 0; j < 3 && mine.ok; j++) if (cudaIpcGetMemHandle(&mine.h[j], mine.raw[j]) != cudaSuccess) mine.ok = 0;
+    }
+    cudaGetLastError();
+    std::vector<WinHello> all((size_t)W);
+    MRC_TRY(comm_allgather_bytes(c, g->stream, &mine, all.data(), sizeof(WinHello)));
+    int ok = mine.ok;
+    for (int r = 0; r < W && ok; r++) ok &= all[r].ok;
+    for (int r = 0; r < W && ok; r++) {
+        if (r == me) { for (int j = 0; j < 3; j++) c->win_peer[r][j] = mine.raw[j]; continue; }
+        if (all[r].pid == mine.pid) {   // same process (mrc_comm_init): plain peer access
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, c->device, all[r].device) != cudaSuccess || !can) { ok = 0; break; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; break; }
+            cudaGetLastError();
+            for (int j = 0; j < 3; j++) c->win_peer[r][j] = all[r].raw[j];
+        } else {
+            for (int j = 0; j < 3; j++)
+                if (cudaIpcOpenMemHandle(&c->win_peer[r][j], all[r].h[j], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { c->win_peer[r][j] = nullptr; ok = 0; }
+            c->win_ipc[r] = true;
+            if (!ok) break;
+        }
+    }
+    cudaGetLastError();
+    // every rank must come to the same conclusion
+    WinHello verdict;
+    memset(&verdict, 0, sizeof verdict);
+    verdict.ok = ok;
+    MRC_TRY(comm_allgather_bytes(c, g->stream, &verdict, all.data(), sizeof(WinHello)));
+    for (int r = 0; r < W; r++) ok &= all[r].ok;
+    c->win_ok = ok != 0;
+    if (getenv("MRC_B200_TRACE") && me == 0) fprintf(stderr, "  peer window for n=%lld over %d ranks: %s\n", (long long)n, W, c->win_ok ? "mapped" : "unavailable");
+    return MRC_OK;
+}
+
+// this rank's slice of a destination-sorted edge stream: vertices [v_lo, v_hi) and their in-edges [e_lo, e_hi), cut at vertex
+// boundaries near m * r / W (every rank derives the same cuts from the same replica)
+static int graph_slice(mrc_graph *g, int W, int me) {
+    if (g->slice_W == W && g->slice_me == me) return MRC_OK;
+    if (!g->d_starts) {
+        DALLOC(g->d_starts, ((size_t)g->n + 1) * 4);
+        in_offsets_kernel<<<(int)std::min<ll>((g->n + 256) / 256, (ll)g->sms * 8), 256, 0, g->stream>>>(g->d_dst, g->m, g->n, g->d_starts);
+        CUDA_TRY(cudaGetLastError());
+        { g->stats.other_launches++; g->stats.kernel_launches++; }
+    }
+    int v[2] = {0, (int)g->n}, e[2] = {0, (int)g->m};
+    for (int j = 0; j < 2; j++) {
+        const int r = me + j;
+        if (r == 0 || r == W) continue;
+        CUDA_TRY(cudaMemcpyAsync(&v[j], g->d_dst + g->m * r / W, 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+        CUDA_TRY(cudaMemcpyAsync(&e[j], g->d_starts + v[j], 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_TRY(cudaStreamSynchronize(g->stream));
+    }
+    g->slice_v[0] = v[0]; g->slice_v[1] = v[1]; g->slice_e[0] = e[0]; g->slice_e[1] = e[1];
+    g->slice_W = W; g->slice_me = me;
+    return MRC_OK;
+}
+
+// One single-candidate numeric probe run by all ranks of c together (collective; every rank gets the same verdict and, for a
+// negative one, the same cycle in its own cycle buffer).
+static int run_probe_dist(mrc_comm *c, mrc_graph *g, double lam, double slack, ProbeOut *res) {
+    const int W = c->nranks, me = c->rank;
+    MRC_TRY(graph_slice(g, W, me));
+    ProbeRun pr;
+    pr.device_init = true;
+    MRC_TRY(pr.begin(g, false, 1, &lam, nullptr, nullptr, slack, 0, res));
+    pr.use_sparse = false; pr.may_compact = false;
+    ProbeArgs pa;
+    MRC_TRY(probe_args(g, pr, 0, nullptr, pa));
+    const ll e_lo = g->slice_e[0], e_hi = g->slice_e[1];
+    pa.r.src += e_lo; pa.r.dst += e_lo; pa.r.cost += e_lo; pa.r.time += e_lo; pa.r.m = e_hi - e_lo;
+    pa.r.dist = c->win_dist; pa.r.pred = c->win_pred;
+    pa.c.dist = c->win_dist; pa.c.pred = c->win_pred;
+    pa.dG = g->dprobe_group > 0 ? g->dprobe_group : std::max(1, W / 2);
+    pa.dW = W; pa.dme = me; pa.e_base = (unsigned)e_lo; pa.v_lo = g->slice_v[0]; pa.v_hi = g->slice_v[1];
+    int np = 0;
+    for (int r = 0; r < W; r++) {
+        pa.peer_mbox[r] = (ull *)c->win_peer[r][2];
+        if (r == me) continue;
+        pa.pp.peer[np] = (ull *)c->win_peer[r][0];
+        pa.peer_pred[np] = (ull *)c->win_peer[r][1];
+        np++;
+    }
+    pa.pp.n_peers = np;
+    pa.mbox = c->win_mbox;
+    pa.check_growth = 100;   // checks after 2, 6, 12, 24, ... sweeps: a check costs a gather of pred over NVLink on top of the pointer doubling
+    pa.seq0 = c->xseq;
+    c->xseq += 1ull << 32;
+    if (const char *env = getenv("MRC_B200_DPROBE_MAXPASS")) pa.max_passes = std::max(8, atoi(env));   // debugging aid
+    MRC_TRY(probe_launch_collect(g, pr, pa, res));
+    if (getenv("MRC_B200_TRACE")) {
+        std::vector<double> h((size_t)g->n);
+        CUDA_TRY(cudaMemcpy(h.data(), c->win_dist, (size_t)g->n * 8, cudaMemcpyDeviceToHost));
+        double mn = 0; ll deep = 0;
+        for (double x : h) { mn = std::min(mn, x); deep += x < -1e4; }
+        const ProbeDev &o = *g->h_probe;
+        fprintf(stderr, "    rank %d: slice e[%lld,%lld) v[%lld,%lld) G %d sweeps %u checks %u cuts %u verdict %d passes %lld min dist %.6g (%lld below -1e4) sweep %.1f us/step\n",
+                me, (long long)e_lo, (long long)e_hi, (long long)pa.v_lo, (long long)pa.v_hi, pa.dG, o.n_sweep[0], o.n_check, o.cuts, res[0].verdict,
+                (long long)res[0].passes, mn, (long long)deep, o.n_sweep[0] ? 1e-3 * (double)o.ns_sweep[0] / ((double)o.n_sweep[0] / pa.dG) : 0.0);
+    }
+    if (res[0].verdict < 0) return set_err(MRC_ERR_COMM, "distributed probe: a peer did not answer (rank %d of %d)", me, W);
+    return MRC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ sharded search
 // Bracket logic of a tick, shared by every rank (and testable without a device): see mrc_shard_fold in the header.
 static int shard_fold(int nrec, const double *rec, double *lo, double *hi, int *have_cycle, uint8_t *implied) {
@@ -320,6 +498,8 @@ static int shard_solve_rank(mrc_comm *c, mrc_graph *g, double lo, double hi, int
     bool exhausted = false;      // max_iter probes started: this rank only takes part in the exchange from now on
     int cap = g->burst_init;     // passes of the next tick, agreed by all ranks
     double plan_hi = hi;         // upper end of the bracket when my running probe was planned
+    bool go_dist = false;        // a cycle is in hand and the peer window is mapped: the rest of the search is distributed probes
+    if (W > 1 && g->dprobe) MRC_TRY(comm_window(c, g));   // collective the first time a graph of this size is seen
     for (int k = 0; k < K; k++) res[k] = ProbeOut();
     for (size_t i = 0; i < per; i++) c->h_send[i] = 0.0;
     for (int k = 0; k < K; k++) c->h_send[MRC_HDR + MRC_REC * k + 1] = (double)MRC_V_ABANDONED;
@@ -428,6 +608,13 @@ static int shard_solve_rank(mrc_comm *c, mrc_graph *g, double lo, double hi, int
             fprintf(stderr, "\n");
         }
         if (hi - lo <= tol) { out->converged = true; break; }   // solver.py:1075-1076, on the tick every rank sees it
+        // ... not before the second tick: the candidates next to lambda* close their cycle a few sweeps after the far ones, and
+        // starting the Newton chain from a far cycle costs two or three extra probes (measured on 2 GPUs: 2.8 -> 3.4 ms)
+        if (have_cycle && W > 1 && c->win_ok && g->dprobe && ticks >= 2) {   // same records, same fold: every rank leaves the tick loop on this tick
+            if (running) { for (int k = 0; k < pr.K; k++) pr.drop(k, MRC_V_ABANDONED); pr.finish(); running = false; }
+            go_dist = true;
+            break;
+        }
         // ---- length of the next tick.  Every rank runs at the pace of the slowest one (the all-gather waits), so the
         // tick follows the probe that is on the critical path: the LAST rank holds the top of the plan -- with a cycle
         // in hand its last candidate is the certifier of that cycle, the one probe that can end the search -- and its
@@ -455,6 +642,34 @@ static int shard_solve_rank(mrc_comm *c, mrc_graph *g, double lo, double hi, int
         if (have_cycle && lead_wish > 0) next_cap = lead_wish;
         cap = std::max(1, std::min(next_cap, g->tick_max));
         if (!anyone && all_exhausted) break;   // max_iter probes everywhere and the bracket is still open
+    }
+    // ---- Newton steps on the best cycle's ratio, every probe run by all ranks together (run_probe_dist): the certifier of the
+    // current cycle either converges (the cycle is optimal to within tol) or returns a better cycle, whose certifier is next
+    while (go_dist && rounds < max_iter + 64) {
+        double cert;
+        mrc_plan(lo, hi, 1, tol, 1, &cert);
+        ProbeOut r;
+        MRC_TRY(run_probe_dist(c, g, cert, slack, &r));
+        rounds++; ticks++;
+        g->stats.rounds++;
+        const double ratio = (r.verdict == MRC_V_NEG || r.verdict == MRC_V_TIE) ? r.sumc / r.sumt : NAN;
+        if (trace && me == 0) {
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            fprintf(stderr, "  distributed probe %d t=%.3f ms lam %.12g verdict %d passes %lld ratio %.12g\n", rounds, el * 1e3, cert, r.verdict, (long long)r.passes, ratio);
+        }
+        if (r.verdict == MRC_V_NONNEG || r.verdict == MRC_V_TIE) lo = std::max(lo, cert);
+        if ((r.verdict == MRC_V_NEG || r.verdict == MRC_V_TIE) && ratio < hi) {
+            hi = ratio;
+            best_owner = 0;   // every rank extracted the same cycle; rank 0 keeps it
+            if (me == 0) { MRC_TRY(stash_cycle(g, 0, r)); best_o = r; }
+        } else if (r.verdict == MRC_V_NEG) {
+            lo = std::max(lo, std::min(hi, cert));   // a negative cycle that is not better than the one in hand: rounding noise at the optimum
+        } else if (r.verdict == MRC_V_NEG_NOCYCLE) {
+            hi = cert; have_cycle = 0; best_owner = -1;   // pass limit without a cycle to show (reference: hi = mid, solver.py:1057-1060)
+            break;
+        }
+        if (lo > hi) lo = hi;
+        if (hi - lo <= tol) { out->converged = true; break; }
     }
     out->iterations = rounds; out->ticks = ticks; out->lo = lo; out->hi = hi;
     // ---- the winning cycle: its owner brings it to the host and broadcasts it

@@ -92,6 +92,8 @@ struct DevStatus {
     unsigned decided;        // candidates for which this probe's checks reported a cycle (bit per slot); cleared by the host per probe
     unsigned act_count;      // sparse mode: vertices lowered by the last relaxation pass (size of the next worklist)
     unsigned act_cnt[3];     // worklist sizes, rotating: pass p reads [p % 3], appends to [(p+1) % 3], zeroes [(p+2) % 3]
+    unsigned xpad;
+    ull xword[4];            // distributed probe: (step << 8 | OR of every rank's payload) of the last exchanges, for the CTAs of this GPU
 };
 
 // Sparse (worklist) relaxation, see relax_sparse_kernel
@@ -180,6 +182,8 @@ struct ParamView {
     __device__ __forceinline__ ull *pred() const { return p.pred; }
     __device__ __forceinline__ int ks() const { return p.ks; }
     __device__ __forceinline__ int k0() const { return p.k0; }
+    __device__ __forceinline__ unsigned e_base() const { return 0u; }
+    template <typename T> __device__ __forceinline__ void push(int, T) const {}
 };
 template <int K> struct RegView {
     double lam_[K];
@@ -194,6 +198,39 @@ template <int K> struct RegView {
     __device__ __forceinline__ ull *pred() const { return pred_; }
     __device__ __forceinline__ int ks() const { return ks_; }
     __device__ __forceinline__ int k0() const { return k0_; }
+    __device__ __forceinline__ unsigned e_base() const { return 0u; }
+    template <typename T> __device__ __forceinline__ void push(int, T) const {}
+};
+// One candidate, one SLICE of the edge stream, the other slices on peer GPUs (distributed probe, mrc_probe.cuh): edge ids
+// are offset by the slice start, and every value this GPU lowers is pushed into the peers' replicas of dist -- each vertex
+// has a single owner (the GPU holding its in-edges), the push is an atomic min so that stores of different warps cannot
+// land out of order, and only the few vertices a pass still lowers cross NVLink (8 bytes each per peer).
+struct PeerPush {
+    ull *peer[MRC_KMAX];   // dist replicas of the other ranks ([n][1]); n_peers entries
+    int n_peers;
+};
+struct DistView {
+    double lam_;
+    ll a_, b_;
+    void *dist_;
+    ull *pred_;
+    unsigned e_base_;
+    const PeerPush *pp_;
+    __device__ __forceinline__ double lam(int) const { return lam_; }
+    __device__ __forceinline__ ll a(int) const { return a_; }
+    __device__ __forceinline__ ll b(int) const { return b_; }
+    __device__ __forceinline__ void *dist() const { return dist_; }
+    __device__ __forceinline__ ull *pred() const { return pred_; }
+    __device__ __forceinline__ int ks() const { return 1; }
+    __device__ __forceinline__ int k0() const { return 0; }
+    __device__ __forceinline__ unsigned e_base() const { return e_base_; }
+    __device__ __forceinline__ void push(int v, double cand) const {
+        const ull bits = (ull)__double_as_longlong(cand);
+        for (int r = 0; r < pp_->n_peers; r++) atomicMax_system(pp_->peer[r] + v, bits);
+    }
+    __device__ __forceinline__ void push(int v, ll cand) const {
+        for (int r = 0; r < pp_->n_peers; r++) atomicMin_system(reinterpret_cast<ll *>(pp_->peer[r]) + v, cand);
+    }
 };
 template <typename V> __device__ __forceinline__ double mrc_cand(const V &vw, int k, double du, double c, double t) {
     return __dadd_rn(du, __dsub_rn(c, __dmul_rn(vw.lam(k), t)));
@@ -321,7 +358,8 @@ __device__ __forceinline__ void relax_row(const RelaxArgs &p, const V &vw, unsig
 #pragma unroll
         for (int k = 0; k < H; k++)
             if (((wins >> k) & 1u) && mrc_lowered(old[k], cand[k])) {
-                __stcg(vw.pred() + (size_t)v * ks + h + k, ((ull)(unsigned)u << 32) | e);
+                __stcg(vw.pred() + (size_t)v * ks + h + k, ((ull)(unsigned)u << 32) | (e + vw.e_base()));
+                vw.push(v, cand[k]);
                 chg |= 1u << (h + k);
                 lowered = true;
             }

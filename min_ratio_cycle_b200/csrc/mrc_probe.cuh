@@ -52,7 +52,23 @@ struct ProbeArgs {
     int bm_words;
     const void *warm;          // [n] start potentials, or NULL = zero
     ProbeDev *out;
+    // distributed probe (dW > 1; K = 1, numeric): the ranks of a communicator run ONE probe together.  This rank sweeps the
+    // slice r.src .. r.src + r.m of the edge stream (global edge ids = local + e_base) = the in-edges of the vertices
+    // [v_lo, v_hi) it owns, keeps a full replica of dist (r.dist: peers push what they lower) and of pred (r.pred: own slice
+    // live, the others gathered before every check), and agrees with its peers through mailboxes in peer memory.
+    int dW, dme;
+    int dG;                    // sweeps of the slice between two exchanges (the sweeps of a group run back to back, no barrier of any kind)
+    unsigned e_base;
+    ll v_lo, v_hi;
+    PeerPush pp;               // the other ranks' dist replicas
+    ull *peer_pred[MRC_KMAX];  // ... and pred replicas (same order)
+    ull *peer_mbox[MRC_KMAX];  // every rank's mailbox, mine included (index = rank)
+    ull *mbox;                 // mine: [dW][MRC_MBOX_SLOTS] words (step << 8 | payload), slot = step % MRC_MBOX_SLOTS
+    ull seq0;                  // step number of this probe's first message (steps never repeat over the life of a communicator)
 };
+#define MRC_MBOX_SLOTS 16      /* a rank is never more than one step ahead of the slowest */
+#define MRC_X_TIMEOUT 0x80u    /* payload bit: a peer did not answer within MRC_X_TIMEOUT_NS (its process died?) */
+#define MRC_X_TIMEOUT_NS 4000000000ull
 
 // The arguments of the probe in flight.  They live in constant memory rather than in the kernel's parameter block so that
 // the sweeps can be SEPARATE (noinline) functions with their own register allocation and still take every array pointer and
@@ -73,9 +89,12 @@ struct ProbeCtl {              // per-CTA copy of the control state (identical i
     int sparse_mode, sp_in, sp_ci;
     unsigned cin;              // size of the worklist the next worklist pass reads
     ll pass, next_check, next_look;
+    unsigned step;             // iterations of the pass loop so far (a step is one sweep, or one group of sweeps of a distributed probe)
     int track;                 // the next dense sweep records the vertices it lowers
     int do_compaction, do_check, do_colcopy, do_bmclear;
     int any_neg;
+    ull xstep;                 // distributed probe: messages exchanged so far
+    int xfail;                 // ... a peer timed out: the probe is abandoned
     int verdict[MRC_KMAX];
     ll passes[MRC_KMAX];
     double sumc[MRC_KMAX], sumt[MRC_KMAX];   // cost / time sums of the verified cycles (pruning by their ratio)
@@ -159,10 +178,12 @@ __device__ __noinline__ void probe_start(ProbeCtl *s, ProbeClock *clk) {
     s->active = (1u << p.K) - 1u;
     s->ck = -1;
     s->sparse_mode = 0; s->sp_in = 0; s->sp_ci = 0; s->cin = 0u;
+    s->step = 0u;
     s->pass = 0; s->next_check = p.first_check; s->next_look = p.look0 - 1;
     s->track = p.use_sparse && p.look0 <= 1;
     s->do_compaction = s->do_check = s->do_colcopy = s->do_bmclear = 0;
     s->any_neg = 0;
+    s->xstep = 0; s->xfail = 0;
     for (int k = 0; k < MRC_KMAX; k++) { s->verdict[k] = -1; s->passes[k] = 0; }
 }
 
@@ -191,6 +212,48 @@ template <bool EXACT> __device__ __forceinline__ void probe_prune(ProbeCtl *s) {
     }
 }
 
+// ---- distributed probe: one word per rank and step through mailboxes in peer memory (NVLink P2P stores; no host, no NCCL).
+// Called by thread 0 of every CTA after a grid sync.  The chief (CTA 0) sends this rank's payload to every rank, waits for
+// all of them and publishes the OR in st->xword; the other leaders wait for that word, so every CTA takes the same decision
+// even when a peer times out.  Everything this GPU wrote to peer memory before the grid sync is visible to a peer once it
+// has received the step's message (fence.sys on both sides).
+__device__ __noinline__ unsigned probe_exchange(ProbeCtl *s, unsigned payload) {
+    const ProbeArgs &p = c_probe;
+    DevStatus *st = p.c.st;
+    const ull step = p.seq0 + s->xstep;
+    s->xstep++;
+    volatile ull *xw = &st->xword[step & 3];
+    if (blockIdx.x == 0) {
+        __threadfence_system();
+        const ull msg = (step << 8) | (ull)(payload & 0x7fu);
+        for (int r = 0; r < p.dW; r++) {
+            volatile ull *slot = p.peer_mbox[r] + (size_t)p.dme * MRC_MBOX_SLOTS + (step % MRC_MBOX_SLOTS);
+            *slot = msg;
+        }
+        __threadfence_system();
+        unsigned acc = 0;
+        const ull t0 = mrc_globaltimer();
+        for (int r = 0; r < p.dW && !(acc & MRC_X_TIMEOUT); r++) {
+            volatile ull *slot = p.mbox + (size_t)r * MRC_MBOX_SLOTS + (step % MRC_MBOX_SLOTS);
+            for (;;) {
+                const ull v = *slot;
+                if ((v >> 8) == step) { acc |= (unsigned)(v & 0xffu); break; }
+                if (mrc_globaltimer() - t0 > MRC_X_TIMEOUT_NS) { acc |= MRC_X_TIMEOUT; break; }
+            }
+        }
+        __threadfence_system();
+        *xw = (step << 8) | acc;
+        __threadfence();
+        if (acc & MRC_X_TIMEOUT) s->xfail = 1;
+        return acc;
+    }
+    ull v;
+    do { v = *xw; } while ((v >> 8) != step);
+    __threadfence();
+    if (v & MRC_X_TIMEOUT) s->xfail = 1;
+    return (unsigned)(v & 0xffu);
+}
+
 // ---- control point after a pass (every CTA's thread 0: same inputs, same answer): what did it decide, what comes next
 template <int KT, bool EXACT>
 __device__ __noinline__ void probe_after_pass(ProbeCtl *s, ProbeClock *clk) {
@@ -200,7 +263,7 @@ __device__ __noinline__ void probe_after_pass(ProbeCtl *s, ProbeClock *clk) {
     const unsigned active = s->active;
     const ll pass = s->pass;
     const bool sparse_now = s->sparse_mode != 0;
-    unsigned *chw = &st->changed[pass & 3];
+    unsigned *chw = &st->changed[s->step & 3u];
     if (blockIdx.x == 0) {
         const ull d = mrc_lap(clk);
         ProbeDev &acc = clk->acc;
@@ -213,17 +276,26 @@ __device__ __noinline__ void probe_after_pass(ProbeCtl *s, ProbeClock *clk) {
             int kc = KT, k0 = 0;
             if (s->ck >= 0) kc = 1; else mrc_narrow(KT, active, kc, k0);
             const int wi = kc == 1 ? 0 : kc == 2 ? 1 : 2;
-            acc.ns_sweep[wi] += d; acc.n_sweep[wi]++;
-            if (pass < 2) { acc.ns_crowded += d; acc.n_crowded++; }
-            acc.slots += (ull)__popc(active);
+            const unsigned G = p.dW > 1 ? (unsigned)p.dG : 1u;   // sweeps of this step
+            acc.ns_sweep[wi] += d; acc.n_sweep[wi] += G;
+            if (pass < 2) { acc.ns_crowded += d; acc.n_crowded += G; }
+            acc.slots += (ull)__popc(active) * G;
         }
-        st->changed[(pass + 2) & 3] = 0u;   // last read two control points ago, next written two sweeps from now
+        st->changed[(s->step + 2u) & 3u] = 0u;   // last read two control points ago, next written two sweeps from now
     }
-    const unsigned chg = __ldcg(chw);
-    s->pass = pass + 1;
+    unsigned chg = __ldcg(chw);
+    ll done = 1;   // sweeps of this step
+    if (p.dW > 1) {   // distributed probe: a candidate is at its fixed point only if NO rank lowered anything in this group of sweeps
+        done = p.dG;
+        chg = probe_exchange(s, chg & 1u);
+        if (chg & MRC_X_TIMEOUT) { s->step++; s->pass = pass + done; s->active = 0u; s->do_compaction = s->do_check = s->do_colcopy = s->do_bmclear = 0; return; }
+        chg &= 1u;
+    }
+    s->step++;
+    s->pass = pass + done;
     for (int k = 0; k < p.K; k++)
         if (((active >> k) & 1u) && !((chg >> k) & 1u)) {   // nothing moved: a true fixed point
-            s->verdict[k] = MRC_V_NONNEG; s->passes[k] = pass + 1;
+            s->verdict[k] = MRC_V_NONNEG; s->passes[k] = pass + done;
         }
     s->active = active & chg;
     probe_prune<EXACT>(s);
@@ -302,6 +374,19 @@ __device__ __noinline__ void probe_check(ProbeCtl *s, ProbeClock *clk, cg::grid_
     DevStatus *st = p.c.st;
     const unsigned act_now = s->active;
     const int ck = s->ck, K = p.K;
+    if (p.dW > 1) {
+        // every rank brings its slice of pred to every peer, then all of them run the same check on identical copies
+        const ll tid0 = (ll)blockIdx.x * blockDim.x + threadIdx.x, stride = (ll)gridDim.x * blockDim.x;
+        for (ll i = p.v_lo + tid0; i < p.v_hi; i += stride) {
+            const ull x = __ldcg(p.r.pred + i);
+            for (int r = 0; r < p.pp.n_peers; r++) p.peer_pred[r][i] = x;
+        }
+        __threadfence_system();
+        grid.sync();
+        if (threadIdx.x == 0) probe_exchange(s, 0u);
+        __syncthreads();
+        if (s->xfail) { if (threadIdx.x == 0) s->active = 0u; return; }   // grid-uniform
+    }
     unsigned cyc;
     if (KT > 1 && ck >= 0) {
         CheckRegView cv;
@@ -407,6 +492,19 @@ __device__ __noinline__ void probe_sweep_narrow(int k0, bool compact, unsigned a
     const RegView<W> v = mrc_reg_view<W, KT, EXACT>(k0, compact);
     relax_sweep<W, EXACT, false, RegView<W>, MRC_PROBE_PF>(c_probe.r, v, act, chw, act_out);
 }
+// the distributed sweep: this rank's slice of the edge stream, lowered values pushed to the peers' replicas
+__device__ __noinline__ void probe_sweep_dist(unsigned *chw) {
+    const ProbeArgs &p = c_probe;
+    DistView v;
+    v.lam_ = p.r.lam[0]; v.a_ = p.r.a[0]; v.b_ = p.r.b[0];
+    v.dist_ = p.r.dist; v.pred_ = p.r.pred; v.e_base_ = p.e_base; v.pp_ = &p.pp;
+    // A group of sweeps between two exchanges: at 8 ranks a sweep of the slice takes ~7 us and an exchange (grid sync, one word
+    // per rank over NVLink, control) ~15 us.  Relaxation needs no barrier between sweeps; only the fixed-point test does, and
+    // it stays exact: the candidate is declared converged when NO rank lowered anything during a WHOLE group.
+    for (int i = 0; i < p.dG; i++) relax_sweep<1, false, false, DistView, MRC_PROBE_PF>(p.r, v, 1u, chw, nullptr);
+    __threadfence_system();   // my pushes are performed before the grid sync that precedes this step's message
+}
+
 template <int KT, bool EXACT>
 __device__ __noinline__ void probe_sparse_pass(unsigned active, int ck, int in, unsigned cin, int co, unsigned *chw) {
     const ProbeArgs &p = c_probe;
@@ -429,6 +527,12 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, MRC_PROBE_MINBLOCKS) probe_
 
     probe_start<KT>(&s, &clk);
     grid.sync();
+    if constexpr (KT == 1 && !EXACT) {
+        if (c_probe.dW > 1) {   // no rank pushes into a replica that its owner is still initialising
+            if (threadIdx.x == 0) probe_exchange(&s, 0u);
+            __syncthreads();
+        }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) clk.t_start = clk.t_prev = mrc_globaltimer();
 
     for (;;) {
@@ -436,7 +540,7 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, MRC_PROBE_MINBLOCKS) probe_
         const unsigned active = vs.active;
         if (!active) break;
         const int ck = vs.ck;
-        unsigned *chw = &c_probe.c.st->changed[vs.pass & 3];
+        unsigned *chw = &c_probe.c.st->changed[vs.step & 3u];
         if (vs.sparse_mode) {
             // ---- one worklist pass
             const int ci = vs.sp_ci, co = ci == 2 ? 0 : ci + 1, cz = co == 2 ? 0 : co + 1;
@@ -447,7 +551,9 @@ __global__ void __launch_bounds__(MRC_RELAX_THREADS, MRC_PROBE_MINBLOCKS) probe_
             unsigned *act_out = vs.track ? c_probe.bm[0] : nullptr;
             int kc = KT, k0 = 0;
             if (ck >= 0) { kc = 1; k0 = ck; } else mrc_narrow(KT, active, kc, k0);
-            if (kc == KT && ck < 0) probe_sweep_full<KT, EXACT>(active, chw, act_out);
+            if (KT == 1 && !EXACT && c_probe.dW > 1) {
+                if constexpr (KT == 1 && !EXACT) probe_sweep_dist(chw);
+            } else if (kc == KT && ck < 0) probe_sweep_full<KT, EXACT>(active, chw, act_out);
             else if constexpr (KT > 1) {
                 if (kc == 1) probe_sweep_narrow<1, KT, EXACT>(k0, ck >= 0, 1u, chw, act_out);
                 else if constexpr (KT > 2) probe_sweep_narrow<2, KT, EXACT>(k0, false, active >> k0, chw, act_out);

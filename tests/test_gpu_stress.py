@@ -45,13 +45,20 @@ def _graph(kind, rng, integer):
     return n_, U, V, C, T
 
 
-@pytest.fixture(params=["default", "sparse_forced"])
+@pytest.fixture(params=["default", "sparse_forced", "persist_all", "persist_all_sparse", "burst_only"])
 def relax_mode(request, monkeypatch):
-    """default: small graphs sweep densely.  sparse_forced: worklist passes from the first burst boundary on, on every
-    graph (environment switches read at graph creation), so the sparse kernel sees ties, parallel edges, self-loops."""
-    if request.param == "sparse_forced":
+    """default: small graphs sweep densely; single-candidate probes run as ONE persistent probe kernel, wider ones through
+    the burst driver.  sparse_forced: worklist passes from the first burst boundary on, on every graph (environment
+    switches read at graph creation), so the sparse kernel sees ties, parallel edges, self-loops.  persist_all: every probe
+    of up to 4 candidates in the persistent kernel (narrowing, compact survivor, pruning and check schedule on the device),
+    with and without forced worklist passes.  burst_only: no persistent kernel at all."""
+    if request.param in ("sparse_forced", "persist_all_sparse"):
         monkeypatch.setenv("MRC_B200_SPARSE_MIN_EDGES", "0")
         monkeypatch.setenv("MRC_B200_SPARSE_DIV", "1")
+    if request.param.startswith("persist_all"):
+        monkeypatch.setenv("MRC_B200_PERSIST", "1")
+    if request.param == "burst_only":
+        monkeypatch.setenv("MRC_B200_PERSIST", "0")
     monkeypatch.setenv("MRC_B200_COMPACT_MIN_EDGES", "0")   # compact-survivor path on every K >= 2 probe that narrows to one slot
     return request.param
 
