@@ -248,7 +248,7 @@ def main():
     barrier()
     st = g.stats()
     allv = gather([dev_s, wall, float(st["relax_edge_visits"]), float(st["relax_launches"]), st["relax_ms"],
-                   float(st["kernel_launches"]), st["check_ms"]])
+                   float(st["kernel_launches"]), st["check_ms"], float(st["relax_stream_bytes"])])
     t_max = float(allv[:, 0].max())
     relax_total = float(allv[:, 2].sum())
     value = relax_total / t_max / 1e9
@@ -299,7 +299,9 @@ def main():
         relax_launches = float(allv[0, 3])
         relax_ms = float(allv[0, 4])
         bytes_per_launch = 24.0 * m + (16.0 * n * K if 8.0 * n * K > L2_BYTES else 0.0)
-        achieved = bytes_per_launch * relax_launches / (relax_ms * 1e-3) / 1e9 if relax_ms > 0 else 0.0
+        # algorithmic bytes of rank 0's sweeps: 24 B per edge SWEPT (at N > 1 the probes of the Newton phase sweep a 1/N slice per rank)
+        stream_bytes = float(allv[0, 7]) + (16.0 * n * K * relax_launches if 8.0 * n * K > L2_BYTES else 0.0)
+        achieved = stream_bytes / (relax_ms * 1e-3) / 1e9 if relax_ms > 0 else 0.0
         traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "relax_traffic.json")) as fh:
@@ -320,7 +322,8 @@ def main():
             "config": {"workload": workload, "n": n, "m": m, "seed": SEED,
                        "step": "one full solve(): every relaxation sweep, cycle check and lambda probe until hi - lo <= 1e-12",
                        "search": f"K-way multisection, {K} lambda candidates per GPU per probe, candidates sharded over {world} GPU(s); "
-                                 "first round at quantiles of the edge-ratio sample, then uniform candidates + certifier",
+                                 "first round at quantiles of the edge-ratio sample (all candidates); once a cycle is in hand, Newton steps on its ratio + the "
+                                 "certifying probe, single-candidate probes in the persistent kernel (N = 1) or distributed over the ranks (N > 1)",
                        "lambda_candidates_per_gpu": K, "tolerance": tol, "sparse_passes": bool(args.sparse),
                        "l2": "edge arrays 240 MB > 126 MB L2, streamed every pass (no flush needed)",
                        "parallelism": f"lambda-candidate sharding x{world}"},
@@ -341,11 +344,14 @@ def main():
                              "mrc_solve_numeric_sharded + mrc_graph_destroy")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
-                         "kernel": f"relax_kernel<K={K if K in (1,2,4,8) else 8},f64>",
-                         "kernel_note": "average over every relaxation launch of the timed solves that did work (rank 0), update-heavy "
-                                        "first passes and launches narrowed to the undecided candidates (relax_kernel<1|2>) "
-                                        "included; launches gated out after convergence are not counted",
-                         "bytes_per_launch": bytes_per_launch, "frac_of_8TBs_nominal": achieved / 8000.0,
+                         "kernel": f"relax_sweep<f64> (relax_kernel<K={K if K in (1,2,4,8) else 8}> + probe_kernel<1>)",
+                         "kernel_note": "average over every relaxation sweep of the timed solves (rank 0): relax_kernel<4|2|1> launches of the "
+                                        "first round (CUDA events per burst; update-heavy first sweeps and narrowed launches included, launches "
+                                        "gated out after convergence not counted) and the sweeps inside the persistent probe kernel "
+                                        "(relax_sweep, the same device function; device globaltimer at the grid syncs); at N > 1 the sweeps of "
+                                        "the distributed probes read a 1/N slice each (bytes_per_launch_avg)",
+                         "bytes_per_launch": bytes_per_launch, "bytes_per_launch_avg": stream_bytes / max(relax_launches, 1),
+                         "frac_of_8TBs_nominal": achieved / 8000.0,
                          "steady_state": {"us_per_launch": steady_us, "achieved": steady, "frac": steady / peak,
                                           "note": "outside the timed region; launches 21-30 of a 30-launch sweep"}},
         }

@@ -96,6 +96,7 @@ typedef struct mrc_stats {
     double check_doubling_ms;     /* inside check_ms (device globaltimer): predecessor-graph pointer doubling ... */
     double check_extract_ms;      /* ... and cycle extraction + verification */
     int64_t check_rounds;         /* pointer-doubling rounds over all checks */
+    int64_t relax_stream_bytes;   /* edge-stream bytes the dense sweeps read: 24 B x edges swept (a rank of a distributed probe sweeps its slice only) */
 } mrc_stats;
 
 int mrc_abi_version(void);

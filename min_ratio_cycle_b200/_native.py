@@ -58,6 +58,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int64), ("probe_launches", C.c_int64), ("probe_ms", C.c_double),
         ("crowded_sweeps", C.c_int64), ("crowded_ms", C.c_double),
         ("check_doubling_ms", C.c_double), ("check_extract_ms", C.c_double), ("check_rounds", C.c_int64),
+        ("relax_stream_bytes", C.c_int64),
     ]
 
     def as_dict(self):

@@ -101,9 +101,12 @@ struct mrc_graph {
     int tick_max = 8;            // option "tick_max": longest tick (passes between two exchanges) of the sharded search
     int check_growth = 50;       // option "check_growth" (0 = the doubling schedule 2, 6, 14, 30, ...): see ProbeRun::enqueue_burst
     int check_every = 0;         // option "check_every" (experiments): cycle checks every so many passes after the first instead of 2, 6, 14, 30, ...
+    int k_after_cycle = 1;       // option "k_after_cycle": candidates per round once the search holds a cycle (0 = as many as before).  Multisection
+                                 // brackets lambda*; with a cycle in hand what is left is Newton steps on its ratio and the final certifying probe --
+                                 // single-candidate probes that run 1-wide in the persistent kernel instead of dragging K - 1 companions along
     int dprobe = 1;              // option "dprobe": with several ranks, probes of a search that holds a cycle are DISTRIBUTED (every rank sweeps
                                  // a slice of the edge stream, mrc_comm.cuh) instead of run by one rank while the others wait
-    int dprobe_group = 0;        // option "dprobe_group": sweeps of a distributed probe between two exchanges (0 = ranks / 2)
+    int dprobe_group = 0;        // option "dprobe_group": sweeps of a distributed probe between two exchanges (0 = max(2, ranks / 2))
     int slice_W = 0, slice_me = -1;   // distributed probe: cached slice of this rank (graph_slice)
     ll slice_e[2] = {0, 0}, slice_v[2] = {0, 0};
     int qstart = 1;              // option "qstart": the first round of a search without a known cycle places its candidates at low quantiles of the
@@ -1083,6 +1086,7 @@ int ProbeRun::collect() {
         if ((ll)hs.act_count * g->sparse_div > 2 * n) sparse_mode = false;   // the worklist grew back: sweep densely again
     } else {
         g->stats.relax_launches += ran;
+        g->stats.relax_stream_bytes += (int64_t)ran * m * 24;
         g->stats.other_launches += nb - ran + (use_sparse ? 1 : 0);
         g->stats.kernel_launches += use_sparse ? 1 : 0;   // the compaction (sweeps and check are counted where they are launched)
         if (use_sparse) {
@@ -1225,7 +1229,10 @@ static int probe_launch_collect(mrc_graph *g, ProbeRun &pr, const ProbeArgs &pa,
         }
     }
     mrc_stats &st = g->stats;
-    for (int i = 0; i < MRC_PW; i++) { st.relax_launches += o.n_sweep[i]; st.relax_ms += 1e-6 * (double)o.ns_sweep[i]; }
+    for (int i = 0; i < MRC_PW; i++) {
+        st.relax_launches += o.n_sweep[i]; st.relax_ms += 1e-6 * (double)o.ns_sweep[i];
+        st.relax_stream_bytes += (int64_t)o.n_sweep[i] * pa.r.m * 24;
+    }
     st.crowded_sweeps += o.n_crowded; st.crowded_ms += 1e-6 * (double)o.ns_crowded;
     st.sparse_passes += o.n_sparse; st.sparse_ms += 1e-6 * (double)o.ns_sparse;
     st.check_launches += o.n_check; st.check_ms += 1e-6 * (double)o.ns_check;
@@ -1533,6 +1540,7 @@ extern "C" int mrc_set_option(mrc_graph *g, const char *name, int value) {
     else if (s == "persist") g->persist = std::max(0, std::min(2, value));
     else if (s == "qstart") g->qstart = value != 0;
     else if (s == "dprobe") g->dprobe = value != 0;
+    else if (s == "k_after_cycle") g->k_after_cycle = std::max(0, std::min(value, MRC_KMAX));
     else if (s == "dprobe_group") g->dprobe_group = std::max(0, std::min(value, 64));
     else if (s == "qstart_min_edges") g->qstart_min_edges = std::max(0, value);
     else if (s == "check_every") g->check_every = std::max(0, value);
@@ -1654,24 +1662,25 @@ extern "C" int mrc_solve_numeric(mrc_graph *g, double lo, double hi, int hi_is_c
         }
         iters++;
         g->stats.rounds++;
-        if (!(i == 0 && !have_cycle && plan_first_round(g, lo, hi, K, lam))) MRC_TRY(mrc_plan_candidates(lo, hi, have_cycle, tol, K, lam));
+        const int Kr = (have_cycle && g->k_after_cycle > 0) ? std::min(K, g->k_after_cycle) : K;   // candidates of this round
+        if (!(i == 0 && !have_cycle && plan_first_round(g, lo, hi, Kr, lam))) MRC_TRY(mrc_plan_candidates(lo, hi, have_cycle, tol, Kr, lam));
         // Option "stop_on_neg": intermediate rounds only need a better cycle, so a round may end at the first
         // check (from pass 6 on) that verified one, leaving the slow non-negative candidates undecided; the round in
         // which nothing is negative still runs to convergence and proves the lower end.
-        MRC_TRY(run_probe(g, false, K, lam, nullptr, nullptr, slack,
-                          MRC_F_MONOTONE_PRUNE | ((g->stop_on_neg && K >= g->stop_on_neg) ? MRC_F_STOP_ON_NEG : 0u) |
+        MRC_TRY(run_probe(g, false, Kr, lam, nullptr, nullptr, slack,
+                          MRC_F_MONOTONE_PRUNE | ((g->stop_on_neg && Kr >= g->stop_on_neg) ? MRC_F_STOP_ON_NEG : 0u) |
                               (g->patience ? MRC_F_PATIENCE : 0u) | ((have_cycle && g->cert_first) ? MRC_F_CERT_FIRST : 0u), res));
-        for (int k = 0; k < K; k++) {
+        for (int k = 0; k < Kr; k++) {
             vd[k] = res[k].verdict;
             cr[k] = (vd[k] == MRC_V_NEG || vd[k] == MRC_V_TIE) ? res[k].sumc / res[k].sumt : NAN;
         }
         if (trace) {
             fprintf(stderr, "  round %d:", i);
-            for (int k = 0; k < K; k++) fprintf(stderr, " [%.12g v%d p%lld len %d r=%.12g]", lam[k], vd[k], (long long)res[k].passes, res[k].len, cr[k]);
+            for (int k = 0; k < Kr; k++) fprintf(stderr, " [%.12g v%d p%lld len %d r=%.12g]", lam[k], vd[k], (long long)res[k].passes, res[k].len, cr[k]);
             fprintf(stderr, "\n");
         }
         int best = -1;
-        MRC_TRY(mrc_reduce_round(K, lam, vd, cr, &lo, &hi, &have_cycle, &best));
+        MRC_TRY(mrc_reduce_round(Kr, lam, vd, cr, &lo, &hi, &have_cycle, &best));
         if (best >= 0) {
             MRC_TRY(stash_cycle(g, best, res[best]));
             best_o = res[best];

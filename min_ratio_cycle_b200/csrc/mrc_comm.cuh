@@ -258,6 +258,8 @@ extern "C" int mrc_graph_create_replicated(mrc_comm *c, int root, int64_t n, int
 struct WinHello {              // what a rank tells the others about its window (one all-gather)
     long long pid;
     int device, ok;
+    char bus[16];          // PCI bus id of the rank's GPU: the ranks of a distributed probe must sit on DIFFERENT GPUs (their kernels wait
+                           // for one another; two of them time-sliced on one GPU would never meet)
     void *raw[3];
     cudaIpcMemHandle_t h[3];
 };
@@ -289,6 +291,7 @@ static int comm_window(mrc_comm *c, mrc_graph *g) {
     WinHello mine;
     memset(&mine, 0, sizeof mine);
     mine.pid = (long long)getpid(); mine.device = c->device; mine.ok = 1;
+    if (cudaDeviceGetPCIBusId(mine.bus, sizeof mine.bus, c->device) != cudaSuccess) mine.ok = 0;
     const size_t mbox_bytes = (size_t)W * MRC_MBOX_SLOTS * 8;
     if (cudaMalloc((void **)&c->win_dist, (size_t)n * 8) != cudaSuccess || cudaMalloc((void **)&c->win_pred, (size_t)n * 8) != cudaSuccess ||
         cudaMalloc((void **)&c->win_mbox, mbox_bytes) != cudaSuccess) mine.ok = 0;
@@ -302,6 +305,8 @@ static int comm_window(mrc_comm *c, mrc_graph *g) {
     MRC_TRY(comm_allgather_bytes(c, g->stream, &mine, all.data(), sizeof(WinHello)));
     int ok = mine.ok;
     for (int r = 0; r < W && ok; r++) ok &= all[r].ok;
+    for (int r = 0; r < W && ok; r++)
+        for (int q = 0; q < r; q++) if (!strncmp(all[r].bus, all[q].bus, sizeof mine.bus)) ok = 0;   // two ranks on one GPU
     for (int r = 0; r < W && ok; r++) {
         if (r == me) { for (int j = 0; j < 3; j++) c->win_peer[r][j] = mine.raw[j]; continue; }
         if (all[r].pid == mine.pid) {   // same process (mrc_comm_init): plain peer access
@@ -369,7 +374,7 @@ static int run_probe_dist(mrc_comm *c, mrc_graph *g, double lam, double slack, P
     pa.r.src += e_lo; pa.r.dst += e_lo; pa.r.cost += e_lo; pa.r.time += e_lo; pa.r.m = e_hi - e_lo;
     pa.r.dist = c->win_dist; pa.r.pred = c->win_pred;
     pa.c.dist = c->win_dist; pa.c.pred = c->win_pred;
-    pa.dG = g->dprobe_group > 0 ? g->dprobe_group : std::max(1, W / 2);
+    pa.dG = g->dprobe_group > 0 ? g->dprobe_group : std::max(2, W / 2);   // an exchange costs ~16 us, a sweep of the slice 26 / 13 / 7 us at 2 / 4 / 8 ranks
     pa.dW = W; pa.dme = me; pa.e_base = (unsigned)e_lo; pa.v_lo = g->slice_v[0]; pa.v_hi = g->slice_v[1];
     int np = 0;
     for (int r = 0; r < W; r++) {
@@ -381,20 +386,28 @@ static int run_probe_dist(mrc_comm *c, mrc_graph *g, double lam, double slack, P
     }
     pa.pp.n_peers = np;
     pa.mbox = c->win_mbox;
-    pa.check_growth = 100;   // checks after 2, 6, 12, 24, ... sweeps: a check costs a gather of pred over NVLink on top of the pointer doubling
+    // A check costs a gather of pred over NVLink on top of the pointer doubling (~85 us) while a group of sweeps of the slices costs
+    // 50 us at 8 ranks: first check after two groups, then at doubling distances (8, 16, 32, ... sweeps at 8 ranks; 2, 6, 12, ... at 2)
+    pa.first_check = std::max(g->burst_init, 2 * (g->dprobe_group > 0 ? g->dprobe_group : std::max(2, W / 2)));
+    pa.check_growth = 100;
     pa.seq0 = c->xseq;
     c->xseq += 1ull << 32;
     if (const char *env = getenv("MRC_B200_DPROBE_MAXPASS")) pa.max_passes = std::max(8, atoi(env));   // debugging aid
     MRC_TRY(probe_launch_collect(g, pr, pa, res));
     if (getenv("MRC_B200_TRACE")) {
-        std::vector<double> h((size_t)g->n);
-        CUDA_TRY(cudaMemcpy(h.data(), c->win_dist, (size_t)g->n * 8, cudaMemcpyDeviceToHost));
         double mn = 0; ll deep = 0;
-        for (double x : h) { mn = std::min(mn, x); deep += x < -1e4; }
+        if (atoi(getenv("MRC_B200_TRACE")) >= 2) {   // (a 8 MB copy per probe: distorts the timeline)
+            std::vector<double> h((size_t)g->n);
+            CUDA_TRY(cudaMemcpy(h.data(), c->win_dist, (size_t)g->n * 8, cudaMemcpyDeviceToHost));
+            for (double x : h) { mn = std::min(mn, x); deep += x < -1e4; }
+        }
         const ProbeDev &o = *g->h_probe;
-        fprintf(stderr, "    rank %d: slice e[%lld,%lld) v[%lld,%lld) G %d sweeps %u checks %u cuts %u verdict %d passes %lld min dist %.6g (%lld below -1e4) sweep %.1f us/step\n",
+        fprintf(stderr, "    rank %d: slice e[%lld,%lld) v[%lld,%lld) G %d sweeps %u checks %u cuts %u verdict %d passes %lld min dist %.6g (%lld below -1e4) "
+                        "sweep %.1f us/step; kernel %.3f ms = sweeps %.3f + checks %.3f + other %.3f (exchanges, waits)\n",
                 me, (long long)e_lo, (long long)e_hi, (long long)pa.v_lo, (long long)pa.v_hi, pa.dG, o.n_sweep[0], o.n_check, o.cuts, res[0].verdict,
-                (long long)res[0].passes, mn, (long long)deep, o.n_sweep[0] ? 1e-3 * (double)o.ns_sweep[0] / ((double)o.n_sweep[0] / pa.dG) : 0.0);
+                (long long)res[0].passes, mn, (long long)deep, o.n_sweep[0] ? 1e-3 * (double)o.ns_sweep[0] / ((double)o.n_sweep[0] / pa.dG) : 0.0,
+                1e-6 * (double)o.ns_total, 1e-6 * (double)o.ns_sweep[0], 1e-6 * (double)o.ns_check,
+                1e-6 * ((double)o.ns_total - (double)o.ns_sweep[0] - (double)o.ns_check));
     }
     if (res[0].verdict < 0) return set_err(MRC_ERR_COMM, "distributed probe: a peer did not answer (rank %d of %d)", me, W);
     return MRC_OK;
@@ -610,7 +623,9 @@ static int shard_solve_rank(mrc_comm *c, mrc_graph *g, double lo, double hi, int
         if (hi - lo <= tol) { out->converged = true; break; }   // solver.py:1075-1076, on the tick every rank sees it
         // ... not before the second tick: the candidates next to lambda* close their cycle a few sweeps after the far ones, and
         // starting the Newton chain from a far cycle costs two or three extra probes (measured on 2 GPUs: 2.8 -> 3.4 ms)
-        if (have_cycle && W > 1 && c->win_ok && g->dprobe && ticks >= 2) {   // same records, same fold: every rank leaves the tick loop on this tick
+        // With 16 or more candidates on the quantile ladder the ones just above lambda* sit within a few per cent of it: their
+        // cycle is almost always the optimal one, and if it is not a distributed Newton step costs less than a tick.
+        if (have_cycle && W > 1 && c->win_ok && g->dprobe && ticks >= (KT_all >= 16 ? 1 : 2)) {   // same records, same fold: every rank leaves the tick loop on this tick
             if (running) { for (int k = 0; k < pr.K; k++) pr.drop(k, MRC_V_ABANDONED); pr.finish(); running = false; }
             go_dist = true;
             break;
@@ -697,22 +712,39 @@ static int shard_solve_rank(mrc_comm *c, mrc_graph *g, double lo, double hi, int
         msg[2] = (double)verts.size();
     }
     if (W > 1) {
-        CUDA_TRY(cudaMemcpyAsync(c->d_send, msg, 24, cudaMemcpyHostToDevice, g->stream));
-        NCCL_TRY(api, api->Broadcast(c->d_send, c->d_send, 3, ncclDouble, best_owner, c->comm, g->stream));
-        CUDA_TRY(cudaMemcpyAsync(msg, c->d_send, 24, cudaMemcpyDeviceToHost, g->stream));
-        CUDA_TRY(cudaStreamSynchronize(g->stream));
-        const size_t L = (size_t)msg[2];
-        if (c->cyc_cap < L) {
+        // ONE broadcast carries the sums, the length and (up to HEAD vertices of) the cycle; longer cycles need a second one
+        const size_t HEAD = 2048, head_ints = 6 + HEAD;   // 3 doubles = 6 ints
+        if (c->cyc_cap < head_ints) {
             if (c->d_cyc) CUDA_TRY(cudaFree(c->d_cyc));
-            c->cyc_cap = std::max<size_t>(L, 1024);
+            c->cyc_cap = head_ints;
             CUDA_TRY(cudaMalloc((void **)&c->d_cyc, c->cyc_cap * 4));
         }
-        if (me == best_owner) CUDA_TRY(cudaMemcpyAsync(c->d_cyc, verts.data(), L * 4, cudaMemcpyHostToDevice, g->stream));
-        NCCL_TRY(api, api->Broadcast(c->d_cyc, c->d_cyc, L, ncclInt, best_owner, c->comm, g->stream));
-        verts.resize(L);
-        CUDA_TRY(cudaMemcpyAsync(verts.data(), c->d_cyc, L * 4, cudaMemcpyDeviceToHost, g->stream));
+        std::vector<int> pack(head_ints, 0);
+        if (me == best_owner) {
+            memcpy(pack.data(), msg, 24);
+            memcpy(pack.data() + 6, verts.data(), std::min(verts.size(), HEAD) * 4);
+            CUDA_TRY(cudaMemcpyAsync(c->d_cyc, pack.data(), head_ints * 4, cudaMemcpyHostToDevice, g->stream));
+        }
+        NCCL_TRY(api, api->Broadcast(c->d_cyc, c->d_cyc, head_ints, ncclInt, best_owner, c->comm, g->stream));
+        if (me != best_owner) CUDA_TRY(cudaMemcpyAsync(pack.data(), c->d_cyc, head_ints * 4, cudaMemcpyDeviceToHost, g->stream));
         CUDA_TRY(cudaStreamSynchronize(g->stream));
+        if (me != best_owner) memcpy(msg, pack.data(), 24);
+        const size_t L = (size_t)msg[2];
+        if (me != best_owner) verts.assign(pack.begin() + 6, pack.begin() + 6 + std::min(L, HEAD));
+        if (L > HEAD) {
+            if (c->cyc_cap < L) {
+                CUDA_TRY(cudaFree(c->d_cyc));
+                c->cyc_cap = L;
+                CUDA_TRY(cudaMalloc((void **)&c->d_cyc, c->cyc_cap * 4));
+            }
+            if (me == best_owner) CUDA_TRY(cudaMemcpyAsync(c->d_cyc, verts.data(), L * 4, cudaMemcpyHostToDevice, g->stream));
+            NCCL_TRY(api, api->Broadcast(c->d_cyc, c->d_cyc, L, ncclInt, best_owner, c->comm, g->stream));
+            verts.resize(L);
+            CUDA_TRY(cudaMemcpyAsync(verts.data(), c->d_cyc, L * 4, cudaMemcpyDeviceToHost, g->stream));
+            CUDA_TRY(cudaStreamSynchronize(g->stream));
+        }
     }
+    if (trace && me == 0) fprintf(stderr, "  cycle handed over t=%.3f ms\n", 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     out->cycle = verts; out->sc = msg[0]; out->st = msg[1]; out->have_best = true;
     return MRC_OK;
 }
