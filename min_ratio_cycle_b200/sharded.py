@@ -147,6 +147,26 @@ def sensitivity_analysis_sharded(solver, edge_perturbations, group=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     mine = shard_units(len(edge_perturbations), rank, world)
     local = solver.sensitivity_analysis([edge_perturbations[i] for i in mine]) if len(mine) else []
+    # Almost every scenario keeps the unperturbed optimal cycle: those travel as (sum_cost, sum_time) pairs in one array and
+    # are rebuilt on arrival; only the few results with another cycle (or a failure) travel as objects.  Pickling 1,024
+    # SolverResult objects with their configs cost more than the re-solves themselves.
+    base = solver._last_result
+    base_cycle = list(base.cycle) if base is not None and base.success else None
+    plain = [r.success and base_cycle is not None and r.cycle == base_cycle and r.metrics is not None and r.metrics.iterations == 1
+             for r in local]
+    sums = np.array([[r.sum_cost, r.sum_time] if p else [np.nan, np.nan] for r, p in zip(local, plain)], dtype=np.float64).reshape(-1, 2)
+    rest = {i: r for i, (r, p) in enumerate(zip(local, plain)) if not p}
     gathered = [None] * world
-    dist.all_gather_object(gathered, local, group=group)
-    return [r for part in gathered for r in part]
+    dist.all_gather_object(gathered, (sums.tobytes(), rest), group=group)
+    from .solver import SolverMetrics, SolverResult
+    out = []
+    for blob, others in gathered:
+        part = np.frombuffer(blob, dtype=np.float64).reshape(-1, 2)
+        for i in range(len(part)):
+            if i in others:
+                out.append(others[i])
+            else:
+                sc, st = float(part[i, 0]), float(part[i, 1])
+                out.append(SolverResult(cycle=list(base_cycle), sum_cost=sc, sum_time=st, ratio=sc / st, success=True,
+                                        metrics=SolverMetrics(iterations=1, mode_used="numeric"), config_used=solver.config))
+    return out

@@ -289,6 +289,17 @@ class MinRatioCycleSolver:
     def _num_edges(self) -> int:
         return len(self._edges) + sum(len(b[0]) for b in self._bulk)
 
+    def _inv_order(self) -> np.ndarray:
+        """insertion index -> position in the destination-sorted arrays (the inverse of _order), kept until _order changes:
+        at m = 2 M the scatter costs 30 ms, more than 1,024 perturbation re-solves on the device."""
+        order = self._order
+        cached = getattr(self, "_inv_order_cache", None)
+        if cached is None or cached[0] is not order:
+            inv = np.empty(len(order), dtype=np.int64)
+            inv[order] = np.arange(len(order))
+            self._inv_order_cache = cached = (order, inv)
+        return cached[1]
+
     def _close_multi(self) -> None:
         if self._mg is not None:
             self._mg.close()
@@ -922,19 +933,31 @@ class MinRatioCycleSolver:
             if ok:
                 warm = list(self._last_result.cycle)
         m = self._num_edges()
-        inv = np.empty(m, dtype=np.int64)
-        inv[self._order] = np.arange(m)
+        inv = self._inv_order()
         scen_arrays = []
-        for scenario in edge_perturbations:
-            for idx in scenario:
-                if idx < 0 or idx >= m:
-                    raise IndexError("edge index out of range")
-            pos = inv[np.fromiter(scenario.keys(), dtype=np.int64, count=len(scenario))]
-            dc = np.array([float(d[0]) for d in scenario.values()], dtype=np.float64)
-            dt = np.array([float(d[1]) for d in scenario.values()], dtype=np.float64)
-            if np.any(self._T[pos] + dt <= 0):
+        S = len(edge_perturbations)
+        single = None   # (pos, dc, dt) arrays when every scenario touches exactly one edge (the sweep of BASELINE config 5)
+        if S and all(len(sc) == 1 for sc in edge_perturbations):
+            keys = np.fromiter((next(iter(sc)) for sc in edge_perturbations), dtype=np.int64, count=S)
+            vals = np.array([next(iter(sc.values())) for sc in edge_perturbations], dtype=np.float64).reshape(S, 2)
+            if np.any(keys < 0) or np.any(keys >= m):
+                raise IndexError("edge index out of range")
+            pos_all = inv[keys]
+            if np.any(self._T[pos_all] + vals[:, 1] <= 0):
                 raise ValueError("Edge transit time must be strictly positive")
-            scen_arrays.append((pos, dc, dt))
+            single = (pos_all, np.ascontiguousarray(vals[:, 0]), np.ascontiguousarray(vals[:, 1]))
+            scen_arrays = [(pos_all[i:i + 1], single[1][i:i + 1], single[2][i:i + 1]) for i in range(S)]
+        else:
+            for scenario in edge_perturbations:
+                for idx in scenario:
+                    if idx < 0 or idx >= m:
+                        raise IndexError("edge index out of range")
+                pos = inv[np.fromiter(scenario.keys(), dtype=np.int64, count=len(scenario))]
+                dc = np.array([float(d[0]) for d in scenario.values()], dtype=np.float64)
+                dt = np.array([float(d[1]) for d in scenario.values()], dtype=np.float64)
+                if np.any(self._T[pos] + dt <= 0):
+                    raise ValueError("Edge transit time must be strictly positive")
+                scen_arrays.append((pos, dc, dt))
         results: list[SolverResult | None] = [None] * len(scen_arrays)
         tol, slack = self.config.numeric_tolerance, self.config.numeric_cycle_slack
 
@@ -943,11 +966,15 @@ class MinRatioCycleSolver:
         # means that cycle is still optimal to within tol -- the answer the sequential path below would give.  Scenarios
         # whose optimum moves (or that touch several edges) fall through to it.
         if warm is not None:
-            singles = np.array([i for i, sa in enumerate(scen_arrays) if len(sa[0]) == 1], dtype=np.int64)
+            singles = np.arange(S, dtype=np.int64) if single is not None else \
+                np.array([i for i, sa in enumerate(scen_arrays) if len(sa[0]) == 1], dtype=np.int64)
             if len(singles):
-                keep = self._certify_single_edge_scenarios(warm, np.array([scen_arrays[i][0][0] for i in singles]),
-                                                           np.array([scen_arrays[i][1][0] for i in singles]),
-                                                           np.array([scen_arrays[i][2][0] for i in singles]), tol, slack)
+                if single is not None:
+                    keep = self._certify_single_edge_scenarios(warm, single[0], single[1], single[2], tol, slack)
+                else:
+                    keep = self._certify_single_edge_scenarios(warm, np.array([scen_arrays[i][0][0] for i in singles]),
+                                                               np.array([scen_arrays[i][1][0] for i in singles]),
+                                                               np.array([scen_arrays[i][2][0] for i in singles]), tol, slack)
                 for i, k in zip(singles, keep):
                     if k is not None:
                         results[i] = SolverResult(cycle=list(warm), sum_cost=k[0], sum_time=k[1], ratio=k[0] / k[1], success=True,
@@ -986,8 +1013,7 @@ class MinRatioCycleSolver:
             res = self.sensitivity_analysis([{idx: (float(self._C[p]) * epsilon, float(self._T[p]) * epsilon)}
                                              for idx, p in enumerate(np.argsort(self._order))])
             return {idx: res[idx].cycle == base.cycle for idx in range(m)}
-        inv = np.empty(m, dtype=np.int64)
-        inv[self._order] = np.arange(m)                      # insertion index -> sorted position
+        inv = self._inv_order()                              # insertion index -> sorted position
         keep = self._certify_single_edge_scenarios(list(base.cycle), inv, self._C[inv] * epsilon, self._T[inv] * epsilon,
                                                    self.config.numeric_tolerance, self.config.numeric_cycle_slack)
         out = {}

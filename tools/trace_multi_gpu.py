@@ -1,3 +1,5 @@
+"""Timeline of ONE multi-GPU solve (single process, one host thread per device): W=<ranks> KLOCAL=<candidates per rank> python tools/trace_multi_gpu.py
+prints the ticks of the first round, every distributed probe with its device-time breakdown per rank, and the cycle hand-over (MRC_B200_TRACE=1)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
