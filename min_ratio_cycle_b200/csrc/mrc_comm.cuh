@@ -392,7 +392,6 @@ static int run_probe_dist(mrc_comm *c, mrc_graph *g, double lam, double slack, P
     pa.check_growth = 100;
     pa.seq0 = c->xseq;
     c->xseq += 1ull << 32;
-    if (const char *env = getenv("MRC_B200_DPROBE_MAXPASS")) pa.max_passes = std::max(8, atoi(env));   // debugging aid
     MRC_TRY(probe_launch_collect(g, pr, pa, res));
     if (getenv("MRC_B200_TRACE")) {
         double mn = 0; ll deep = 0;

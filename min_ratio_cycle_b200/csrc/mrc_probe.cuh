@@ -142,8 +142,7 @@ __device__ __forceinline__ ull mrc_lap(ProbeClock *c) {
     return d;
 }
 
-// The cold parts of the probe are separate functions (own register allocation): what is inlined into the kernel body is
-// the sweeps alone, with their operands in the constant bank like the stand-alone relax_kernel.
+// Every part of the probe is a separate function with its own register allocation; the kernel body is the loop that calls them.
 
 // ---- start: dist = 0 (or the warm potentials), pred = none, bitmaps clean, status words zero
 template <int KT>
@@ -168,6 +167,7 @@ __device__ __noinline__ void probe_start(ProbeCtl *s, ProbeClock *clk) {
         st->decided = 0u;
         st->act_count = 0u;
         st->act_cnt[0] = st->act_cnt[1] = st->act_cnt[2] = 0u;
+        for (int i = 0; i < 4; i++) st->xword[i] = 0ull;   // (a graph may serve several communicators, whose step numbers repeat)
         ProbeDev &acc = clk->acc;
         for (int i = 0; i < MRC_PW; i++) { acc.ns_sweep[i] = 0; acc.n_sweep[i] = 0; }
         acc.ns_crowded = acc.ns_sparse = acc.ns_check = acc.ns_other = 0;
