@@ -214,6 +214,11 @@ int mrc_bench_relax(mrc_graph *g, const double *lam, int K, int passes, float *m
  * devices, may be used from different threads). */
 int mrc_set_option(mrc_graph *g, const char *name, int value);
 
+/* Quantile levels of the FIRST round of a search that holds no cycle (csrc/mrc_b200.cu, plan_first_round): K increasing levels
+ * in (0, 1); candidate j is the q[j]-quantile of a sample of cost/time over the edges instead of a uniform point of
+ * [min c/t - 1, max c/t + 1] (solver.py:1019-1023, :1053).  Exposed so that a caller (or a test) can see where a round will look. */
+int mrc_first_round_levels(int K, double *q);
+
 /* Pure host helpers shared by mrc_solve_numeric and the multi-GPU driver (one process per GPU, the
  * candidates of a round split across ranks, verdicts all-gathered): no device work.
  * plan: writes K_total candidates in increasing order for the bracket [lo, hi]; have_cycle says whether

@@ -37,7 +37,7 @@ EXPORTS = [
     "mrc_comm_unique_id", "mrc_comm_init_rank", "mrc_comm_init", "mrc_comm_destroy", "mrc_comm_info",
     "mrc_graph_create_replicated", "mrc_solve_numeric_sharded", "mrc_mgraph_create", "mrc_mgraph_destroy", "mrc_mgraph_graph",
     "mrc_mgraph_solve_numeric", "mrc_shard_fold", "mrc_scenarios_certify",
-    "mrc_graph_build", "mrc_graph_fetch_arrays", "mrc_cycle_weights",
+    "mrc_graph_build", "mrc_graph_fetch_arrays", "mrc_cycle_weights", "mrc_first_round_levels",
 ]
 
 
@@ -129,6 +129,7 @@ def lib():
     L.mrc_graph_build.argtypes = [C.c_int64, C.c_int64, vp, vp, C.c_int, pd, pd, C.c_int, C.c_int, C.POINTER(vp), p64, p64, p64]
     L.mrc_graph_fetch_arrays.argtypes = [vp, p32, p32, pd, pd, p32, pu8]
     L.mrc_cycle_weights.argtypes = [vp, C.c_int64, p32, pd, pd, p32, p32]
+    L.mrc_first_round_levels.argtypes = [C.c_int, pd]
     L.mrc_scenarios_certify.argtypes = [vp, C.c_int64, p64, pd, pd, pd, C.c_double, C.c_double, C.c_int, p32, p64]
     for name in EXPORTS:
         if name == "mrc_mgraph_graph":
@@ -573,6 +574,13 @@ def shard_fold(rec, lo: float, hi: float, have_cycle: bool):
     check(lib().mrc_shard_fold(len(rec), _ptr(rec, C.c_double), C.byref(clo), C.byref(chi), C.byref(hc), C.byref(best),
                                _ptr(imp, C.c_uint8)))
     return clo.value, chi.value, bool(hc.value), best.value, imp.astype(bool)
+
+
+def first_round_levels(K: int) -> np.ndarray:
+    """Quantile levels of the first round of a search without a known cycle (mrc_first_round_levels)."""
+    q = np.zeros(int(K), np.float64)
+    check(lib().mrc_first_round_levels(int(K), _ptr(q, C.c_double)))
+    return q
 
 
 def plan_candidates(lo: float, hi: float, have_cycle: bool, tol: float, K_total: int) -> np.ndarray:

@@ -1605,6 +1605,11 @@ static void first_round_levels(int K, double *q) {
     const double q_lo = K == 2 ? 0.02 : K <= 4 ? 0.01 : K <= 8 ? 0.005 : 0.002, q_hi = K == 2 ? 0.10 : K <= 4 ? 0.25 : 0.5;
     for (int j = 0; j < K; j++) q[j] = q_lo * std::pow(q_hi / q_lo, (double)j / (double)(K - 1));
 }
+extern "C" int mrc_first_round_levels(int K, double *q) {
+    if (K < 1 || K > 4096 || !q) return set_err(MRC_ERR_ARG, "bad arguments");
+    first_round_levels(K, q);
+    return MRC_OK;
+}
 // K candidates for the first round of a search over (lo, hi) without a known cycle; false = use the uniform plan
 static bool plan_first_round(mrc_graph *g, double lo, double hi, int K, double *lam) {
     if (!g->qstart || g->m < g->qstart_min_edges || K < 1) return false;

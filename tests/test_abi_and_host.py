@@ -188,3 +188,17 @@ def test_dimacs_loader_and_regression_helpers(tmp_path):
     assert B.regression_check([0.011, 0.0105, 0.012], 1.0, base) == {"performance": False, "quality": False}
     assert B.regression_check([0.5, 0.6, 0.55], 1.0 + 1e-6, base) == {"performance": True, "quality": True}
     assert B.regression_check([0.5], 1.0, base)["performance"] is True          # < 2 samples: 1.5x mean rule
+
+
+def test_first_round_levels_are_a_low_quantile_ladder():
+    """plan_first_round (csrc/mrc_b200.cu): the first round of a search without a known cycle looks at low quantiles of the
+    edge-ratio sample -- increasing, inside (0, 1), denser towards the low tail; one candidate sits at 5 %."""
+    from min_ratio_cycle_b200 import _native as N
+    assert N.first_round_levels(1)[0] == pytest.approx(0.05)
+    for K in (2, 3, 4, 8, 16, 32, 64):
+        q = N.first_round_levels(K)
+        assert len(q) == K and np.all(np.diff(q) > 0) and q[0] > 0 and q[-1] <= 0.5 + 1e-12
+        assert np.allclose(q[1:] / q[:-1], q[1] / q[0])          # geometric
+    assert N.first_round_levels(4)[0] == pytest.approx(0.01) and N.first_round_levels(4)[-1] == pytest.approx(0.25)
+    with pytest.raises(N.NativeError):
+        N.first_round_levels(0)
