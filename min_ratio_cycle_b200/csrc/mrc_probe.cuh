@@ -469,22 +469,14 @@ __device__ __noinline__ void probe_finish(const ProbeCtl *s, const ProbeClock *c
 }
 
 // ---- the hot parts: one function per sweep width
-#ifndef MRC_PROBE_FULL_INLINE
-#define MRC_PROBE_FULL_INLINE 0
-#endif
 #ifndef MRC_PROBE_PF
-#define MRC_PROBE_PF 2
+#define MRC_PROBE_PF 2         /* prefetch mode of the probe's sweeps (relax_sweep): 2 = prefetch.global.L2 one chunk ahead, no register double buffer */
 #endif
 #ifndef MRC_PROBE_MINBLOCKS
-#define MRC_PROBE_MINBLOCKS 4
-#endif
-#if MRC_PROBE_FULL_INLINE
-#define MRC_PROBE_FULL_ATTR __forceinline__
-#else
-#define MRC_PROBE_FULL_ATTR __noinline__
+#define MRC_PROBE_MINBLOCKS 4  /* CTAs per SM the probe kernel is compiled for (3 was measured: slower, profiles/r02_persist.txt) */
 #endif
 template <int KT, bool EXACT>
-__device__ MRC_PROBE_FULL_ATTR void probe_sweep_full(unsigned active, unsigned *chw, unsigned *act_out) {
+__device__ __noinline__ void probe_sweep_full(unsigned active, unsigned *chw, unsigned *act_out) {
     relax_sweep<KT, EXACT, false, ParamView, MRC_PROBE_PF>(c_probe.r, ParamView{c_probe.r}, active, chw, act_out);
 }
 template <int W, int KT, bool EXACT>
