@@ -200,6 +200,28 @@ static int device_info(int device, const DeviceInfo **out) {
     return MRC_OK;
 }
 
+// Pinned host blocks for the status / result read-backs of a graph handle ([DevStatus][ProbeDev]).  cudaMallocHost and
+// cudaFreeHost cost 0.1-0.2 ms each; callers that create a handle per solve (bench.py's e2e leg, the facade) get a block
+// back from this small process-wide cache instead.
+static std::mutex g_pin_mu;
+static std::vector<void *> g_pin_free;
+static constexpr size_t kPinBytes = ((sizeof(DevStatus) + 255) & ~(size_t)255) + sizeof(ProbeDev);
+static int pin_get(void **out) {
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mu);
+        if (!g_pin_free.empty()) { *out = g_pin_free.back(); g_pin_free.pop_back(); return MRC_OK; }
+    }
+    CUDA_TRY(cudaMallocHost(out, kPinBytes));
+    return MRC_OK;
+}
+static void pin_put(void *p) {
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mu);
+        if (g_pin_free.size() < 16) { g_pin_free.push_back(p); return; }
+    }
+    cudaFreeHost(p);
+}
+
 extern "C" int mrc_graph_destroy(mrc_graph *g) {
     if (!g) return MRC_OK;
     cudaSetDevice(g->device);
@@ -212,8 +234,7 @@ extern "C" int mrc_graph_destroy(mrc_graph *g) {
         for (void *q : ptrs) if (q) cudaFreeAsync(q, g->stream);
         cudaStreamSynchronize(g->stream);
     }
-    if (g->h_status) cudaFreeHost(g->h_status);
-    if (g->h_probe) cudaFreeHost(g->h_probe);
+    if (g->h_status) pin_put(g->h_status);   // (h_probe lives in the same block)
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
@@ -282,9 +303,13 @@ static int graph_new(int64_t n, int64_t m, int device, bool with_int, mrc_graph 
         DALLOC(g->d_cyc_edges, (size_t)g->cyc_cap * MRC_KMAX * 4);
         DALLOC(g->d_status, sizeof(DevStatus));
         CUDA_TRY(cudaMemsetAsync(g->d_status, 0, sizeof(DevStatus), g->stream));
-        CUDA_TRY(cudaMallocHost(&g->h_status, sizeof(DevStatus)));
+        {
+            void *blk = nullptr;
+            MRC_TRY(pin_get(&blk));
+            g->h_status = (DevStatus *)blk;
+            g->h_probe = (ProbeDev *)((char *)blk + ((sizeof(DevStatus) + 255) & ~(size_t)255));
+        }
         DALLOC(g->d_probe, sizeof(ProbeDev));
-        CUDA_TRY(cudaMallocHost(&g->h_probe, sizeof(ProbeDev)));
         DALLOC(g->d_keys, 16);
         DALLOC(g->d_verr, 4);
         MRC_TRY(graph_geometry(g, di));
